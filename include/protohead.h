@@ -1,0 +1,149 @@
+/*
+ * protohead.h -- C ABI of libprotohead_b200.so: ProtoPFormer's prototype head on B200 (sm_100a).
+ *
+ * The reference (zju-vipa/ProtoPFormer) has no FFI for this path: it is a Python nn.Module whose arithmetic is
+ * ~35 ATen library calls (protopformer.py:141-335).  This library is what a maintainer binds instead of those
+ * calls (ctypes stub in INTEGRATION.md; the shipped binding is protopformer_b200/_lib.py).  Each entry point
+ * cites the reference lines it replaces.
+ *
+ * Conventions (all entry points):
+ *   - extern "C", plain pointers and ints; every pointer is a DEVICE pointer owned and pre-allocated by the
+ *     caller unless the parameter comment says "host".
+ *   - `stream` is a cudaStream_t passed as void*.  Nothing allocates, nothing synchronises, no global state
+ *     except a per-thread last-error string -> every call is CUDA-graph capturable.
+ *   - return 0 on success, a negative PPH_E* argument error, or a positive cudaError_t from the launch.
+ *     pph_last_error_string() describes the last non-zero return on the calling thread.
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point returns a cudaError_t.
+ *   - float tensors are fp32 row-major contiguous; "bf16" is the 16-bit brain float (uint16_t storage).
+ *
+ * Symbols (B images, N patch tokens, K reserved tokens, Din backbone width, D prototype dim, P local
+ * prototypes, Pg global prototypes, C classes, m = P / C prototypes per class):
+ */
+#ifndef PROTOHEAD_B200_H
+#define PROTOHEAD_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PPH_VERSION 100
+
+/* argument errors */
+#define PPH_EINVAL   (-1)   /* bad dimension / null pointer */
+#define PPH_EUNSUP   (-2)   /* shape outside what the sm_100a kernels were built for */
+#define PPH_EDRIVER  (-3)   /* cuTensorMapEncodeTiled unavailable / failed */
+
+/* similarity precision modes (pph_similarity_fwd `mode`) */
+#define PPH_MODE_FP32_FMA 0  /* CUDA-core FP32 FMA contraction (exact-order reference mode, materialises maps) */
+#define PPH_MODE_BF16X3   1  /* tcgen05 bf16 tensor cores, 3-term split operands (hi*hi + hi*lo + lo*hi), fp32-grade */
+#define PPH_MODE_BF16     2  /* tcgen05 bf16 tensor cores, single pass */
+
+/* prototype activation function, protopformer.py:228-234 */
+#define PPH_ACT_LOG    0     /* log((d+1)/(d+eps)) */
+#define PPH_ACT_LINEAR 1     /* -d */
+
+typedef void* pph_stream_t;  /* cudaStream_t */
+
+int         pph_version(void);
+const char* pph_last_error_string(void);
+/* number of SMs of the current device (persistent-grid sizing), or <0 */
+int         pph_sm_count(void);
+
+/* (a1) protopformer.py:157-158  topk(cls_token_attn, K)[1].sort()[0]
+ * scores [B,H,N] (H>=1; H>1: the mean over H is taken first), idx32 [B,K] ascending, idx64 [B,K] or NULL.
+ * N <= 1024, 1 <= K <= N.  Ties: the lower token index wins. */
+int pph_select_topk(const float* scores, int B, int H, int N, int K,
+                    int32_t* idx32, int64_t* idx64, pph_stream_t stream);
+
+/* (a2) protopformer.py:159-172 + ctor :109-113  gather -> 1x1 conv ('regular' add-on) -> sigmoid, for the K
+ * selected patch tokens and the CLS token of every image.
+ * tokens [B,1+N,Din], idx32 [B,K], Wa [D,Din], ba [D] ->
+ *   Zs [B,K,D] fp32, Zc [B,D] fp32, z2s [B,K] = |Zs|^2, z2c [B] = |Zc|^2,
+ *   Zs_hi/Zs_lo [B*K,D] bf16 split (hi = rn(z), lo = rn(z - hi)), Zc_hi/Zc_lo [B,D],
+ *   z2s_hi [B,K] / z2c_hi [B] = |hi|^2, the norms of the ROUNDED operand (what PPH_MODE_BF16 must be given as
+ *   z2s/z2c so that the distance of the rounded vectors stays consistent).  The six bf16-side outputs may be NULL. */
+int pph_addon_fwd(const float* tokens, const int32_t* idx32, const float* Wa, const float* ba,
+                  int B, int N, int Din, int D, int K,
+                  float* Zs, float* Zc, float* z2s, float* z2c, float* z2s_hi, float* z2c_hi,
+                  uint16_t* Zs_hi, uint16_t* Zs_lo, uint16_t* Zc_hi, uint16_t* Zc_lo, pph_stream_t stream);
+
+/* operand preparation for the tensor-core modes: V [R,D] fp32 -> hi/lo bf16 split [R,D], v2 [R] = |V|^2
+ * (the p2 term of protopformer.py:207-208), v2_hi [R] = |hi|^2.  Any output may be NULL. */
+int pph_split_rows(const float* V, int R, int D, uint16_t* hi, uint16_t* lo, float* v2, float* v2_hi,
+                   pph_stream_t stream);
+
+/* (a3,a4,a5) protopformer.py:201-218, 228-234, 236-247  squared-L2 distances of every selected token to every
+ * local prototype (and of the CLS token to every global prototype), log/linear similarity, max over tokens.
+ * Local:  dmin_l [B,P] = min_k relu(z2 - 2 z.p + p2), argmin_l [B,P] (token slot 0..K-1, lowest on ties),
+ *         act_l [B,P] = act(dmin_l).      Global: dmin_g [B,Pg], act_g [B,Pg].
+ * mode FP32_FMA reads Zs/Zc/Pl/Pg (fp32) and can also write the materialised maps dist_map / act_map [B,P,K]
+ * (protopformer.py:301 aux `distances`, :344 `proto_acts`); the tcgen05 modes read the bf16 operands (lo
+ * pointers unused in PPH_MODE_BF16, which wants z2s/z2c/p2l/p2g = norms of the rounded operands), never write
+ * the maps (dist_map/act_map must be NULL) and require D % 64 == 0, 64 <= D <= 512, 1 <= K <= 256. */
+int pph_similarity_fwd(int mode, int act_fn, float eps, int B, int K, int D, int P, int Pg,
+                       const float* Zs, const float* Zc, const float* z2s, const float* z2c,
+                       const uint16_t* Zs_hi, const uint16_t* Zs_lo, const uint16_t* Zc_hi, const uint16_t* Zc_lo,
+                       const float* Pl, const float* Pgl, const float* p2l, const float* p2g,
+                       const uint16_t* Pl_hi, const uint16_t* Pl_lo, const uint16_t* Pg_hi, const uint16_t* Pg_lo,
+                       float* dmin_l, int32_t* argmin_l, float* act_l, float* dmin_g, float* act_g,
+                       float* dist_map, float* act_map, pph_stream_t stream);
+
+/* (a6) protopformer.py:297-300 / 314-316  logits = gc * act_g Wg^T + (1-gc) * act_l Wl^T
+ * Wl [C,P], Wg [C,Pg] -> logits, logits_g, logits_l [B,C] */
+int pph_logits_fwd(const float* act_l, const float* act_g, const float* Wl, const float* Wg,
+                   int B, int P, int Pg, int C, float global_coe,
+                   float* logits, float* logits_g, float* logits_l, pph_stream_t stream);
+
+/* (a7) protopformer.py:249-288  PPC loss.  For image b and its label y the m prototypes y*m..y*m+m-1:
+ * activation rows over the K selected tokens are recomputed from Zs/Pl in fp32 (the reference gathers them
+ * from the (B,P,K) map), placed on the side x side grid by idx32, -> weighted mean / variance -> the two losses.
+ * labels [B] int64.  Saved for backward: dslice [B,m,K] (distances), stats [B,m,8] = S, mu_r, mu_c, V_r, V_c, pre_cov, 0, 0.
+ * losses [2] = (ppc_cov_loss, ppc_mean_loss); partial [B,2] and counter [1] (uint32, zero before first use,
+ * self-resetting) are scratch for the deterministic final sum. */
+int pph_ppc_fwd(const float* Zs, const float* z2s, const float* Pl, const float* p2l,
+                const int32_t* idx32, const int64_t* labels,
+                int B, int K, int D, int P, int m, int N, int act_fn, float eps,
+                float cov_thresh, float mean_thresh,
+                float* dslice, float* stats, float* partial, uint32_t* counter, float* losses, pph_stream_t stream);
+
+/* backward of pph_ppc_fwd.  g_losses [2] = upstream gradients of (cov, mean) (device).
+ * dZs [B,K,D] is OVERWRITTEN with the PPC contribution; dP [P,D] must be zero-filled by the caller and is
+ * accumulated with atomics (several images may share a label). */
+int pph_ppc_bwd(const float* Zs, const float* Pl, const int32_t* idx32, const int64_t* labels,
+                const float* dslice, const float* stats, const float* g_losses,
+                int B, int K, int D, int P, int m, int N, int act_fn, float eps,
+                float cov_thresh, float mean_thresh,
+                float* dZs, float* dP, pph_stream_t stream);
+
+/* (a8, part 1) autograd of protopformer.py:297-300 and :228-244 collapsed to one scalar per (b,p):
+ *   g_l[b,p] = (1-gc) * (sum_c dlogits[b,c] Wl[c,p] [+ gc_extra terms]) * act'(dmin_l[b,p]) * [dmin_l > 0]
+ *   g_g[b,p] = gc * (sum_c dlogits[b,c] Wg[c,p]) * act'(dmin_g[b,p]) * [dmin_g > 0]
+ * dlogits, dlogits_g, dlogits_l [B,C] (the latter two may be NULL: no upstream gradient on logits_global/local). */
+int pph_logits_bwd(const float* dlogits, const float* dlogits_g, const float* dlogits_l,
+                   const float* Wl, const float* Wg, const float* dmin_l, const float* dmin_g,
+                   int B, int P, int Pg, int C, float global_coe, int act_fn, float eps,
+                   float* g_l, float* g_g, pph_stream_t stream);
+
+/* (a8, part 2) max-pool routing + distance backward:
+ *   dPl[p,:]   = 2 * sum_b g_l[b,p] * (Pl[p,:] - Zs[b,argmin[b,p],:])      dPg[p,:] = 2 * sum_b g_g[b,p] * (Pg[p,:] - Zc[b,:])
+ *   dZs[b,k,:] = 2 * sum_{p: argmin[b,p]=k} g_l[b,p] * (Zs[b,k,:] - Pl[p,:])   dZc[b,:] = 2 * sum_p g_g[b,p] * (Zc[b,:] - Pg[p,:])
+ * All four outputs are OVERWRITTEN. */
+int pph_similarity_bwd(const float* g_l, const float* g_g, const int32_t* argmin_l,
+                       const float* Zs, const float* Zc, const float* Pl, const float* Pgl,
+                       int B, int K, int D, int P, int Pg,
+                       float* dZs, float* dZc, float* dPl, float* dPg, pph_stream_t stream);
+
+/* (a8, part 3) backward of pph_addon_fwd: dpre = dZ * Z * (1-Z);  dWa = dpre^T X_sel;  dba = sum dpre;
+ * dtokens[b, 1+idx] = dpre Wa (CLS row 0 likewise), every other row zero.
+ * dWa [D,Din], dba [D], dtokens [B,1+N,Din] are OVERWRITTEN (dtokens may be NULL: no gradient to the backbone). */
+int pph_addon_bwd(const float* tokens, const int32_t* idx32, const float* Wa,
+                  const float* Zs, const float* Zc, const float* dZs, const float* dZc,
+                  int B, int N, int Din, int D, int K,
+                  float* dWa, float* dba, float* dtokens, pph_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PROTOHEAD_B200_H */

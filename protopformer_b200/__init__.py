@@ -1,0 +1,13 @@
+"""protopformer_b200 -- ProtoPFormer's prototype head as sm_100a CUDA kernels behind the reference's PPNet API.
+
+    from protopformer_b200 import PPNet, construct_PPNet      # drop-in for protopformer.py
+    from protopformer_b200 import ops                          # functional head: ops.head_forward / ops.ppc_loss
+
+The compute lives in lib/libprotohead_b200.so (C ABI: include/protohead.h), built by `python -m protopformer_b200.build`.
+"""
+from . import ops  # noqa: F401
+from .head import PPNet, ProtoMap, construct_PPNet, base_architecture_to_features  # noqa: F401
+from .ops import HeadConfig, head_forward, ppc_loss, select_topk  # noqa: F401
+
+__all__ = ["PPNet", "ProtoMap", "construct_PPNet", "base_architecture_to_features", "HeadConfig", "head_forward",
+           "ppc_loss", "select_topk", "ops"]

@@ -1,0 +1,80 @@
+"""ctypes binding of libprotohead_b200.so (the C ABI declared in include/protohead.h).
+
+There is no fallback of any kind: if the shared library is missing this module raises at first use, and every
+compute entry point needs a CUDA device (sm_100a).  The library is built in-tree by ``protopformer_b200.build``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libprotohead_b200.so")
+
+MODE_FP32_FMA, MODE_BF16X3, MODE_BF16 = 0, 1, 2
+MODES = {"fp32_fma": MODE_FP32_FMA, "fp32": MODE_BF16X3, "bf16x3": MODE_BF16X3, "bf16": MODE_BF16}
+ACT_LOG, ACT_LINEAR = 0, 1
+ACTS = {"log": ACT_LOG, "linear": ACT_LINEAR}
+
+_p, _i, _f = C.c_void_p, C.c_int, C.c_float
+
+# name -> argtypes (restype is always int unless listed in _RESTYPES); mirrors include/protohead.h one to one
+SIGNATURES = {
+    "pph_version": [],
+    "pph_last_error_string": [],
+    "pph_sm_count": [],
+    "pph_select_topk": [_p, _i, _i, _i, _i, _p, _p, _p],
+    "pph_addon_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "pph_split_rows": [_p, _i, _i, _p, _p, _p, _p, _p],
+    "pph_similarity_fwd": [_i, _i, _f, _i, _i, _i, _i, _i] + [_p] * 24,
+    "pph_logits_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p],
+    "pph_ppc_fwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _p, _p, _p, _p, _p, _p],
+    "pph_ppc_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _p, _p, _p],
+    "pph_logits_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _f, _p, _p, _p],
+    "pph_similarity_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p],
+    "pph_addon_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p],
+}
+_RESTYPES = {"pph_last_error_string": C.c_char_p}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library (once).  Raises if it has not been built -- never falls back to another path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -m protopformer_b200.build` "
+                "(needs nvcc; there is no CPU or PyTorch fallback for the prototype head)")
+        lib = C.CDLL(LIB_PATH)
+        for name, args in SIGNATURES.items():
+            fn = getattr(lib, name)      # AttributeError here = header / library mismatch
+            fn.argtypes = args
+            fn.restype = _RESTYPES.get(name, C.c_int)
+        _lib = lib
+    return _lib
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda, "prototype-head tensors must live on a CUDA device (no CPU path exists)"
+    assert t.is_contiguous(), "prototype-head tensors must be contiguous"
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name: str, *args):
+    """Invoke an entry point on the current CUDA stream; tensors are passed as device pointers."""
+    lib = load()
+    conv = [(_ptr(a) if (a is None or isinstance(a, torch.Tensor)) else a) for a in args]
+    rc = getattr(lib, name)(*conv, _stream())
+    if rc != 0:
+        msg = lib.pph_last_error_string()
+        raise RuntimeError(f"{name} failed (rc={rc}): {msg.decode() if msg else ''}")

@@ -1,0 +1,423 @@
+// (a3-a5) Fused normalise + similarity + max-pool kernel on the 5th-gen tensor cores (PPH_MODE_BF16X3 / PPH_MODE_BF16).
+// Replaces the two conv2d + ~10 elementwise passes + max_pool2d of protopformer.py:201-247 with ONE persistent
+// kernel; the (B,P,K) distance map lives only in TMEM and never touches HBM.
+//
+//   tile (local)  : 128 prototypes (UMMA M, TMEM lanes) x G images * K tokens (UMMA N <= 256, TMEM columns)
+//                   A = prototype rows [128 x D] bf16 K-major, B = token rows [G*K x D] bf16 K-major (Zs is [B*K, D],
+//                   so G consecutive images are one contiguous TMA box), accumulated over D in 64-wide k-blocks.
+//   tile (global) : 128 global prototypes x up to 256 images (one CLS token each).
+//   precision     : BF16X3 runs three k-passes into the same accumulator, P_lo*Z_hi + P_hi*Z_lo + P_hi*Z_hi
+//                   (small terms first), which restores ~16 mantissa bits per operand; BF16 runs P_hi*Z_hi only.
+//   epilogue      : thread = prototype (TMEM lane), walks its row with tcgen05.ld: d = z2[col] - 2*acc, running
+//                   min/argmin per image, then + p2, relu, log((d+1)/(d+eps)); writes dmin/argmin/act [B,P].
+//
+// Warp roles (384 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0 TMA producer | warp 1 MMA issuer | warp 2 TMEM allocator | warp 3 idle
+//   warps 4-7 epilogue group 0 (even tiles of this CTA) | warps 8-11 epilogue group 1 (odd tiles)
+// Pipelines: 4-stage smem ring (full/empty mbarriers, TMA complete_tx / tcgen05.commit) and a 2-stage TMEM
+// accumulator ring (2 x 256 columns; tmem_full by tcgen05.commit, tmem_empty by the epilogue warps), so the
+// epilogue of tile i overlaps the MMAs of tile i+1 and the other group's epilogue of tile i-1.
+#include <math.h>
+
+#include "pph_common.cuh"
+#include "pph_tc_ptx.cuh"
+
+namespace pph {
+
+constexpr int kTcThreads = 384;
+constexpr int kTcStages = 4;
+constexpr int kTcBlockM = 128;
+constexpr int kTcBlockK = 64;                               // bf16 elements per k-block = one 128B swizzle row
+constexpr int kTcMaxN = 256;
+constexpr int kTcABytes = kTcBlockM * kTcBlockK * 2;        // 16 KB
+constexpr int kTcBBytes = kTcMaxN * kTcBlockK * 2;          // 32 KB
+constexpr int kTcStageBytes = kTcABytes + kTcBBytes;
+constexpr int kTcSmemBytes = 1024 /*align slack*/ + kTcStages * kTcStageBytes + 2 * kTcMaxN * 4 /*x2*/ + 256 /*bars*/;
+
+struct TcParams {
+    int B, K, D, P, Pg;
+    int G;                    // images per local tile
+    int MT_l, NG_l;           // local tiles: prototype tiles x image groups
+    int MT_g, NB_g;           // global tiles: prototype tiles x image chunks (256 images)
+    int n_local, n_tiles;
+    int umma_n_l, umma_n_g;   // UMMA N (multiple of 16)
+    int box_rows_l, box_rows_g;
+    int act_fn;
+    float eps;
+    const float *z2s, *z2c, *p2l, *p2g;
+    float *dmin_l, *act_l, *dmin_g, *act_g;
+    int32_t* argmin_l;
+};
+
+struct TcTile {
+    bool is_global;
+    int mt;        // prototype tile
+    int grp;       // image group (local) or image chunk (global)
+};
+
+__device__ __forceinline__ TcTile tc_decode(const TcParams& prm, int tile) {
+    TcTile t;
+    if (tile < prm.n_local) {
+        t.is_global = false;
+        t.grp = tile / prm.MT_l;
+        t.mt = tile - t.grp * prm.MT_l;
+    } else {
+        const int u = tile - prm.n_local;
+        t.is_global = true;
+        t.grp = u / prm.MT_g;
+        t.mt = u - t.grp * prm.MT_g;
+    }
+    return t;
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int NTERMS, int KT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+similarity_tc_kernel(const __grid_constant__ CUtensorMap tmAl_hi, const __grid_constant__ CUtensorMap tmAl_lo,
+                     const __grid_constant__ CUtensorMap tmBl_hi, const __grid_constant__ CUtensorMap tmBl_lo,
+                     const __grid_constant__ CUtensorMap tmAg_hi, const __grid_constant__ CUtensorMap tmAg_lo,
+                     const __grid_constant__ CUtensorMap tmBg_hi, const __grid_constant__ CUtensorMap tmBg_lo,
+                     const TcParams prm) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint8_t* ring = smem;
+    float* x2s = reinterpret_cast<float*>(smem + kTcStages * kTcStageBytes);          // [2][256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kTcStages * kTcStageBytes + 2 * kTcMaxN * 4);
+    uint64_t* full = bars;                      // [kTcStages]
+    uint64_t* empty = bars + kTcStages;         // [kTcStages]
+    uint64_t* tmem_full = bars + 2 * kTcStages; // [2]
+    uint64_t* tmem_empty = tmem_full + 2;       // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kblocks = prm.D / kTcBlockK;      // per term
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmAl_hi);
+        ptx::prefetch_tmap(&tmBl_hi);
+        if (NTERMS == 3) { ptx::prefetch_tmap(&tmAl_lo); ptx::prefetch_tmap(&tmBl_lo); }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kTcStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 4); }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) ptx::tmem_alloc(tmem_ptr, 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
+            const TcTile t = tc_decode(prm, tile);
+            const int rowA = t.mt * kTcBlockM;
+            const int rowB = t.is_global ? t.grp * kTcMaxN : t.grp * prm.G * prm.K;
+            const uint32_t bytes = kTcABytes + (uint32_t)(t.is_global ? prm.box_rows_g : prm.box_rows_l) * kTcBlockK * 2;
+#pragma unroll 1
+            for (int term = 0; term < NTERMS; ++term) {
+                // BF16X3 pass order: (A_lo,B_hi), (A_hi,B_lo), (A_hi,B_hi); BF16: (A_hi,B_hi)
+                const bool a_lo = (NTERMS == 3) && term == 0;
+                const bool b_lo = (NTERMS == 3) && term == 1;
+                const CUtensorMap* ma = t.is_global ? (a_lo ? &tmAg_lo : &tmAg_hi) : (a_lo ? &tmAl_lo : &tmAl_hi);
+                const CUtensorMap* mb = t.is_global ? (b_lo ? &tmBg_lo : &tmBg_hi) : (b_lo ? &tmBl_lo : &tmBl_hi);
+#pragma unroll 1
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    if (lane == 0) {
+                        ptx::mbar_wait(&empty[stage], phase ^ 1u);
+                        ptx::mbar_expect_tx(&full[stage], bytes);
+                        uint8_t* sA = ring + stage * kTcStageBytes;
+                        ptx::tma_load_2d(sA, ma, &full[stage], kb * kTcBlockK, rowA);
+                        ptx::tma_load_2d(sA + kTcABytes, mb, &full[stage], kb * kTcBlockK, rowB);
+                    }
+                    __syncwarp();
+                    if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        const uint32_t idesc_l = ptx::umma_idesc_bf16(kTcBlockM, prm.umma_n_l);
+        const uint32_t idesc_g = ptx::umma_idesc_bf16(kTcBlockM, prm.umma_n_g);
+        for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x, ++it) {
+            const TcTile t = tc_decode(prm, tile);
+            const int acc = it & 1;
+            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            const uint32_t idesc = t.is_global ? idesc_g : idesc_l;
+            const uint32_t d_tmem = tmem_base + (uint32_t)acc * kTcMaxN;
+            if (lane == 0) ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);   // epilogue drained this accumulator
+            __syncwarp();
+            ptx::tc_fence_after();
+            const int nkb = NTERMS * kblocks;
+#pragma unroll 1
+            for (int kbt = 0; kbt < nkb; ++kbt) {
+                if (lane == 0) {
+                    ptx::mbar_wait(&full[stage], phase);
+                    ptx::tc_fence_after();
+                    const uint32_t a_base = ptx::smem_u32(ring + stage * kTcStageBytes);
+                    const uint32_t b_base = a_base + kTcABytes;
+#pragma unroll
+                    for (int kk = 0; kk < kTcBlockK / 16; ++kk) {
+                        ptx::mma_bf16_ss(d_tmem, ptx::umma_desc_k_sw128(a_base + kk * 32),
+                                         ptx::umma_desc_k_sw128(b_base + kk * 32), idesc, (uint32_t)((kbt | kk) != 0));
+                    }
+                    ptx::mma_commit(&empty[stage]);                       // smem slot reusable once these MMAs retire
+                    if (kbt == nkb - 1) ptx::mma_commit(&tmem_full[acc]);  // accumulator complete
+                }
+                __syncwarp();
+                if (++stage == kTcStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int grp_id = (warp - 4) >> 2;          // which accumulator stage this warp drains
+        const int quarter = warp & 3;                // TMEM lane quarter this warp may read
+        const int gtid = threadIdx.x - 128 - grp_id * 128;   // 0..127 inside the group
+        float* x2 = x2s + grp_id * kTcMaxN;
+        const float4* x2v = reinterpret_cast<const float4*>(x2);
+        int it = 0;
+        for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x, ++it) {
+            if ((it & 1) != grp_id) continue;
+            const TcTile t = tc_decode(prm, tile);
+            const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+            // stage the token norms of this tile's columns (overlaps the MMAs of this tile)
+            named_bar_sync(1 + grp_id, 128);
+            if (!t.is_global) {
+                const long r0 = (long)t.grp * prm.G * prm.K, rmax = (long)prm.B * prm.K;
+                for (int c = gtid; c < kTcMaxN; c += 128) x2[c] = (r0 + c < rmax) ? __ldg(prm.z2s + r0 + c) : 0.f;
+            } else {
+                const int b0 = t.grp * kTcMaxN;
+                for (int c = gtid; c < kTcMaxN; c += 128) x2[c] = (b0 + c < prm.B) ? __ldg(prm.z2c + b0 + c) : 0.f;
+            }
+            named_bar_sync(1 + grp_id, 128);
+            const int p = t.mt * kTcBlockM + quarter * 32 + lane;
+            const uint32_t taddr = tmem_base + (uint32_t)grp_id * kTcMaxN + ((uint32_t)(quarter * 32) << 16);
+
+            ptx::mbar_wait(&tmem_full[grp_id], acc_phase);
+            ptx::tc_fence_after();
+
+            if (!t.is_global) {
+                const bool pv = p < prm.P;
+                const float p2 = pv ? __ldg(prm.p2l + p) : 0.f;
+                const int b0 = t.grp * prm.G;
+                auto store = [&](int g, float best, int bk) {
+                    const int b = b0 + g;
+                    if (pv && b < prm.B) {
+                        const float d = fmaxf(best + p2, 0.0f);
+                        const size_t o = (size_t)b * prm.P + p;
+                        prm.dmin_l[o] = d;
+                        prm.argmin_l[o] = bk;
+                        prm.act_l[o] = act_of_dist(d, prm.act_fn, prm.eps);
+                    }
+                };
+                float best = INFINITY;
+                int bk = 0;
+                if constexpr (KT > 0) {
+                    constexpr int GS = kTcMaxN / KT, TC = GS * KT;
+#pragma unroll
+                    for (int ch = 0; ch < (TC + 31) / 32; ++ch) {
+                        uint32_t v[32];
+                        ptx::tmem_ld_32x32(taddr + ch * 32, v);
+                        float4 xq[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) xq[i] = x2v[ch * 8 + i];
+                        ptx::tmem_ld_wait(v);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const int col = ch * 32 + j;
+                            if (col < TC) {
+                                const int k = col % KT, g = col / KT;
+                                const float4 q = xq[j >> 2];
+                                const float xx = (j & 3) == 0 ? q.x : (j & 3) == 1 ? q.y : (j & 3) == 2 ? q.z : q.w;
+                                const float d = fmaf(-2.0f, __uint_as_float(v[j]), xx);
+                                if (k == 0) { best = d; bk = 0; }
+                                else if (d < best) { best = d; bk = k; }
+                                if (k == KT - 1) store(g, best, bk);
+                            }
+                        }
+                    }
+                } else {
+                    const int Kc = prm.K;
+                    const int gcnt = min(prm.G, prm.B - b0);
+                    const int ncols = gcnt * Kc;
+                    int g = 0, k = 0;
+                    for (int c0 = 0; c0 < ncols; c0 += 32) {
+                        uint32_t v[32];
+                        ptx::tmem_ld_32x32(taddr + c0, v);
+                        ptx::tmem_ld_wait(v);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            if (c0 + j < ncols) {
+                                const float d = fmaf(-2.0f, __uint_as_float(v[j]), x2[c0 + j]);
+                                if (d < best) { best = d; bk = k; }
+                                if (++k == Kc) {
+                                    store(g, best, bk);
+                                    ++g; k = 0; best = INFINITY; bk = 0;
+                                }
+                            }
+                        }
+                    }
+                }
+            } else {
+                const bool pv = p < prm.Pg;
+                const float p2 = pv ? __ldg(prm.p2g + p) : 0.f;
+                const int b0 = t.grp * kTcMaxN;
+                const int ncols = min(prm.B - b0, kTcMaxN);
+                for (int c0 = 0; c0 < ncols; c0 += 32) {
+                    uint32_t v[32];
+                    ptx::tmem_ld_32x32(taddr + c0, v);
+                    ptx::tmem_ld_wait(v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        if (c0 + j < ncols && pv) {
+                            const float d = fmaxf(fmaf(-2.0f, __uint_as_float(v[j]), x2[c0 + j]) + p2, 0.0f);
+                            const size_t o = (size_t)(b0 + c0 + j) * prm.Pg + p;
+                            prm.dmin_g[o] = d;
+                            prm.act_g[o] = act_of_dist(d, prm.act_fn, prm.eps);
+                        }
+                    }
+                }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&tmem_empty[grp_id]);
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+    if (e != cudaSuccess || q != cudaDriverEntryPointSuccess || !p) {
+        (void)cudaGetLastError();
+        return nullptr;
+    }
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+    return fn;
+}
+
+// bf16 matrix [rows, D] row-major -> 2-D tiled map, box {64 elements, box_rows}, 128B swizzle, OOB rows read as 0
+static int make_map(CUtensorMap* m, const uint16_t* base, int rows, int D, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PPH_EDRIVER; }
+    cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)D * 2};
+    cuuint32_t box[2] = {(cuuint32_t)kTcBlockK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<uint16_t*>(base), gdim, gstr, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed: CUresult %d (rows=%d D=%d box_rows=%d ptr=%p)", (int)r, rows, D,
+                  box_rows, (const void*)base);
+        return PPH_EDRIVER;
+    }
+    return 0;
+}
+
+template <int NTERMS, int KT>
+static int launch_tc(const CUtensorMap* maps, const TcParams& prm, int grid, cudaStream_t st) {
+    auto kern = similarity_tc_kernel<NTERMS, KT>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        configured = true;
+    }
+    kern<<<grid, kTcThreads, kTcSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6],
+                                                 maps[7], prm);
+    return launch_status("pph_similarity_fwd(tcgen05)");
+}
+
+int similarity_fwd_tc(int mode, int act_fn, float eps, int B, int K, int D, int P, int Pg,
+                      const float* z2s, const float* z2c,
+                      const uint16_t* Zs_hi, const uint16_t* Zs_lo, const uint16_t* Zc_hi, const uint16_t* Zc_lo,
+                      const float* p2l, const float* p2g,
+                      const uint16_t* Pl_hi, const uint16_t* Pl_lo, const uint16_t* Pg_hi, const uint16_t* Pg_lo,
+                      float* dmin_l, int32_t* argmin_l, float* act_l, float* dmin_g, float* act_g, cudaStream_t st) {
+    const bool x3 = (mode == PPH_MODE_BF16X3);
+    PPH_REQUIRE(D % kTcBlockK == 0 && D >= 64 && D <= 512, PPH_EUNSUP,
+                "tcgen05 similarity needs D %% 64 == 0 and 64 <= D <= 512 (D=%d)", D);
+    PPH_REQUIRE(K >= 1 && K <= kTcMaxN, PPH_EUNSUP, "tcgen05 similarity needs 1 <= K <= 256 (K=%d)", K);
+    PPH_REQUIRE(P >= 1 && Zs_hi && Pl_hi && z2s && p2l && dmin_l && argmin_l && act_l, PPH_EINVAL,
+                "tcgen05 similarity: null local operand");
+    PPH_REQUIRE(!x3 || (Zs_lo && Pl_lo), PPH_EINVAL, "PPH_MODE_BF16X3 needs the lo operands");
+    PPH_REQUIRE(Pg == 0 || (Zc_hi && Pg_hi && z2c && p2g && dmin_g && act_g && (!x3 || (Zc_lo && Pg_lo))), PPH_EINVAL,
+                "tcgen05 similarity: null global operand");
+
+    TcParams prm;
+    prm.B = B; prm.K = K; prm.D = D; prm.P = P; prm.Pg = Pg;
+    const bool static81 = (K == 81), static121 = (K == 121);
+    prm.G = kTcMaxN / K;
+    prm.MT_l = ceil_div(P, kTcBlockM);
+    prm.NG_l = ceil_div(B, prm.G);
+    prm.MT_g = Pg > 0 ? ceil_div(Pg, kTcBlockM) : 0;
+    prm.NB_g = Pg > 0 ? ceil_div(B, kTcMaxN) : 0;
+    prm.n_local = prm.MT_l * prm.NG_l;
+    prm.n_tiles = prm.n_local + prm.MT_g * prm.NB_g;
+    prm.box_rows_l = prm.G * K;
+    prm.umma_n_l = ceil_div(prm.box_rows_l, 16) * 16;
+    prm.umma_n_g = ceil_div(B < kTcMaxN ? B : kTcMaxN, 16) * 16;
+    prm.box_rows_g = prm.umma_n_g;
+    prm.act_fn = act_fn; prm.eps = eps;
+    prm.z2s = z2s; prm.z2c = z2c; prm.p2l = p2l; prm.p2g = p2g;
+    prm.dmin_l = dmin_l; prm.act_l = act_l; prm.dmin_g = dmin_g; prm.act_g = act_g; prm.argmin_l = argmin_l;
+
+    CUtensorMap maps[8];
+    int rc;
+    if ((rc = make_map(&maps[0], Pl_hi, P, D, kTcBlockM))) return rc;
+    if ((rc = make_map(&maps[1], x3 ? Pl_lo : Pl_hi, P, D, kTcBlockM))) return rc;
+    if ((rc = make_map(&maps[2], Zs_hi, B * K, D, prm.box_rows_l))) return rc;
+    if ((rc = make_map(&maps[3], x3 ? Zs_lo : Zs_hi, B * K, D, prm.box_rows_l))) return rc;
+    if (Pg > 0) {
+        if ((rc = make_map(&maps[4], Pg_hi, Pg, D, kTcBlockM))) return rc;
+        if ((rc = make_map(&maps[5], x3 ? Pg_lo : Pg_hi, Pg, D, kTcBlockM))) return rc;
+        if ((rc = make_map(&maps[6], Zc_hi, B, D, prm.box_rows_g))) return rc;
+        if ((rc = make_map(&maps[7], x3 ? Zc_lo : Zc_hi, B, D, prm.box_rows_g))) return rc;
+    } else {
+        for (int i = 4; i < 8; ++i) maps[i] = maps[i - 4];
+    }
+    static int sms = 0;
+    if (sms <= 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    const int grid = prm.n_tiles < sms ? prm.n_tiles : sms;
+    if (x3) {
+        if (static81) return launch_tc<3, 81>(maps, prm, grid, st);
+        if (static121) return launch_tc<3, 121>(maps, prm, grid, st);
+        return launch_tc<3, 0>(maps, prm, grid, st);
+    }
+    if (static81) return launch_tc<1, 81>(maps, prm, grid, st);
+    if (static121) return launch_tc<1, 121>(maps, prm, grid, st);
+    return launch_tc<1, 0>(maps, prm, grid, st);
+}
+
+}  // namespace pph

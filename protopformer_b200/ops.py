@@ -1,0 +1,328 @@
+"""Host-side operators of the prototype head: thin autograd wrappers over the C ABI (include/protohead.h).
+
+Every function launches sm_100a kernels on the current CUDA stream through ``_lib.call``; nothing here computes
+on the CPU or through PyTorch math (torch is used to allocate device buffers and to carry autograd edges).
+Reference lines are those of /root/reference/protopformer.py.
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+
+import torch
+
+from . import _lib
+
+
+@dataclasses.dataclass(frozen=True)
+class HeadConfig:
+    """Scalars of one prototype head (PPNet ctor arguments that reach the kernels, protopformer.py:14-44)."""
+
+    K: int                        # reserve_token_nums[-1]
+    global_coe: float = 0.5
+    act_fn: str = "log"           # prototype_activation_function: 'log' | 'linear'
+    eps: float = 1e-4             # PPNet.epsilon
+    mode: str = "fp32"            # 'fp32' (= bf16x3 on tcgen05) | 'bf16' | 'fp32_fma'
+    ppc_cov_thresh: float = 1.0
+    ppc_mean_thresh: float = 2.0
+
+    @property
+    def mode_id(self) -> int:
+        return _lib.MODES[self.mode]
+
+    @property
+    def act_id(self) -> int:
+        return _lib.ACTS[self.act_fn]
+
+
+def _empty(shape, dtype, like):
+    return torch.empty(shape, dtype=dtype, device=like.device)
+
+
+def tc_supported(D: int, K: int) -> bool:
+    """Shapes the tcgen05 similarity kernel was built for (include/protohead.h, pph_similarity_fwd)."""
+    return D % 64 == 0 and 64 <= D <= 512 and 1 <= K <= 256
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# (a1) selection -- protopformer.py:157-158
+# ------------------------------------------------------------------------------------------------------------------
+def select_topk(scores: torch.Tensor, K: int, want_int64: bool = False):
+    """scores (B,N) or (B,H,N) fp32 -> ascending int32 index list (B,K) [and its int64 twin]."""
+    s = scores.detach()
+    if s.dtype != torch.float32:
+        s = s.float()
+    s = s.contiguous()
+    if s.dim() == 2:
+        B, N = s.shape
+        H = 1
+    else:
+        B, H, N = s.shape
+    idx32 = _empty((B, K), torch.int32, s)
+    idx64 = _empty((B, K), torch.int64, s) if want_int64 else None
+    _lib.call("pph_select_topk", s, B, H, N, K, idx32, idx64)
+    return (idx32, idx64) if want_int64 else idx32
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# (a2) gather + add-on layer -- protopformer.py:159-172
+# ------------------------------------------------------------------------------------------------------------------
+class _Addon(torch.autograd.Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, tokens, idx32, Wa, ba, want_split):
+        tokens, Wa, ba = tokens.contiguous(), Wa.contiguous(), ba.contiguous()
+        B, n1, Din = tokens.shape
+        N, K, D = n1 - 1, idx32.shape[1], Wa.shape[0]
+        f32, bf = torch.float32, torch.bfloat16
+        Zs, Zc = _empty((B, K, D), f32, tokens), _empty((B, D), f32, tokens)
+        z2s, z2c = _empty((B, K), f32, tokens), _empty((B,), f32, tokens)
+        if want_split:
+            z2s_hi, z2c_hi = _empty((B, K), f32, tokens), _empty((B,), f32, tokens)
+            Zs_hi, Zs_lo = _empty((B * K, D), bf, tokens), _empty((B * K, D), bf, tokens)
+            Zc_hi, Zc_lo = _empty((B, D), bf, tokens), _empty((B, D), bf, tokens)
+        else:
+            z2s_hi = z2c_hi = Zs_hi = Zs_lo = Zc_hi = Zc_lo = None
+        _lib.call("pph_addon_fwd", tokens, idx32, Wa, ba, B, N, Din, D, K, Zs, Zc, z2s, z2c, z2s_hi, z2c_hi,
+                  Zs_hi, Zs_lo, Zc_hi, Zc_lo)
+        ctx.save_for_backward(tokens, idx32, Wa, Zs, Zc)
+        ctx.dims = (B, N, Din, D, K)
+        aux = [z2s, z2c, z2s_hi, z2c_hi, Zs_hi, Zs_lo, Zc_hi, Zc_lo]
+        aux = [a if a is not None else _empty((0,), f32, tokens) for a in aux]
+        ctx.mark_non_differentiable(*aux)
+        return (Zs, Zc, *aux)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dZs, dZc, *_unused):
+        tokens, idx32, Wa, Zs, Zc = ctx.saved_tensors
+        B, N, Din, D, K = ctx.dims
+        dZs = torch.zeros_like(Zs) if dZs is None else dZs.contiguous()
+        dZc = torch.zeros_like(Zc) if dZc is None else dZc.contiguous()
+        dWa, dba = torch.empty_like(Wa), _empty((D,), torch.float32, Wa)
+        dtok = torch.empty_like(tokens) if ctx.needs_input_grad[0] else None
+        _lib.call("pph_addon_bwd", tokens, idx32, Wa, Zs, Zc, dZs, dZc, B, N, Din, D, K, dWa, dba, dtok)
+        return dtok, None, dWa, dba, None
+
+
+@dataclasses.dataclass
+class TokenFeatures:
+    """Output of the add-on stage: fp32 features (autograd-tracked) + the operands the tensor-core kernel reads."""
+
+    Zs: torch.Tensor            # (B,K,D)
+    Zc: torch.Tensor            # (B,D)
+    z2s: torch.Tensor           # (B,K)
+    z2c: torch.Tensor           # (B,)
+    z2s_hi: torch.Tensor | None
+    z2c_hi: torch.Tensor | None
+    Zs_hi: torch.Tensor | None  # (B*K,D) bf16
+    Zs_lo: torch.Tensor | None
+    Zc_hi: torch.Tensor | None
+    Zc_lo: torch.Tensor | None
+    idx32: torch.Tensor         # (B,K)
+
+
+def addon(tokens, idx32, Wa, ba, want_split: bool) -> TokenFeatures:
+    """tokens (B,1+N,Din), idx32 (B,K), Wa (D,Din) or (D,Din,1,1), ba (D)."""
+    Wa2 = Wa.reshape(Wa.shape[0], -1)
+    out = _Addon.apply(tokens, idx32, Wa2, ba, want_split)
+    Zs, Zc, z2s, z2c, z2s_hi, z2c_hi, Zs_hi, Zs_lo, Zc_hi, Zc_lo = out
+    if not want_split:
+        z2s_hi = z2c_hi = Zs_hi = Zs_lo = Zc_hi = Zc_lo = None
+    return TokenFeatures(Zs, Zc, z2s, z2c, z2s_hi, z2c_hi, Zs_hi, Zs_lo, Zc_hi, Zc_lo, idx32)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# operand preparation for prototypes -- the p2 term of protopformer.py:207-208 (+ bf16 split for tcgen05)
+# ------------------------------------------------------------------------------------------------------------------
+@dataclasses.dataclass
+class ProtoOperands:
+    P: torch.Tensor                 # (R,D) fp32 (detached, contiguous)
+    p2: torch.Tensor                # (R,)
+    p2_hi: torch.Tensor | None
+    hi: torch.Tensor | None         # (R,D) bf16
+    lo: torch.Tensor | None
+
+
+def prepare_prototypes(P2d: torch.Tensor, want_split: bool) -> ProtoOperands:
+    P = P2d.detach()
+    if P.dtype != torch.float32:
+        P = P.float()
+    P = P.contiguous()
+    R, D = P.shape
+    p2 = _empty((R,), torch.float32, P)
+    if want_split:
+        hi, lo = _empty((R, D), torch.bfloat16, P), _empty((R, D), torch.bfloat16, P)
+        p2_hi = _empty((R,), torch.float32, P)
+    else:
+        hi = lo = p2_hi = None
+    _lib.call("pph_split_rows", P, R, D, hi, lo, p2, p2_hi)
+    return ProtoOperands(P, p2, p2_hi, hi, lo)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# (a3-a6) similarity + pooling + last layers -- protopformer.py:201-247, 297-300
+# ------------------------------------------------------------------------------------------------------------------
+def _similarity_raw(cfg: HeadConfig, tf: TokenFeatures, pl: ProtoOperands, pg: ProtoOperands,
+                    want_maps: bool = False, mode_id: int | None = None):
+    """Launch pph_similarity_fwd; returns dmin_l, argmin, act_l, dmin_g, act_g (+ dist_map, act_map)."""
+    Zs = tf.Zs.detach()
+    B, K, D = Zs.shape
+    P, Pg = pl.P.shape[0], pg.P.shape[0]
+    mode = cfg.mode_id if mode_id is None else mode_id
+    f32 = torch.float32
+    dmin_l, act_l = _empty((B, P), f32, Zs), _empty((B, P), f32, Zs)
+    argmin = _empty((B, P), torch.int32, Zs)
+    dmin_g, act_g = _empty((B, Pg), f32, Zs), _empty((B, Pg), f32, Zs)
+    dist_map = act_map = None
+    if want_maps:
+        assert mode == _lib.MODE_FP32_FMA
+        dist_map, act_map = _empty((B, P, K), f32, Zs), _empty((B, P, K), f32, Zs)
+    rounded = mode == _lib.MODE_BF16          # single-pass bf16: norms of the rounded operands
+    _lib.call("pph_similarity_fwd", mode, cfg.act_id, float(cfg.eps), B, K, D, P, Pg,
+              Zs, tf.Zc.detach(), tf.z2s_hi if rounded else tf.z2s, tf.z2c_hi if rounded else tf.z2c,
+              tf.Zs_hi, tf.Zs_lo, tf.Zc_hi, tf.Zc_lo,
+              pl.P, pg.P, pl.p2_hi if rounded else pl.p2, pg.p2_hi if rounded else pg.p2,
+              pl.hi, pl.lo, pg.hi, pg.lo,
+              dmin_l, argmin, act_l, dmin_g, act_g, dist_map, act_map)
+    return dmin_l, argmin, act_l, dmin_g, act_g, dist_map, act_map
+
+
+class _SimilarityLogits(torch.autograd.Function):
+    """(Zs, Zc, P, Pg) -> logits.  Wl / Wg are the frozen last layers (protopformer.py:130-131): no gradient."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, Zs, Zc, P2d, Pg2d, Wl, Wg, tf, cfg):
+        want_split = cfg.mode_id != _lib.MODE_FP32_FMA
+        pl, pg = prepare_prototypes(P2d, want_split), prepare_prototypes(Pg2d, want_split)
+        dmin_l, argmin, act_l, dmin_g, act_g, _, _ = _similarity_raw(cfg, tf, pl, pg)
+        B, P = act_l.shape
+        Pg, C = act_g.shape[1], Wl.shape[0]
+        Wl, Wg = Wl.detach().contiguous(), Wg.detach().contiguous()
+        logits = _empty((B, C), torch.float32, Zs)
+        logits_g, logits_l = torch.empty_like(logits), torch.empty_like(logits)
+        _lib.call("pph_logits_fwd", act_l, act_g, Wl, Wg, B, P, Pg, C, float(cfg.global_coe), logits, logits_g, logits_l)
+        ctx.save_for_backward(Zs, Zc, pl.P, pg.P, Wl, Wg, dmin_l, dmin_g, argmin)
+        ctx.cfg = cfg
+        ctx.mark_non_differentiable(act_l, act_g, dmin_l, dmin_g, argmin, pl.p2)
+        return logits, logits_g, logits_l, act_l, act_g, dmin_l, dmin_g, argmin, pl.p2
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, dlogits, dlogits_g, dlogits_l, *_unused):
+        Zs, Zc, Pl, Pgl, Wl, Wg, dmin_l, dmin_g, argmin = ctx.saved_tensors
+        cfg = ctx.cfg
+        B, K, D = Zs.shape
+        P, Pg, C = Pl.shape[0], Pgl.shape[0], Wl.shape[0]
+        f32 = torch.float32
+        if dlogits is None:
+            dlogits = torch.zeros((B, C), dtype=f32, device=Zs.device)
+        dlogits = dlogits.contiguous()
+        dlogits_g = None if dlogits_g is None else dlogits_g.contiguous()
+        dlogits_l = None if dlogits_l is None else dlogits_l.contiguous()
+        g_l, g_g = _empty((B, P), f32, Zs), _empty((B, Pg), f32, Zs)
+        _lib.call("pph_logits_bwd", dlogits, dlogits_g, dlogits_l, Wl, Wg, dmin_l, dmin_g, B, P, Pg, C,
+                  float(cfg.global_coe), cfg.act_id, float(cfg.eps), g_l, g_g)
+        dZs, dZc = torch.empty_like(Zs), torch.empty_like(Zc)
+        dPl, dPg = torch.empty_like(Pl), torch.empty_like(Pgl)
+        _lib.call("pph_similarity_bwd", g_l, g_g, argmin, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, dZs, dZc, dPl, dPg)
+        return dZs, dZc, dPl, dPg, None, None, None, None
+
+
+@dataclasses.dataclass
+class HeadOutput:
+    logits: torch.Tensor
+    logits_global: torch.Tensor
+    logits_local: torch.Tensor
+    act_l: torch.Tensor         # (B,P) pooled local activations
+    act_g: torch.Tensor         # (B,Pg)
+    dmin_l: torch.Tensor        # (B,P) min distance over tokens
+    dmin_g: torch.Tensor
+    argmin: torch.Tensor        # (B,P) int32 token slot of the max activation
+    p2l: torch.Tensor           # (P,) |prototype|^2 (reused by the PPC loss)
+    tf: TokenFeatures
+
+
+def head_forward(cfg: HeadConfig, tokens, scores, Wa, ba, P, Pg, Wl, Wg) -> HeadOutput:
+    """The whole prototype head after the backbone: selection -> add-on -> similarity/pool -> logits.
+
+    tokens (B,1+N,Din), scores (B,N)|(B,H,N), Wa (D,Din[,1,1]), ba (D), P (P,D[,1,1]), Pg (Pg,D[,1,1]),
+    Wl (C,P), Wg (C,Pg).  Replaces protopformer.py:156-172 + 311-316.
+    """
+    if tokens.shape[0] == 0:
+        return _empty_head_output(cfg, tokens, Wa, P, Pg, Wl)
+    idx32 = select_topk(scores, cfg.K)
+    want_split = cfg.mode_id != _lib.MODE_FP32_FMA
+    tf = addon(tokens, idx32, Wa, ba, want_split)
+    P2d, Pg2d = P.reshape(P.shape[0], -1), Pg.reshape(Pg.shape[0], -1)
+    out = _SimilarityLogits.apply(tf.Zs, tf.Zc, P2d, Pg2d, Wl, Wg, tf, cfg)
+    logits, lg, ll, act_l, act_g, dmin_l, dmin_g, argmin, p2l = out
+    return HeadOutput(logits, lg, ll, act_l, act_g, dmin_l, dmin_g, argmin, p2l, tf)
+
+
+def _empty_head_output(cfg, tokens, Wa, P, Pg, Wl) -> HeadOutput:
+    """B == 0 (e.g. an empty last shard): nothing to launch."""
+    f32, dev = torch.float32, tokens.device
+    D, Pn, Pgn, C = Wa.shape[0], P.shape[0], Pg.shape[0], Wl.shape[0]
+    z = lambda *s, dt=f32: torch.zeros(s, dtype=dt, device=dev)  # noqa: E731
+    tf = TokenFeatures(z(0, cfg.K, D), z(0, D), z(0, cfg.K), z(0), None, None, None, None, None, None,
+                       z(0, cfg.K, dt=torch.int32))
+    return HeadOutput(z(0, C), z(0, C), z(0, C), z(0, Pn), z(0, Pgn), z(0, Pn), z(0, Pgn), z(0, Pn, dt=torch.int32),
+                      z(Pn), tf)
+
+
+def materialize_maps(cfg: HeadConfig, tf: TokenFeatures, P, Pg):
+    """Full (B,P,K) distance and activation maps (eval aux `distances` :301, push_forward `proto_acts` :344).
+    Always computed by the FP32-FMA kernel; not part of the autograd graph."""
+    pl = prepare_prototypes(P.reshape(P.shape[0], -1), False)
+    pg = prepare_prototypes(Pg.reshape(Pg.shape[0], -1), False)
+    _, _, _, _, _, dist_map, act_map = _similarity_raw(cfg, tf, pl, pg, want_maps=True, mode_id=_lib.MODE_FP32_FMA)
+    return dist_map, act_map
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# (a7) PPC loss -- protopformer.py:249-288
+# ------------------------------------------------------------------------------------------------------------------
+class _PPC(torch.autograd.Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
+    def forward(ctx, Zs, P2d, z2s, p2l, idx32, labels, m, N, cfg):
+        Zs, Pl = Zs.contiguous(), P2d.contiguous()
+        B, K, D = Zs.shape
+        P = Pl.shape[0]
+        f32 = torch.float32
+        labels = labels.to(torch.int64).contiguous()
+        dslice, stats = _empty((B, m, K), f32, Zs), _empty((B, m, 8), f32, Zs)
+        partial = _empty((B, 2), f32, Zs)
+        counter = torch.zeros((1,), dtype=torch.int32, device=Zs.device)
+        losses = _empty((2,), f32, Zs)
+        _lib.call("pph_ppc_fwd", Zs, z2s, Pl, p2l, idx32, labels, B, K, D, P, m, N, cfg.act_id, float(cfg.eps),
+                  float(cfg.ppc_cov_thresh), float(cfg.ppc_mean_thresh), dslice, stats, partial, counter, losses)
+        ctx.save_for_backward(Zs, Pl, idx32, labels, dslice, stats)
+        ctx.meta = (m, N, cfg)
+        return losses[0], losses[1]
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, g_cov, g_mean):
+        Zs, Pl, idx32, labels, dslice, stats = ctx.saved_tensors
+        m, N, cfg = ctx.meta
+        B, K, D = Zs.shape
+        P = Pl.shape[0]
+        zero = torch.zeros((), dtype=torch.float32, device=Zs.device)
+        g = torch.stack([zero if g_cov is None else g_cov.float(), zero if g_mean is None else g_mean.float()])
+        dZs, dP = torch.empty_like(Zs), torch.zeros_like(Pl)
+        _lib.call("pph_ppc_bwd", Zs, Pl, idx32, labels, dslice, stats, g, B, K, D, P, m, N, cfg.act_id,
+                  float(cfg.eps), float(cfg.ppc_cov_thresh), float(cfg.ppc_mean_thresh), dZs, dP)
+        return dZs, dP, None, None, None, None, None, None, None
+
+
+def ppc_loss(cfg: HeadConfig, tf: TokenFeatures, P, p2l, labels, m: int, N: int):
+    """-> (ppc_cov_loss, ppc_mean_loss) 0-dim tensors; gradients reach Zs (hence the add-on and tokens) and P."""
+    side = int(round(math.sqrt(N)))
+    assert side * side == N, "original_fea_len must be a perfect square (protopformer.py:260)"
+    P2d = P.reshape(P.shape[0], -1)
+    if p2l is None:
+        p2l = prepare_prototypes(P2d, False).p2
+    return _PPC.apply(tf.Zs, P2d, tf.z2s, p2l, tf.idx32, labels, m, N, cfg)

@@ -1,0 +1,129 @@
+"""CPU-side checks (no GPU): the C-ABI library loads and exports every symbol include/protohead.h declares, the
+ctypes signatures agree with the header, the product never touches oracle/, host logic of the module and of the
+multi-process plumbing (gloo, world_size 2)."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "protohead.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(?:int|const char\*)\s+(pph_\w+)\s*\(([^;]*?)\)\s*;", src, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args == "void" else len([a for a in args.split(",") if a.strip()])
+    return out
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    from protopformer_b200 import _lib, build
+    build.build()
+    lib = _lib.load()
+    decl = _header_functions()
+    assert len(decl) >= 13
+    for name, nargs in decl.items():
+        assert hasattr(lib, name), f"{name} declared in protohead.h but not exported"
+        assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
+        assert len(_lib.SIGNATURES[name]) == nargs, f"{name}: header has {nargs} args, binding {len(_lib.SIGNATURES[name])}"
+    assert set(_lib.SIGNATURES) == set(decl)
+    assert lib.pph_version() == 100
+
+
+def test_sass_contains_blackwell_tensor_and_tma_instructions():
+    from protopformer_b200 import _lib
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    if not sass:
+        pytest.skip("cuobjdump unavailable")
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, f"{mnemonic} missing from the SASS of the similarity kernel"
+
+
+def test_no_cpu_fallback_argument_errors_and_loud_failure_without_gpu():
+    from protopformer_b200 import _lib, ops
+    lib = _lib.load()
+    # argument validation happens before any launch
+    assert lib.pph_select_topk(None, 1, 1, 8, 4, None, None, None) == -1
+    assert b"null" in lib.pph_last_error_string()
+    if not torch.cuda.is_available():
+        with pytest.raises((AssertionError, RuntimeError)):
+            ops.select_topk(torch.rand(2, 16), 4)          # CPU tensors are refused, nothing falls back
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "protopformer_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("oracle/ is the checker", ""), f"{f} mentions the oracle"
+                assert "/root/reference" not in txt or f.endswith(".py") and "Reference lines" in txt
+
+
+def test_module_constructs_on_cpu_with_reference_attribute_names():
+    import torch.nn as nn
+    from protopformer_b200 import PPNet
+
+    class MyVisionTransformer(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc = nn.Linear(24, 24)
+            self.patch_embed = nn.Module()
+            self.patch_embed.num_patches = 16
+
+    net = PPNet(MyVisionTransformer(), 224, [20, 16, 1, 1], [14, 16, 16, 8.0], 4, reserve_layers=[11],
+                reserve_token_nums=[9], use_global=True, use_ppc_loss=True, global_proto_per_class=2,
+                add_on_layers_type='regular')
+    assert net.num_prototypes_per_class == 5 and net.num_prototypes_global == 8 and net.epsilon == 1e-4
+    assert tuple(net.prototype_vectors.shape) == (20, 16, 1, 1) and tuple(net.prototype_vectors_global.shape) == (8, 16, 1, 1)
+    assert not net.last_layer.weight.requires_grad and not net.ones.requires_grad
+    w = net.last_layer.weight
+    assert w[0, :5].eq(1).all() and w[0, 5:].eq(-0.5).all()                  # protopformer.py:367-386
+    for attr in ("features", "add_on_layers", "prototype_vectors", "prototype_vectors_global"):
+        assert hasattr(net, attr)                                            # tools/create_optimizer.py:31-39
+    with pytest.raises(NotImplementedError):
+        PPNet(MyVisionTransformer(), 224, [20, 16, 1, 1], [14, 16, 16, 8.0], 4, use_global=False)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from protopformer_b200.dist import FlatGradReducer, shard_batch
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    P = torch.nn.Parameter(torch.rand(6, 4))
+    W = torch.nn.Parameter(torch.rand(3))
+    red = FlatGradReducer([("P", P), ("W", W)])
+    red.zero()
+    lo, hi = shard_batch(10, rank, world)
+    x = torch.arange(10, dtype=torch.float32)[lo:hi]
+    loss = (P.sum() * x.sum()) + (W * (rank + 1)).sum()
+    loss.backward()
+    assert P.grad.data_ptr() == red.views[0].data_ptr()       # autograd accumulated in place into the flat buffer
+    red.allreduce()
+    q.put((rank, lo, hi, P.grad.clone(), W.grad.clone()))
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, lo0, hi0, gP0, gW0), (_, lo1, hi1, gP1, gW1) = res
+    assert (lo0, hi0, lo1, hi1) == (0, 5, 5, 10)
+    assert torch.allclose(gP0, gP1) and torch.allclose(gW0, gW1)
+    assert torch.allclose(gP0, torch.full((6, 4), 45.0 / 2))      # mean over ranks of sum(x_shard)
+    assert torch.allclose(gW0, torch.full((3,), 1.5))
