@@ -61,27 +61,34 @@ int pph_select_topk(const float* scores, int B, int H, int N, int K,
  * selected patch tokens and the CLS token of every image.
  * tokens [B,1+N,Din], idx32 [B,K], Wa [D,Din], ba [D] ->
  *   Zs [B,K,D] fp32, Zc [B,D] fp32, z2s [B,K] = |Zs|^2, z2c [B] = |Zc|^2,
- *   Zs_hi/Zs_lo [B*K,D] bf16 split (hi = rn(z), lo = rn(z - hi)), Zc_hi/Zc_lo [B,D],
- *   z2s_hi [B,K] / z2c_hi [B] = |hi|^2, the norms of the ROUNDED operand (what PPH_MODE_BF16 must be given as
- *   z2s/z2c so that the distance of the rounded vectors stays consistent).  The six bf16-side outputs may be NULL. */
+ * and the tensor-core operands, taken from the CENTRED features z' = z - center (the squared distance is
+ * translation invariant; centring sigmoid outputs at 0.5 keeps the tcgen05 accumulator ~40x smaller, which is what
+ * makes its truncating fp32 accumulation meet the 1e-4 bar):
+ *   Zs_hi/Zs_lo [B*K,D] bf16 split (hi = rn(z'), lo = rn(z' - hi)), Zc_hi/Zc_lo [B,D],
+ *   z2s_ctr [B,K] / z2c_ctr [B] = |z'|^2 (fp32; the norms PPH_MODE_BF16X3 must be given),
+ *   z2s_hi  [B,K] / z2c_hi  [B] = |hi|^2 (norms of the ROUNDED operand; the norms PPH_MODE_BF16 must be given).
+ * The eight tensor-core-side outputs may be NULL. */
 int pph_addon_fwd(const float* tokens, const int32_t* idx32, const float* Wa, const float* ba,
                   int B, int N, int Din, int D, int K,
-                  float* Zs, float* Zc, float* z2s, float* z2c, float* z2s_hi, float* z2c_hi,
+                  float* Zs, float* Zc, float* z2s, float* z2c,
+                  float center, float* z2s_ctr, float* z2c_ctr, float* z2s_hi, float* z2c_hi,
                   uint16_t* Zs_hi, uint16_t* Zs_lo, uint16_t* Zc_hi, uint16_t* Zc_lo, pph_stream_t stream);
 
-/* operand preparation for the tensor-core modes: V [R,D] fp32 -> hi/lo bf16 split [R,D], v2 [R] = |V|^2
- * (the p2 term of protopformer.py:207-208), v2_hi [R] = |hi|^2.  Any output may be NULL. */
-int pph_split_rows(const float* V, int R, int D, uint16_t* hi, uint16_t* lo, float* v2, float* v2_hi,
-                   pph_stream_t stream);
+/* operand preparation for the tensor-core modes: V [R,D] fp32 -> v2 [R] = |V|^2 (the p2 term of
+ * protopformer.py:207-208) and, from v' = v - center: hi/lo bf16 split [R,D], v2_ctr [R] = |v'|^2, v2_hi [R] = |hi|^2.
+ * `center` must equal the one given to pph_addon_fwd.  Any output may be NULL. */
+int pph_split_rows(const float* V, int R, int D, float center, uint16_t* hi, uint16_t* lo, float* v2, float* v2_ctr,
+                   float* v2_hi, pph_stream_t stream);
 
 /* (a3,a4,a5) protopformer.py:201-218, 228-234, 236-247  squared-L2 distances of every selected token to every
  * local prototype (and of the CLS token to every global prototype), log/linear similarity, max over tokens.
  * Local:  dmin_l [B,P] = min_k relu(z2 - 2 z.p + p2), argmin_l [B,P] (token slot 0..K-1, lowest on ties),
  *         act_l [B,P] = act(dmin_l).      Global: dmin_g [B,Pg], act_g [B,Pg].
  * mode FP32_FMA reads Zs/Zc/Pl/Pg (fp32) and can also write the materialised maps dist_map / act_map [B,P,K]
- * (protopformer.py:301 aux `distances`, :344 `proto_acts`); the tcgen05 modes read the bf16 operands (lo
- * pointers unused in PPH_MODE_BF16, which wants z2s/z2c/p2l/p2g = norms of the rounded operands), never write
- * the maps (dist_map/act_map must be NULL) and require D % 64 == 0, 64 <= D <= 512, 1 <= K <= 256. */
+ * (protopformer.py:301 aux `distances`, :344 `proto_acts`); the tcgen05 modes read the centred bf16 operands and
+ * want z2s/z2c/p2l/p2g = the matching norms (PPH_MODE_BF16X3: the *_ctr norms; PPH_MODE_BF16: the *_hi norms, lo
+ * pointers unused), never write the maps (dist_map/act_map must be NULL) and require D % 64 == 0, 64 <= D <= 512,
+ * 1 <= K <= 256. */
 int pph_similarity_fwd(int mode, int act_fn, float eps, int B, int K, int D, int P, int Pg,
                        const float* Zs, const float* Zc, const float* z2s, const float* z2c,
                        const uint16_t* Zs_hi, const uint16_t* Zs_lo, const uint16_t* Zc_hi, const uint16_t* Zc_lo,

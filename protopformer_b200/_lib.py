@@ -26,8 +26,8 @@ SIGNATURES = {
     "pph_last_error_string": [],
     "pph_sm_count": [],
     "pph_select_topk": [_p, _i, _i, _i, _i, _p, _p, _p],
-    "pph_addon_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p],
-    "pph_split_rows": [_p, _i, _i, _p, _p, _p, _p, _p],
+    "pph_addon_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p],
+    "pph_split_rows": [_p, _i, _i, _f, _p, _p, _p, _p, _p, _p],
     "pph_similarity_fwd": [_i, _i, _f, _i, _i, _i, _i, _i] + [_p] * 24,
     "pph_logits_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p],
     "pph_ppc_fwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _p, _p, _p, _p, _p, _p],
@@ -38,7 +38,19 @@ SIGNATURES = {
 }
 _RESTYPES = {"pph_last_error_string": C.c_char_p}
 
+# kernels launched per entry-point call (memset nodes are not counted); used for the bench's `gpu_launches` claim
+KERNELS_PER_CALL = {
+    "pph_select_topk": 1, "pph_addon_fwd": 1, "pph_split_rows": 1, "pph_logits_fwd": 2, "pph_ppc_fwd": 1,
+    "pph_ppc_bwd": 1, "pph_logits_bwd": 1, "pph_similarity_bwd": 3, "pph_addon_bwd": 2,
+}
+
 _lib = None
+_launches = 0
+
+
+def launch_count() -> int:
+    """Number of protohead kernels launched (or recorded into a CUDA graph) by this process so far."""
+    return _launches
 
 
 def load() -> C.CDLL:
@@ -75,6 +87,11 @@ def call(name: str, *args):
     lib = load()
     conv = [(_ptr(a) if (a is None or isinstance(a, torch.Tensor)) else a) for a in args]
     rc = getattr(lib, name)(*conv, _stream())
+    global _launches
+    if name == "pph_similarity_fwd":
+        _launches += 2 if conv[0] == MODE_FP32_FMA else 1      # local + global kernels vs one fused tcgen05 kernel
+    else:
+        _launches += KERNELS_PER_CALL.get(name, 0)
     if rc != 0:
         msg = lib.pph_last_error_string()
         raise RuntimeError(f"{name} failed (rc={rc}): {msg.decode() if msg else ''}")

@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(kAddThreads)
 addon_fwd_kernel(const float* __restrict__ tokens, const int32_t* __restrict__ idx, const float* __restrict__ Wa,
                  const float* __restrict__ ba, int B, int N, int Din, int D, int K,
                  float* __restrict__ Zs, float* __restrict__ Zc, float* __restrict__ z2s, float* __restrict__ z2c,
+                 float center, float* __restrict__ z2s_ctr, float* __restrict__ z2c_ctr,
                  float* __restrict__ z2s_hi, float* __restrict__ z2c_hi,
                  uint16_t* __restrict__ Zs_hi, uint16_t* __restrict__ Zs_lo,
                  uint16_t* __restrict__ Zc_hi, uint16_t* __restrict__ Zc_lo) {
@@ -42,7 +43,7 @@ addon_fwd_kernel(const float* __restrict__ tokens, const int32_t* __restrict__ i
     }
     __syncthreads();
 
-    float sq[4] = {0.f, 0.f, 0.f, 0.f}, sq_hi[4] = {0.f, 0.f, 0.f, 0.f};
+    float sq[4] = {0.f, 0.f, 0.f, 0.f}, sq_hi[4] = {0.f, 0.f, 0.f, 0.f}, sq_ctr[4] = {0.f, 0.f, 0.f, 0.f};
     for (int nc = 0; nc < D; nc += kAddBN) {
         float acc[4][6];
 #pragma unroll
@@ -92,10 +93,12 @@ addon_fwd_kernel(const float* __restrict__ tokens, const int32_t* __restrict__ i
                 if (n >= D) continue;
                 const float pre = acc[i][j] + __ldg(ba + n);
                 const float z = 1.0f / (1.0f + expf(-pre));
-                const uint16_t hb = bf16_bits(z);
+                const float zc = z - center;          // tensor-core operands are centred (translation-invariant distance)
+                const uint16_t hb = bf16_bits(zc);
                 const float hf = bf16_to_float(hb);
-                const uint16_t lb = bf16_bits(z - hf);
+                const uint16_t lb = bf16_bits(zc - hf);
                 sq[i] = fmaf(z, z, sq[i]);
+                sq_ctr[i] = fmaf(zc, zc, sq_ctr[i]);
                 sq_hi[i] = fmaf(hf, hf, sq_hi[i]);
                 if (dof >= 0) {
                     Zs[dof + n] = z;
@@ -112,15 +115,17 @@ addon_fwd_kernel(const float* __restrict__ tokens, const int32_t* __restrict__ i
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const float s = warp_sum(sq[i]), sh = warp_sum(sq_hi[i]);     // a warp (fixed ty) owns its 4 rows
+        const float s = warp_sum(sq[i]), sh = warp_sum(sq_hi[i]), sc = warp_sum(sq_ctr[i]);   // a warp owns its 4 rows
         const int row = ty * 4 + i;
         if (tx == 0 && src_off[row] >= 0) {
             const long dof = dst_off[row];
             if (dof >= 0) {
                 z2s[dof / D] = s;
+                if (z2s_ctr) z2s_ctr[dof / D] = sc;
                 if (z2s_hi) z2s_hi[dof / D] = sh;
             } else {
                 z2c[-dof - 1] = s;
+                if (z2c_ctr) z2c_ctr[-dof - 1] = sc;
                 if (z2c_hi) z2c_hi[-dof - 1] = sh;
             }
         }
@@ -131,25 +136,30 @@ addon_fwd_kernel(const float* __restrict__ tokens, const int32_t* __restrict__ i
 // operand split: V [R,D] fp32 -> hi/lo bf16, |V|^2 (fp32 operand and rounded-operand flavours). One warp per row.
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-split_rows_kernel(const float* __restrict__ V, int R, int D, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo,
-                  float* __restrict__ v2, float* __restrict__ v2_hi) {
+split_rows_kernel(const float* __restrict__ V, int R, int D, float center, uint16_t* __restrict__ hi,
+                  uint16_t* __restrict__ lo, float* __restrict__ v2, float* __restrict__ v2_ctr,
+                  float* __restrict__ v2_hi) {
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= R) return;
     const float* v = V + (size_t)row * D;
-    float s = 0.f, sh = 0.f;
+    float s = 0.f, sh = 0.f, sc = 0.f;
     for (int c = lane; c < D; c += 32) {
         const float x = __ldg(v + c);
-        const uint16_t hb = bf16_bits(x);
+        const float xc = x - center;
+        const uint16_t hb = bf16_bits(xc);
         const float hf = bf16_to_float(hb);
         if (hi) hi[(size_t)row * D + c] = hb;
-        if (lo) lo[(size_t)row * D + c] = bf16_bits(x - hf);
+        if (lo) lo[(size_t)row * D + c] = bf16_bits(xc - hf);
         s = fmaf(x, x, s);
+        sc = fmaf(xc, xc, sc);
         sh = fmaf(hf, hf, sh);
     }
     s = warp_sum(s);
+    sc = warp_sum(sc);
     sh = warp_sum(sh);
     if (lane == 0) {
         if (v2) v2[row] = s;
+        if (v2_ctr) v2_ctr[row] = sc;
         if (v2_hi) v2_hi[row] = sh;
     }
 }
@@ -223,7 +233,8 @@ struct DxEpi {      // scatter of the token gradient rows
 
 extern "C" int pph_addon_fwd(const float* tokens, const int32_t* idx32, const float* Wa, const float* ba,
                              int B, int N, int Din, int D, int K,
-                             float* Zs, float* Zc, float* z2s, float* z2c, float* z2s_hi, float* z2c_hi,
+                             float* Zs, float* Zc, float* z2s, float* z2c,
+                             float center, float* z2s_ctr, float* z2c_ctr, float* z2s_hi, float* z2c_hi,
                              uint16_t* Zs_hi, uint16_t* Zs_lo, uint16_t* Zc_hi, uint16_t* Zc_lo,
                              pph_stream_t stream) {
     PPH_REQUIRE(tokens && idx32 && Wa && ba && Zs && Zc && z2s && z2c, PPH_EINVAL, "pph_addon_fwd: null pointer");
@@ -232,16 +243,18 @@ extern "C" int pph_addon_fwd(const float* tokens, const int32_t* idx32, const fl
     if (B == 0) return 0;
     const int R = B * (K + 1);
     pph::addon_fwd_kernel<<<pph::ceil_div(R, pph::kAddBM), pph::kAddThreads, 0, pph::as_stream(stream)>>>(
-        tokens, idx32, Wa, ba, B, N, Din, D, K, Zs, Zc, z2s, z2c, z2s_hi, z2c_hi, Zs_hi, Zs_lo, Zc_hi, Zc_lo);
+        tokens, idx32, Wa, ba, B, N, Din, D, K, Zs, Zc, z2s, z2c, center, z2s_ctr, z2c_ctr, z2s_hi, z2c_hi, Zs_hi,
+        Zs_lo, Zc_hi, Zc_lo);
     return pph::launch_status("pph_addon_fwd");
 }
 
-extern "C" int pph_split_rows(const float* V, int R, int D, uint16_t* hi, uint16_t* lo, float* v2, float* v2_hi,
-                              pph_stream_t stream) {
+extern "C" int pph_split_rows(const float* V, int R, int D, float center, uint16_t* hi, uint16_t* lo, float* v2,
+                              float* v2_ctr, float* v2_hi, pph_stream_t stream) {
     PPH_REQUIRE(V, PPH_EINVAL, "pph_split_rows: null pointer");
     PPH_REQUIRE(R >= 0 && D >= 1, PPH_EINVAL, "pph_split_rows: bad dims R=%d D=%d", R, D);
     if (R == 0) return 0;
-    pph::split_rows_kernel<<<pph::ceil_div(R, 8), 256, 0, pph::as_stream(stream)>>>(V, R, D, hi, lo, v2, v2_hi);
+    pph::split_rows_kernel<<<pph::ceil_div(R, 8), 256, 0, pph::as_stream(stream)>>>(V, R, D, center, hi, lo, v2, v2_ctr,
+                                                                                            v2_hi);
     return pph::launch_status("pph_split_rows");
 }
 

@@ -1,0 +1,106 @@
+"""Static-shape training / inference step of the prototype head captured in CUDA graphs.
+
+At the CUB shape the whole head costs tens of microseconds on a B200, i.e. it is launch-bound from Python; the
+idiomatic B200 answer is to record the step once (forward + PPC loss + cross-entropy + backward, ~20 kernels) and
+replay it.  The step goes through exactly the public operators of ``ops`` (nothing is bypassed), reads its inputs
+from static device buffers ("slots") and leaves its results in static tensors:
+
+    step = GraphedHeadStep(params, cfg, B=64, N=196, C=200, m=10, n_slots=2)
+    step.load(slot, tokens, scores, labels)      # device or pinned-host tensors -> async copy into the slot
+    step.run(slot)                               # replay
+    step.loss[slot], step.logits[slot], step.dtokens[slot], param.grad (views of step.reducer.flat)
+
+Reference call sites this mirrors: tools/engine_proto.py:49-66 (forward, CE, get_PPC_loss, weighted sum) and :76
+(backward).  The optimizer step and the backbone are outside this path.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .dist import FlatGradReducer
+
+
+class GraphedHeadStep:
+    def __init__(self, params: dict, cfg: ops.HeadConfig, B: int, N: int, C: int, m: int, n_slots: int = 1,
+                 heads: int = 0, ppc_cov_coe: float = 0.1, ppc_mean_coe: float = 0.5, train: bool = True,
+                 process_group=None, device=None):
+        """params: dict with Wa (D,Din), ba (D), P (P,D), Pg (Pg,D) [leaf tensors, requires_grad in training] and
+        the frozen Wl (C,P), Wg (C,Pg).  ppc_*_coe follow scripts/train_cub.sh:43-44."""
+        self.p, self.cfg, self.B, self.N, self.C, self.m = params, cfg, B, N, C, m
+        self.train = train
+        self.cov_coe, self.mean_coe = ppc_cov_coe, ppc_mean_coe
+        dev = device or params["P"].device
+        Din = params["Wa"].shape[1]
+        sshape = (B, heads, N) if heads > 0 else (B, N)
+        self.tokens = [torch.zeros(B, 1 + N, Din, device=dev, requires_grad=train) for _ in range(n_slots)]
+        self.scores = [torch.zeros(sshape, device=dev) for _ in range(n_slots)]
+        self.labels = [torch.zeros(B, dtype=torch.int64, device=dev) for _ in range(n_slots)]
+        self.loss = [None] * n_slots
+        self.logits = [None] * n_slots
+        self.ppc = [None] * n_slots
+        self.dtokens = [None] * n_slots
+        self.graphs = [None] * n_slots
+        self.reducer = None
+        if train:
+            named = [(k, params[k]) for k in ("P", "Pg", "Wa", "ba")]
+            self.reducer = FlatGradReducer(named, process_group)
+        self.kernel_launches_per_step = 0
+
+    # --------------------------------------------------------------------------------------------------------
+    def _step(self, slot: int):
+        p, cfg = self.p, self.cfg
+        tok = self.tokens[slot]
+        if self.train:
+            self.reducer.zero()
+            tok.grad = None
+        out = ops.head_forward(cfg, tok, self.scores[slot], p["Wa"], p["ba"], p["P"], p["Pg"], p["Wl"], p["Wg"])
+        self.logits[slot] = out.logits
+        if not self.train:
+            self.loss[slot] = F.cross_entropy(out.logits, self.labels[slot])
+            return
+        cov, mean = ops.ppc_loss(cfg, out.tf, p["P"], out.p2l, self.labels[slot], self.m, self.N)
+        loss = F.cross_entropy(out.logits, self.labels[slot]) + self.cov_coe * cov + self.mean_coe * mean
+        loss.backward()
+        self.loss[slot] = loss.detach()
+        self.ppc[slot] = (cov.detach(), mean.detach())
+        self.dtokens[slot] = tok.grad
+
+    def capture(self, warmup: int = 3):
+        from . import _lib
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        ctx = torch.enable_grad() if self.train else torch.no_grad()
+        with ctx:
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    self._step(0)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            pool = None
+            for slot in range(len(self.tokens)):
+                g = torch.cuda.CUDAGraph()
+                n0 = _lib.launch_count()
+                with torch.cuda.graph(g, pool=pool):
+                    self._step(slot)
+                self.kernel_launches_per_step = _lib.launch_count() - n0
+                pool = g.pool()
+                self.graphs[slot] = g
+        return self
+
+    # --------------------------------------------------------------------------------------------------------
+    def load(self, slot: int, tokens, scores, labels):
+        """Asynchronous copy of one batch into the slot (host tensors should be pinned)."""
+        with torch.no_grad():
+            self.tokens[slot].copy_(tokens, non_blocking=True)
+            self.scores[slot].copy_(scores, non_blocking=True)
+            self.labels[slot].copy_(labels, non_blocking=True)
+
+    def run(self, slot: int = 0):
+        self.graphs[slot].replay()
+        return self.loss[slot]
+
+    def allreduce_grads(self):
+        if self.reducer is not None:
+            self.reducer.allreduce()

@@ -25,6 +25,7 @@ class HeadConfig:
     mode: str = "fp32"            # 'fp32' (= bf16x3 on tcgen05) | 'bf16' | 'fp32_fma'
     ppc_cov_thresh: float = 1.0
     ppc_mean_thresh: float = 2.0
+    center: float = 0.5           # tensor-core operands are taken from (z - center), (p - center); see protohead.h
 
     @property
     def mode_id(self) -> int:
@@ -70,7 +71,8 @@ def select_topk(scores: torch.Tensor, K: int, want_int64: bool = False):
 class _Addon(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
-    def forward(ctx, tokens, idx32, Wa, ba, want_split):
+    def forward(ctx, tokens, idx32, Wa, ba, want_split, center):
+        ctx.set_materialize_grads(False)
         tokens, Wa, ba = tokens.contiguous(), Wa.contiguous(), ba.contiguous()
         B, n1, Din = tokens.shape
         N, K, D = n1 - 1, idx32.shape[1], Wa.shape[0]
@@ -78,16 +80,17 @@ class _Addon(torch.autograd.Function):
         Zs, Zc = _empty((B, K, D), f32, tokens), _empty((B, D), f32, tokens)
         z2s, z2c = _empty((B, K), f32, tokens), _empty((B,), f32, tokens)
         if want_split:
+            z2s_ctr, z2c_ctr = _empty((B, K), f32, tokens), _empty((B,), f32, tokens)
             z2s_hi, z2c_hi = _empty((B, K), f32, tokens), _empty((B,), f32, tokens)
             Zs_hi, Zs_lo = _empty((B * K, D), bf, tokens), _empty((B * K, D), bf, tokens)
             Zc_hi, Zc_lo = _empty((B, D), bf, tokens), _empty((B, D), bf, tokens)
         else:
-            z2s_hi = z2c_hi = Zs_hi = Zs_lo = Zc_hi = Zc_lo = None
-        _lib.call("pph_addon_fwd", tokens, idx32, Wa, ba, B, N, Din, D, K, Zs, Zc, z2s, z2c, z2s_hi, z2c_hi,
-                  Zs_hi, Zs_lo, Zc_hi, Zc_lo)
+            z2s_ctr = z2c_ctr = z2s_hi = z2c_hi = Zs_hi = Zs_lo = Zc_hi = Zc_lo = None
+        _lib.call("pph_addon_fwd", tokens, idx32, Wa, ba, B, N, Din, D, K, Zs, Zc, z2s, z2c, float(center),
+                  z2s_ctr, z2c_ctr, z2s_hi, z2c_hi, Zs_hi, Zs_lo, Zc_hi, Zc_lo)
         ctx.save_for_backward(tokens, idx32, Wa, Zs, Zc)
         ctx.dims = (B, N, Din, D, K)
-        aux = [z2s, z2c, z2s_hi, z2c_hi, Zs_hi, Zs_lo, Zc_hi, Zc_lo]
+        aux = [z2s, z2c, z2s_ctr, z2c_ctr, z2s_hi, z2c_hi, Zs_hi, Zs_lo, Zc_hi, Zc_lo]
         aux = [a if a is not None else _empty((0,), f32, tokens) for a in aux]
         ctx.mark_non_differentiable(*aux)
         return (Zs, Zc, *aux)
@@ -102,7 +105,7 @@ class _Addon(torch.autograd.Function):
         dWa, dba = torch.empty_like(Wa), _empty((D,), torch.float32, Wa)
         dtok = torch.empty_like(tokens) if ctx.needs_input_grad[0] else None
         _lib.call("pph_addon_bwd", tokens, idx32, Wa, Zs, Zc, dZs, dZc, B, N, Din, D, K, dWa, dba, dtok)
-        return dtok, None, dWa, dba, None
+        return dtok, None, dWa, dba, None, None
 
 
 @dataclasses.dataclass
@@ -111,9 +114,11 @@ class TokenFeatures:
 
     Zs: torch.Tensor            # (B,K,D)
     Zc: torch.Tensor            # (B,D)
-    z2s: torch.Tensor           # (B,K)
+    z2s: torch.Tensor           # (B,K)  |z|^2
     z2c: torch.Tensor           # (B,)
-    z2s_hi: torch.Tensor | None
+    z2s_ctr: torch.Tensor | None   # |z - center|^2            (BF16X3 mode)
+    z2c_ctr: torch.Tensor | None
+    z2s_hi: torch.Tensor | None    # |bf16(z - center)|^2      (BF16 mode)
     z2c_hi: torch.Tensor | None
     Zs_hi: torch.Tensor | None  # (B*K,D) bf16
     Zs_lo: torch.Tensor | None
@@ -122,14 +127,14 @@ class TokenFeatures:
     idx32: torch.Tensor         # (B,K)
 
 
-def addon(tokens, idx32, Wa, ba, want_split: bool) -> TokenFeatures:
+def addon(tokens, idx32, Wa, ba, want_split: bool, center: float = 0.5) -> TokenFeatures:
     """tokens (B,1+N,Din), idx32 (B,K), Wa (D,Din) or (D,Din,1,1), ba (D)."""
     Wa2 = Wa.reshape(Wa.shape[0], -1)
-    out = _Addon.apply(tokens, idx32, Wa2, ba, want_split)
-    Zs, Zc, z2s, z2c, z2s_hi, z2c_hi, Zs_hi, Zs_lo, Zc_hi, Zc_lo = out
+    out = _Addon.apply(tokens, idx32, Wa2, ba, want_split, center)
+    Zs, Zc, z2s, z2c, z2s_ctr, z2c_ctr, z2s_hi, z2c_hi, Zs_hi, Zs_lo, Zc_hi, Zc_lo = out
     if not want_split:
-        z2s_hi = z2c_hi = Zs_hi = Zs_lo = Zc_hi = Zc_lo = None
-    return TokenFeatures(Zs, Zc, z2s, z2c, z2s_hi, z2c_hi, Zs_hi, Zs_lo, Zc_hi, Zc_lo, idx32)
+        z2s_ctr = z2c_ctr = z2s_hi = z2c_hi = Zs_hi = Zs_lo = Zc_hi = Zc_lo = None
+    return TokenFeatures(Zs, Zc, z2s, z2c, z2s_ctr, z2c_ctr, z2s_hi, z2c_hi, Zs_hi, Zs_lo, Zc_hi, Zc_lo, idx32)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -138,13 +143,14 @@ def addon(tokens, idx32, Wa, ba, want_split: bool) -> TokenFeatures:
 @dataclasses.dataclass
 class ProtoOperands:
     P: torch.Tensor                 # (R,D) fp32 (detached, contiguous)
-    p2: torch.Tensor                # (R,)
-    p2_hi: torch.Tensor | None
+    p2: torch.Tensor                # (R,)  |p|^2
+    p2_ctr: torch.Tensor | None     # |p - center|^2
+    p2_hi: torch.Tensor | None      # |bf16(p - center)|^2
     hi: torch.Tensor | None         # (R,D) bf16
     lo: torch.Tensor | None
 
 
-def prepare_prototypes(P2d: torch.Tensor, want_split: bool) -> ProtoOperands:
+def prepare_prototypes(P2d: torch.Tensor, want_split: bool, center: float = 0.5) -> ProtoOperands:
     P = P2d.detach()
     if P.dtype != torch.float32:
         P = P.float()
@@ -153,11 +159,11 @@ def prepare_prototypes(P2d: torch.Tensor, want_split: bool) -> ProtoOperands:
     p2 = _empty((R,), torch.float32, P)
     if want_split:
         hi, lo = _empty((R, D), torch.bfloat16, P), _empty((R, D), torch.bfloat16, P)
-        p2_hi = _empty((R,), torch.float32, P)
+        p2_ctr, p2_hi = _empty((R,), torch.float32, P), _empty((R,), torch.float32, P)
     else:
-        hi = lo = p2_hi = None
-    _lib.call("pph_split_rows", P, R, D, hi, lo, p2, p2_hi)
-    return ProtoOperands(P, p2, p2_hi, hi, lo)
+        hi = lo = p2_ctr = p2_hi = None
+    _lib.call("pph_split_rows", P, R, D, float(center), hi, lo, p2, p2_ctr, p2_hi)
+    return ProtoOperands(P, p2, p2_ctr, p2_hi, hi, lo)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -178,11 +184,12 @@ def _similarity_raw(cfg: HeadConfig, tf: TokenFeatures, pl: ProtoOperands, pg: P
     if want_maps:
         assert mode == _lib.MODE_FP32_FMA
         dist_map, act_map = _empty((B, P, K), f32, Zs), _empty((B, P, K), f32, Zs)
-    rounded = mode == _lib.MODE_BF16          # single-pass bf16: norms of the rounded operands
+    # norms must match the operands the mode contracts: plain (FP32_FMA), centred fp32 (BF16X3), centred rounded (BF16)
+    sel = {_lib.MODE_FP32_FMA: lambda a, b, c: a, _lib.MODE_BF16X3: lambda a, b, c: b, _lib.MODE_BF16: lambda a, b, c: c}[mode]
     _lib.call("pph_similarity_fwd", mode, cfg.act_id, float(cfg.eps), B, K, D, P, Pg,
-              Zs, tf.Zc.detach(), tf.z2s_hi if rounded else tf.z2s, tf.z2c_hi if rounded else tf.z2c,
+              Zs, tf.Zc.detach(), sel(tf.z2s, tf.z2s_ctr, tf.z2s_hi), sel(tf.z2c, tf.z2c_ctr, tf.z2c_hi),
               tf.Zs_hi, tf.Zs_lo, tf.Zc_hi, tf.Zc_lo,
-              pl.P, pg.P, pl.p2_hi if rounded else pl.p2, pg.p2_hi if rounded else pg.p2,
+              pl.P, pg.P, sel(pl.p2, pl.p2_ctr, pl.p2_hi), sel(pg.p2, pg.p2_ctr, pg.p2_hi),
               pl.hi, pl.lo, pg.hi, pg.lo,
               dmin_l, argmin, act_l, dmin_g, act_g, dist_map, act_map)
     return dmin_l, argmin, act_l, dmin_g, act_g, dist_map, act_map
@@ -194,8 +201,10 @@ class _SimilarityLogits(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, Zs, Zc, P2d, Pg2d, Wl, Wg, tf, cfg):
+        ctx.set_materialize_grads(False)
         want_split = cfg.mode_id != _lib.MODE_FP32_FMA
-        pl, pg = prepare_prototypes(P2d, want_split), prepare_prototypes(Pg2d, want_split)
+        pl = prepare_prototypes(P2d, want_split, cfg.center)
+        pg = prepare_prototypes(Pg2d, want_split, cfg.center)
         dmin_l, argmin, act_l, dmin_g, act_g, _, _ = _similarity_raw(cfg, tf, pl, pg)
         B, P = act_l.shape
         Pg, C = act_g.shape[1], Wl.shape[0]
@@ -254,7 +263,7 @@ def head_forward(cfg: HeadConfig, tokens, scores, Wa, ba, P, Pg, Wl, Wg) -> Head
         return _empty_head_output(cfg, tokens, Wa, P, Pg, Wl)
     idx32 = select_topk(scores, cfg.K)
     want_split = cfg.mode_id != _lib.MODE_FP32_FMA
-    tf = addon(tokens, idx32, Wa, ba, want_split)
+    tf = addon(tokens, idx32, Wa, ba, want_split, cfg.center)
     P2d, Pg2d = P.reshape(P.shape[0], -1), Pg.reshape(Pg.shape[0], -1)
     out = _SimilarityLogits.apply(tf.Zs, tf.Zc, P2d, Pg2d, Wl, Wg, tf, cfg)
     logits, lg, ll, act_l, act_g, dmin_l, dmin_g, argmin, p2l = out
@@ -266,7 +275,7 @@ def _empty_head_output(cfg, tokens, Wa, P, Pg, Wl) -> HeadOutput:
     f32, dev = torch.float32, tokens.device
     D, Pn, Pgn, C = Wa.shape[0], P.shape[0], Pg.shape[0], Wl.shape[0]
     z = lambda *s, dt=f32: torch.zeros(s, dtype=dt, device=dev)  # noqa: E731
-    tf = TokenFeatures(z(0, cfg.K, D), z(0, D), z(0, cfg.K), z(0), None, None, None, None, None, None,
+    tf = TokenFeatures(z(0, cfg.K, D), z(0, D), z(0, cfg.K), z(0), None, None, None, None, None, None, None, None,
                        z(0, cfg.K, dt=torch.int32))
     return HeadOutput(z(0, C), z(0, C), z(0, C), z(0, Pn), z(0, Pgn), z(0, Pn), z(0, Pgn), z(0, Pn, dt=torch.int32),
                       z(Pn), tf)
@@ -288,6 +297,7 @@ class _PPC(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda", cast_inputs=torch.float32)
     def forward(ctx, Zs, P2d, z2s, p2l, idx32, labels, m, N, cfg):
+        ctx.set_materialize_grads(False)
         Zs, Pl = Zs.contiguous(), P2d.contiguous()
         B, K, D = Zs.shape
         P = Pl.shape[0]
