@@ -115,13 +115,16 @@ int pph_ppc_fwd(const float* Zs, const float* z2s, const float* Pl, const float*
                 float cov_thresh, float mean_thresh,
                 float* dslice, float* stats, float* partial, uint32_t* counter, float* losses, pph_stream_t stream);
 
-/* backward of pph_ppc_fwd.  g_losses [2] = upstream gradients of (cov, mean) (device).
- * dZs [B,K,D] is OVERWRITTEN with the PPC contribution; dP [P,D] must be zero-filled by the caller and is
- * accumulated with atomics (several images may share a label). */
+/* backward of pph_ppc_fwd.  Upstream gradients of (cov, mean): g_losses[2] (device, may be NULL = 1) multiplied by
+ * the host scalars g_scale_cov / g_scale_mean (e.g. the loss coefficients of engine_proto.py:61-64).
+ * accumulate = 0: dZs [B,K,D] is OVERWRITTEN with the PPC contribution and dP [P,D] must be zero-filled by the
+ * caller (rows of shared labels are added atomically).  accumulate = 1: the contribution is ADDED to dZs / dP that
+ * already hold the similarity gradients (fused training step: no extra buffers, no extra add kernels). */
 int pph_ppc_bwd(const float* Zs, const float* Pl, const int32_t* idx32, const int64_t* labels,
                 const float* dslice, const float* stats, const float* g_losses,
+                float g_scale_cov, float g_scale_mean,
                 int B, int K, int D, int P, int m, int N, int act_fn, float eps,
-                float cov_thresh, float mean_thresh,
+                float cov_thresh, float mean_thresh, int accumulate,
                 float* dZs, float* dP, pph_stream_t stream);
 
 /* (a8, part 1) autograd of protopformer.py:297-300 and :228-244 collapsed to one scalar per (b,p):
@@ -136,10 +139,13 @@ int pph_logits_bwd(const float* dlogits, const float* dlogits_g, const float* dl
 /* (a8, part 2) max-pool routing + distance backward:
  *   dPl[p,:]   = 2 * sum_b g_l[b,p] * (Pl[p,:] - Zs[b,argmin[b,p],:])      dPg[p,:] = 2 * sum_b g_g[b,p] * (Pg[p,:] - Zc[b,:])
  *   dZs[b,k,:] = 2 * sum_{p: argmin[b,p]=k} g_l[b,p] * (Zs[b,k,:] - Pl[p,:])   dZc[b,:] = 2 * sum_p g_g[b,p] * (Zc[b,:] - Pg[p,:])
- * All four outputs are OVERWRITTEN. */
+ * All four outputs are OVERWRITTEN; every row is summed in a fixed order (bit-reproducible).
+ * `workspace`: caller-owned device scratch of pph_similarity_bwd_ws_bytes() bytes, ZERO-FILLED once before its
+ * first use (it holds the token bins and self-resetting counters). */
+int pph_similarity_bwd_ws_bytes(int B, int K, int D, int P, int Pg, long long* bytes /* host */);
 int pph_similarity_bwd(const float* g_l, const float* g_g, const int32_t* argmin_l,
                        const float* Zs, const float* Zc, const float* Pl, const float* Pgl,
-                       int B, int K, int D, int P, int Pg,
+                       int B, int K, int D, int P, int Pg, void* workspace,
                        float* dZs, float* dZc, float* dPl, float* dPg, pph_stream_t stream);
 
 /* (a8, part 3) backward of pph_addon_fwd: dpre = dZ * Z * (1-Z);  dWa = dpre^T X_sel;  dba = sum dpre;
@@ -149,6 +155,14 @@ int pph_addon_bwd(const float* tokens, const int32_t* idx32, const float* Wa,
                   const float* Zs, const float* Zc, const float* dZs, const float* dZc,
                   int B, int N, int Din, int D, int K,
                   float* dWa, float* dba, float* dtokens, pph_stream_t stream);
+
+/* loss tail adjacent to the head (engine_proto.py:51, 61-64): ce = CrossEntropy(logits, labels) (mean over B),
+ * out_losses[4] = (ce + cov_coe*ppc[0] + mean_coe*ppc[1], ce, ppc[0], ppc[1]) and
+ * dlogits [B,C] = (softmax - onehot) / B * upstream   (NULL: forward only).  ppc_losses [2] may be NULL (= 0).
+ * partial [B] and counter [1] (zero before first use, self-resetting) are scratch. */
+int pph_loss_tail(const float* logits, const int64_t* labels, const float* ppc_losses,
+                  float cov_coe, float mean_coe, float upstream, int B, int C,
+                  float* partial, uint32_t* counter, float* out_losses, float* dlogits, pph_stream_t stream);
 
 #ifdef __cplusplus
 }

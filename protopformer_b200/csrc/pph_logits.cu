@@ -1,98 +1,139 @@
 // (a6) prototype-to-class last layers + global/local combine (protopformer.py:297-300, 314-316) and the first
 // step of their backward, collapsed with the similarity derivative into one scalar per (image, prototype).
 // The last layers are frozen in the reference (protopformer.py:130-131) -> no weight gradient is produced.
-// FP32 FMA on the CUDA cores through the generic tile GEMM; local and global branches share one launch.
+//
+// Both are skinny FP32 contractions (B x C x (P+Pg) with B = 64): too small for a tensor-core tile grid, so they are
+// laid out for L2 traffic and determinism instead:
+//   forward : CTA = 8 images x 8 classes, the 256 threads split the prototype axis (coalesced row reads), 64
+//             register accumulators per thread, one block reduction -> every logit has ONE writer (deterministic).
+//   backward: CTA = 64 images x 32 prototypes, contraction over the C classes from shared memory, 2x4 register tile.
 #include "pph_common.cuh"
-#include "pph_sgemm.cuh"
 
 namespace pph {
 
-// ---- forward ---------------------------------------------------------------------------------------------------
-// contraction index k runs over [0,Plpad) = local prototypes (zero padded to a split boundary), then the global ones
-struct ActConcatOp {
-    static constexpr bool kContigK = true;
-    const float *l, *g;
-    int rows, Kl, Klpad, Kg;
-    __device__ __forceinline__ float operator()(int row, int k) const {
-        if (row >= rows) return 0.f;
-        if (k < Klpad) return k < Kl ? __ldg(l + (size_t)row * Kl + k) : 0.f;
-        const int kk = k - Klpad;
-        return kk < Kg ? __ldg(g + (size_t)row * Kg + kk) : 0.f;
-    }
-};
+constexpr int kLogThreads = 256;
+constexpr int kLogTB = 8, kLogTC = 8;
 
-struct LogitsEpi {
-    float *logits, *logits_g, *logits_l;
-    int C, Klpad, k_per_split;
-    float gc;
-    __device__ __forceinline__ void operator()(int b, int c, float acc, float) const {
-        const bool global = (int)blockIdx.z * k_per_split >= Klpad;
-        const size_t o = (size_t)b * C + c;
-        if (global) {
-            atomicAdd(logits_g + o, acc);
-            atomicAdd(logits + o, gc * acc);
-        } else {
-            atomicAdd(logits_l + o, acc);
-            atomicAdd(logits + o, (1.0f - gc) * acc);
+__global__ void __launch_bounds__(kLogThreads)
+logits_fwd_kernel(const float* __restrict__ act_l, const float* __restrict__ act_g, const float* __restrict__ Wl,
+                  const float* __restrict__ Wg, int B, int P, int Pg, int C, float gc,
+                  float* __restrict__ logits, float* __restrict__ logits_g, float* __restrict__ logits_l) {
+    __shared__ float red[kLogThreads / 32][kLogTB * kLogTC];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int b0 = blockIdx.y * kLogTB, c0 = blockIdx.x * kLogTC;
+    float res[2] = {0.f, 0.f};      // this thread's (b,c) output: local, global   (thread tid < 64 owns output tid)
+    for (int branch = 0; branch < 2; ++branch) {
+        const float* A = branch ? act_g : act_l;
+        const float* W = branch ? Wg : Wl;
+        const int Kd = branch ? Pg : P;
+        float acc[kLogTB][kLogTC];
+#pragma unroll
+        for (int i = 0; i < kLogTB; ++i)
+#pragma unroll
+            for (int j = 0; j < kLogTC; ++j) acc[i][j] = 0.f;
+        for (int p = tid; p < Kd; p += kLogThreads) {
+            float a[kLogTB], w[kLogTC];
+#pragma unroll
+            for (int i = 0; i < kLogTB; ++i) a[i] = (b0 + i < B) ? __ldg(A + (size_t)(b0 + i) * Kd + p) : 0.f;
+#pragma unroll
+            for (int j = 0; j < kLogTC; ++j) w[j] = (c0 + j < C) ? __ldg(W + (size_t)(c0 + j) * Kd + p) : 0.f;
+#pragma unroll
+            for (int i = 0; i < kLogTB; ++i)
+#pragma unroll
+                for (int j = 0; j < kLogTC; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+        // block reduction of the 64 accumulators: warp shuffles, then a fixed-order sum over the 8 warps
+#pragma unroll
+        for (int i = 0; i < kLogTB; ++i)
+#pragma unroll
+            for (int j = 0; j < kLogTC; ++j) {
+                const float v = warp_sum(acc[i][j]);
+                if (lane == 0) red[warp][i * kLogTC + j] = v;
+            }
+        __syncthreads();
+        if (tid < kLogTB * kLogTC) {
+            float s = 0.f;
+#pragma unroll
+            for (int w = 0; w < kLogThreads / 32; ++w) s += red[w][tid];
+            res[branch] = s;
+        }
+        __syncthreads();
+    }
+    if (tid < kLogTB * kLogTC) {
+        const int b = b0 + tid / kLogTC, c = c0 + tid % kLogTC;
+        if (b < B && c < C) {
+            const size_t o = (size_t)b * C + c;
+            logits_l[o] = res[0];
+            logits_g[o] = res[1];
+            logits[o] = gc * res[1] + (1.0f - gc) * res[0];
         }
     }
-};
-
-__global__ void zero3_kernel(float* a, float* b, float* c, int n) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) { a[i] = 0.f; b[i] = 0.f; c[i] = 0.f; }
 }
 
-// ---- backward --------------------------------------------------------------------------------------------------
-// output column n runs over [0,Plpad) = local prototypes (padded to the tile width), then the global ones
-struct UpstreamOp {     // (row = b, k = c): upstream gradient of the branch this CTA's columns belong to
-    static constexpr bool kContigK = true;
-    const float *dlogits, *dlogits_g, *dlogits_l;
-    int rows, C, Plpad;
-    float gc;
-    __device__ __forceinline__ float operator()(int b, int c) const {
-        if (b >= rows || c >= C) return 0.f;
-        const bool global = (int)blockIdx.x * kGemmBN >= Plpad;
-        const size_t o = (size_t)b * C + c;
-        float v = (global ? gc : 1.0f - gc) * __ldg(dlogits + o);
-        const float* extra = global ? dlogits_g : dlogits_l;
-        if (extra) v += __ldg(extra + o);
-        return v;
-    }
-};
+// g[b,p] = (coef * sum_c dlogits[b,c] W[c,p] + sum_c extra[b,c] W[c,p]) * act'(dmin[b,p]) * [dmin > 0]
+constexpr int kLbTB = 64, kLbTP = 32, kLbCC = 64;   // images, prototypes per CTA; class chunk staged in smem
 
-struct LastLayerTOp {   // (row = n, k = c) -> W[c, p]
-    static constexpr bool kContigK = false;
-    const float *Wl, *Wg;
-    int P, Plpad, Pg, C;
-    __device__ __forceinline__ float operator()(int n, int c) const {
-        if (c >= C) return 0.f;
-        if (n < Plpad) return n < P ? __ldg(Wl + (size_t)c * P + n) : 0.f;
-        const int p = n - Plpad;
-        return p < Pg ? __ldg(Wg + (size_t)c * Pg + p) : 0.f;
-    }
-};
-
-struct RouteEpi {
-    const float *dmin_l, *dmin_g;
-    float *g_l, *g_g;
-    int P, Plpad, Pg, act_fn;
-    float eps;
-    __device__ __forceinline__ void operator()(int b, int n, float acc, float) const {
-        if (n < Plpad) {
-            if (n < P) {
-                const size_t o = (size_t)b * P + n;
-                g_l[o] = acc * dact_of_dist(__ldg(dmin_l + o), act_fn, eps);
+__global__ void __launch_bounds__(kLogThreads)
+logits_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ dlogits_g,
+                  const float* __restrict__ dlogits_l, const float* __restrict__ Wl, const float* __restrict__ Wg,
+                  const float* __restrict__ dmin_l, const float* __restrict__ dmin_g,
+                  int B, int P, int Pg, int C, int tiles_l, float gc, int act_fn, float eps,
+                  float* __restrict__ g_l, float* __restrict__ g_g) {
+    __shared__ __align__(16) float up[kLbCC][kLbTB + 2];     // upstream gradient chunk, transposed [c][b]
+    __shared__ __align__(16) float wt[kLbCC][kLbTP];         // last-layer chunk [c][p]
+    const int tid = threadIdx.x;
+    const bool global = (int)blockIdx.x >= tiles_l;
+    const int p0 = (global ? blockIdx.x - tiles_l : blockIdx.x) * kLbTP;
+    const int b0 = blockIdx.y * kLbTB;
+    const int np = global ? Pg : P;
+    const float* W = global ? Wg : Wl;
+    const float* extra = global ? dlogits_g : dlogits_l;
+    const float coef = global ? gc : 1.0f - gc;
+    const int tb = tid & 31, tp = tid >> 5;      // images 2*tb, 2*tb+1; prototypes 4*tp .. 4*tp+3
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    for (int cc = 0; cc < C; cc += kLbCC) {
+        for (int i = tid; i < kLbCC * kLbTB; i += kLogThreads) {
+            const int b = i / kLbCC, c = i - b * kLbCC;       // consecutive threads: consecutive classes (coalesced)
+            float v = 0.f;
+            if (b0 + b < B && cc + c < C) {
+                const size_t o = (size_t)(b0 + b) * C + cc + c;
+                v = coef * __ldg(dlogits + o);
+                if (extra) v += __ldg(extra + o);
             }
-        } else {
-            const int p = n - Plpad;
-            if (p < Pg) {
-                const size_t o = (size_t)b * Pg + p;
-                g_g[o] = acc * dact_of_dist(__ldg(dmin_g + o), act_fn, eps);
+            up[c][b] = v;
+        }
+        for (int i = tid; i < kLbCC * kLbTP; i += kLogThreads) {
+            const int c = i / kLbTP, p = i - c * kLbTP;
+            wt[c][p] = (cc + c < C && p0 + p < np) ? __ldg(W + (size_t)(cc + c) * np + p0 + p) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int c = 0; c < kLbCC; ++c) {
+            const float2 u = *reinterpret_cast<const float2*>(&up[c][2 * tb]);
+            const float4 w = *reinterpret_cast<const float4*>(&wt[c][4 * tp]);
+            acc[0][0] = fmaf(u.x, w.x, acc[0][0]); acc[0][1] = fmaf(u.x, w.y, acc[0][1]);
+            acc[0][2] = fmaf(u.x, w.z, acc[0][2]); acc[0][3] = fmaf(u.x, w.w, acc[0][3]);
+            acc[1][0] = fmaf(u.y, w.x, acc[1][0]); acc[1][1] = fmaf(u.y, w.y, acc[1][1]);
+            acc[1][2] = fmaf(u.y, w.z, acc[1][2]); acc[1][3] = fmaf(u.y, w.w, acc[1][3]);
+        }
+        __syncthreads();
+    }
+    const float* dmin = global ? dmin_g : dmin_l;
+    float* g = global ? g_g : g_l;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int b = b0 + 2 * tb + i;
+        if (b >= B) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int p = p0 + 4 * tp + j;
+            if (p < np) {
+                const size_t o = (size_t)b * np + p;
+                g[o] = acc[i][j] * dact_of_dist(__ldg(dmin + o), act_fn, eps);
             }
         }
     }
-};
+}
 
 }  // namespace pph
 
@@ -104,21 +145,9 @@ extern "C" int pph_logits_fwd(const float* act_l, const float* act_g, const floa
                 "pph_logits_fwd: null pointer");
     PPH_REQUIRE(B >= 0 && P >= 1 && Pg >= 0 && C >= 1, PPH_EINVAL, "pph_logits_fwd: bad dims");
     if (B == 0) return 0;
-    cudaStream_t st = as_stream(stream);
-    const int n = B * C;
-    zero3_kernel<<<ceil_div(n, 256), 256, 0, st>>>(logits, logits_g, logits_l, n);
-    // split the contraction so ~2 waves of CTAs exist; local part padded to a split boundary
-    const int tiles = ceil_div(B, kGemmBM) * ceil_div(C, kGemmBN);
-    int want = ceil_div(2 * 148, tiles);
-    int k_per_split = ceil_div(ceil_div(P + Pg, want), kGemmBK) * kGemmBK;
-    if (k_per_split < 4 * kGemmBK) k_per_split = 4 * kGemmBK;
-    const int Klpad = ceil_div(P, k_per_split) * k_per_split;
-    const int Ktot = Klpad + Pg;
-    ActConcatOp a{act_l, act_g, B, P, Klpad, Pg};
-    ActConcatOp w{Wl, Wg, C, P, Klpad, Pg};
-    LogitsEpi epi{logits, logits_g, logits_l, C, Klpad, k_per_split, global_coe};
-    dim3 grid(ceil_div(C, kGemmBN), ceil_div(B, kGemmBM), ceil_div(Ktot, k_per_split));
-    sgemm_kernel<false><<<grid, kGemmThreads, 0, st>>>(B, C, Ktot, k_per_split, a, w, epi);
+    dim3 grid(ceil_div(C, kLogTC), ceil_div(B, kLogTB));
+    logits_fwd_kernel<<<grid, kLogThreads, 0, as_stream(stream)>>>(act_l, act_g, Wl, Wg, B, P, Pg, C, global_coe,
+                                                                  logits, logits_g, logits_l);
     return launch_status("pph_logits_fwd");
 }
 
@@ -131,10 +160,10 @@ extern "C" int pph_logits_bwd(const float* dlogits, const float* dlogits_g, cons
                 "pph_logits_bwd: null pointer");
     PPH_REQUIRE(B >= 0 && P >= 1 && Pg >= 0 && C >= 1, PPH_EINVAL, "pph_logits_bwd: bad dims");
     if (B == 0) return 0;
-    const int Plpad = ceil_div(P, kGemmBN) * kGemmBN;
-    UpstreamOp a{dlogits, dlogits_g, dlogits_l, B, C, Plpad, global_coe};
-    LastLayerTOp w{Wl, Wg, P, Plpad, Pg, C};
-    RouteEpi epi{dmin_l, dmin_g, g_l, g_g, P, Plpad, Pg, act_fn, eps};
-    launch_sgemm<false>(B, Plpad + Pg, C, 1, a, w, epi, as_stream(stream));
+    const int tiles_l = ceil_div(P, kLbTP), tiles_g = Pg > 0 ? ceil_div(Pg, kLbTP) : 0;
+    dim3 grid(tiles_l + tiles_g, ceil_div(B, kLbTB));
+    logits_bwd_kernel<<<grid, kLogThreads, 0, as_stream(stream)>>>(dlogits, dlogits_g, dlogits_l, Wl, Wg, dmin_l,
+                                                                  dmin_g, B, P, Pg, C, tiles_l, global_coe, act_fn,
+                                                                  eps, g_l, g_g);
     return launch_status("pph_logits_bwd");
 }

@@ -8,8 +8,11 @@
 //   mu_j    = sum_k w pos_k / S_j;   V_j = sum_k w (pos_k - mu_j)^2 / S_j   (per coordinate);  var_j = V_j N/(N-1)
 //   L_cov   = mean_{b,j} relu((var_r + var_c)/2 - cov_thresh)
 //   L_mean  = mean_{b,i,j} relu(mean_thresh - |mu_i - mu_j|) [i != j]     (diagonal zeros stay in the denominator)
-// HBM traffic per image: K*D*4 (token features, L2-resident after the add-on kernel) + m*D*4 + K*4 in,
-// m*K*4 + m*32 out -- a latency-bound kernel; loads are coalesced 128B rows.
+//
+// Layout: the image's K token rows are staged once in shared memory (row stride D+4 floats: 128-bit reads by
+// consecutive tokens hit distinct bank groups), the m label-class prototype rows next to them; thread = (token,
+// prototype group) for the distance slice, warp = prototype for the statistics.  HBM/L2 traffic per image:
+// K*D*4 + m*D*4 + K*4 B in, m*K*4 + m*32 B out -- latency bound; all global loads are 128-bit and coalesced.
 #include <math.h>
 
 #include "pph_common.cuh"
@@ -31,43 +34,80 @@ __device__ __forceinline__ float block_sum_256(float v, float* red) {
     return s;
 }
 
+struct PpcSmem {
+    float *Prow, *Zt, *dsl, *wbuf, *st;
+    int zstride;
+};
+
+__device__ __forceinline__ PpcSmem ppc_carve(float* sm, int m, int D, int K, int kc) {
+    PpcSmem s;
+    s.zstride = D + 4;
+    s.Prow = sm;                                 // [m][D]
+    s.Zt = s.Prow + m * D;                       // [kc][D+4]
+    s.dsl = s.Zt + (size_t)kc * s.zstride;       // [m][K]  distances (fwd) / d loss / d distance (bwd)
+    s.wbuf = s.dsl + m * K;                      // [m][K]  activations
+    s.st = s.wbuf + m * K;                       // [m][8]
+    return s;
+}
+
+static size_t ppc_smem_bytes(int m, int D, int K, int kc) {
+    return sizeof(float) * ((size_t)m * D + (size_t)kc * (D + 4) + 2 * (size_t)m * K + 8 * (size_t)m);
+}
+
+// stage token rows [k0, k0+n) of image b into shared memory (float4, coalesced)
+__device__ __forceinline__ void ppc_stage_tokens(const float* __restrict__ Zb, float* Zt, int zstride, int D, int k0,
+                                                 int n) {
+    const int d4 = D >> 2;
+    for (int i = threadIdx.x; i < n * d4; i += kPpcThreads) {
+        const int r = i / d4, c = i - r * d4;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(Zb + (size_t)(k0 + r) * D) + c);
+        *reinterpret_cast<float4*>(Zt + (size_t)r * zstride + 4 * c) = v;
+    }
+}
+
 __global__ void __launch_bounds__(kPpcThreads)
 ppc_fwd_kernel(const float* __restrict__ Zs, const float* __restrict__ z2s, const float* __restrict__ Pl,
                const float* __restrict__ p2l, const int32_t* __restrict__ idx, const int64_t* __restrict__ labels,
-               int B, int K, int D, int P, int m, int N, int side, int act_fn, float eps,
+               int B, int K, int D, int P, int m, int N, int side, int kc, int act_fn, float eps,
                float cov_thresh, float mean_thresh,
                float* __restrict__ dslice, float* __restrict__ stats, float* partial, unsigned int* counter,
                float* __restrict__ losses) {
-    extern __shared__ float sm[];
-    float* Prow = sm;                 // [m][D]
-    float* dsl = Prow + m * D;        // [m][K]
-    float* mu = dsl + m * K;          // [m][2]
+    extern __shared__ __align__(16) float sm[];
+    const PpcSmem s = ppc_carve(sm, m, D, K, kc);
     __shared__ float red[kPpcThreads / 32];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = kPpcThreads / 32;
     long y = labels[b];
     if (y < 0) y = 0;
     if (y * m + m > P) y = P / m - 1;                 // out-of-range labels are clamped (the reference would raise)
     const int prow0 = (int)y * m;
-    for (int i = tid; i < m * D; i += kPpcThreads) Prow[i] = __ldg(Pl + (size_t)prow0 * D + i);
-    __syncthreads();
+    for (int i = tid; i < m * D / 4; i += kPpcThreads)
+        reinterpret_cast<float4*>(s.Prow)[i] = __ldg(reinterpret_cast<const float4*>(Pl + (size_t)prow0 * D) + i);
+    const float* Zb = Zs + (size_t)b * K * D;
 
-    // distances of the label-class prototypes to every selected token: one warp per token
-    for (int k = warp; k < K; k += nwarp) {
-        const float* zr = Zs + ((size_t)b * K + k) * D;
-        float z[kPpcMaxDV];
-#pragma unroll
-        for (int i = 0; i < kPpcMaxDV; ++i) z[i] = (i * 32 + lane < D) ? __ldg(zr + i * 32 + lane) : 0.f;
-        const float zz = __ldg(z2s + (size_t)b * K + k);
-        for (int j = 0; j < m; ++j) {
-            float dot = 0.f;
-#pragma unroll
-            for (int i = 0; i < kPpcMaxDV; ++i)
-                if (i * 32 < D) dot = fmaf(z[i], (i * 32 + lane < D) ? Prow[j * D + i * 32 + lane] : 0.f, dot);
-            dot = warp_sum(dot);
-            if (lane == 0) {
+    // distance slice: thread = (token, prototype group jg of JG); 128-bit shared reads, fp32 FMA
+    const int JG = kc * 3 <= kPpcThreads ? 3 : (kc * 2 <= kPpcThreads ? 2 : 1);
+    for (int k0 = 0; k0 < K; k0 += kc) {
+        const int n = min(kc, K - k0);
+        __syncthreads();
+        ppc_stage_tokens(Zb, s.Zt, s.zstride, D, k0, n);
+        __syncthreads();
+        for (int t = tid; t < n * JG; t += kPpcThreads) {
+            const int r = t % n, jg = t / n;
+            const float4* zr = reinterpret_cast<const float4*>(s.Zt + (size_t)r * s.zstride);
+            const float zz = __ldg(z2s + (size_t)b * K + k0 + r);
+            for (int j = jg; j < m; j += JG) {
+                const float4* pr = reinterpret_cast<const float4*>(s.Prow + (size_t)j * D);
+                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+                for (int c = 0; c < D / 4; ++c) {
+                    const float4 z = zr[c], p = pr[c];
+                    a0 = fmaf(z.x, p.x, a0); a1 = fmaf(z.y, p.y, a1); a2 = fmaf(z.z, p.z, a2); a3 = fmaf(z.w, p.w, a3);
+                }
+                const float dot = (a0 + a1) + (a2 + a3);
                 const float d = fmaxf(zz + fmaf(-2.0f, dot, __ldg(p2l + prow0 + j)), 0.0f);
-                dsl[j * K + k] = d;
-                dslice[((size_t)b * m + j) * K + k] = d;
+                s.dsl[j * K + k0 + r] = d;
+                s.wbuf[j * K + k0 + r] = act_of_dist(d, act_fn, eps);
+                dslice[((size_t)b * m + j) * K + k0 + r] = d;
             }
         }
     }
@@ -78,7 +118,7 @@ ppc_fwd_kernel(const float* __restrict__ Zs, const float* __restrict__ z2s, cons
     for (int j = warp; j < m; j += nwarp) {
         float S = 0.f, Sr = 0.f, Sc = 0.f;
         for (int k = lane; k < K; k += 32) {
-            const float w = act_of_dist(dsl[j * K + k], act_fn, eps);
+            const float w = s.wbuf[j * K + k];
             const int n = __ldg(idx + (size_t)b * K + k);
             S += w;
             Sr = fmaf(w, (float)(n / side), Sr);
@@ -88,7 +128,7 @@ ppc_fwd_kernel(const float* __restrict__ Zs, const float* __restrict__ z2s, cons
         const float mr = Sr / S, mc = Sc / S;
         float Vr = 0.f, Vc = 0.f;
         for (int k = lane; k < K; k += 32) {
-            const float w = act_of_dist(dsl[j * K + k], act_fn, eps);
+            const float w = s.wbuf[j * K + k];
             const int n = __ldg(idx + (size_t)b * K + k);
             const float dr = (float)(n / side) - mr, dc = (float)(n % side) - mc;
             Vr = fmaf(w, dr * dr, Vr);
@@ -99,19 +139,19 @@ ppc_fwd_kernel(const float* __restrict__ Zs, const float* __restrict__ z2s, cons
         const float scale = (float)N / (float)(N - 1);
         const float pre = (Vr * scale + Vc * scale) * 0.5f - cov_thresh;
         if (lane == 0) {
-            mu[2 * j] = mr; mu[2 * j + 1] = mc;
-            float* st = stats + ((size_t)b * m + j) * 8;
+            float* st = s.st + j * 8;
             st[0] = S; st[1] = mr; st[2] = mc; st[3] = Vr; st[4] = Vc; st[5] = pre; st[6] = 0.f; st[7] = 0.f;
             cov_sum += fmaxf(pre, 0.0f);
         }
     }
-    const float cov_img = block_sum_256(lane == 0 ? cov_sum : 0.f, red);   // includes the barrier that publishes mu[]
+    const float cov_img = block_sum_256(lane == 0 ? cov_sum : 0.f, red);   // includes the barrier that publishes st[]
+    for (int i = tid; i < m * 8; i += kPpcThreads) stats[(size_t)b * m * 8 + i] = s.st[i];
 
     float mean_sum = 0.f;
     for (int t = tid; t < m * m; t += kPpcThreads) {
         const int i = t / m, j = t - i * m;
         if (i != j) {
-            const float dr = mu[2 * i] - mu[2 * j], dc = mu[2 * i + 1] - mu[2 * j + 1];
+            const float dr = s.st[i * 8 + 1] - s.st[j * 8 + 1], dc = s.st[i * 8 + 2] - s.st[j * 8 + 2];
             mean_sum += fmaxf(mean_thresh - sqrtf(dr * dr + dc * dc), 0.0f);
         }
     }
@@ -125,38 +165,54 @@ ppc_fwd_kernel(const float* __restrict__ Zs, const float* __restrict__ z2s, cons
         const unsigned int ticket = atomicAdd(counter, 1u);
         if (ticket == (unsigned int)(B - 1)) {
             __threadfence();
-            float c = 0.f, s = 0.f;
+            float c = 0.f, sacc = 0.f;
             for (int i = 0; i < B; ++i) {
                 c += __ldcg(partial + 2 * i);
-                s += __ldcg(partial + 2 * i + 1);
+                sacc += __ldcg(partial + 2 * i + 1);
             }
             losses[0] = c / ((float)B * (float)m);
-            losses[1] = s / ((float)B * (float)m * (float)m);
+            losses[1] = sacc / ((float)B * (float)m * (float)m);
             *counter = 0u;          // ready for the next launch / graph replay
         }
     }
 }
 
-__global__ void __launch_bounds__(kPpcThreads)
+// backward.  accumulate = 0: dZs rows are overwritten, dP is expected zero-filled (atomicAdd).
+//            accumulate = 1: the PPC contribution is ADDED to dZs (one CTA owns its token rows: plain
+//                            read-modify-write) and atomically added to dP -- the caller has already written the
+//                            similarity gradients there.
+// Grid = (image, chunk of kPpcBwdTok tokens): many small CTAs instead of one serial CTA per image (latency bound).
+constexpr int kPpcBwdTok = 16, kPpcBwdThreads = 128;
+
+template <int DV>
+__global__ void __launch_bounds__(kPpcBwdThreads)
 ppc_bwd_kernel(const float* __restrict__ Zs, const float* __restrict__ Pl, const int32_t* __restrict__ idx,
                const int64_t* __restrict__ labels, const float* __restrict__ dslice, const float* __restrict__ stats,
-               const float* __restrict__ g_losses, int B, int K, int D, int P, int m, int N, int side,
-               int act_fn, float eps, float mean_thresh, float* __restrict__ dZs, float* __restrict__ dP) {
-    extern __shared__ float sm[];
-    float* Prow = sm;                 // [m][D]
-    float* dd = Prow + m * D;         // [m][K]   d loss / d distance
-    float* st = dd + m * K;           // [m][8]   stats, then [6],[7] <- d loss / d mu
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = kPpcThreads / 32;
+               const float* __restrict__ g_losses, float g_scale_cov, float g_scale_mean,
+               int B, int K, int D, int P, int m, int N, int side,
+               int act_fn, float eps, float mean_thresh, int accumulate, float* __restrict__ dZs,
+               float* __restrict__ dP) {
+    extern __shared__ __align__(16) float sm[];
+    float* Prow = sm;                         // [m][D]
+    float* Zt = Prow + m * D;                 // [kPpcBwdTok][D]
+    float* dd = Zt + kPpcBwdTok * D;          // [m][kPpcBwdTok]
+    float* st = dd + m * kPpcBwdTok;          // [m][8]
+    const int b = blockIdx.x, k0 = blockIdx.y * kPpcBwdTok, n = min(kPpcBwdTok, K - k0);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = kPpcBwdThreads / 32;
     long y = labels[b];
     if (y < 0) y = 0;
     if (y * m + m > P) y = P / m - 1;
     const int prow0 = (int)y * m;
-    for (int i = tid; i < m * D; i += kPpcThreads) Prow[i] = __ldg(Pl + (size_t)prow0 * D + i);
-    for (int i = tid; i < m * 8; i += kPpcThreads) st[i] = __ldg(stats + (size_t)b * m * 8 + i);
+    for (int i = tid; i < m * D / 4; i += kPpcBwdThreads)
+        reinterpret_cast<float4*>(Prow)[i] = __ldg(reinterpret_cast<const float4*>(Pl + (size_t)prow0 * D) + i);
+    for (int i = tid; i < n * D / 4; i += kPpcBwdThreads)
+        reinterpret_cast<float4*>(Zt)[i] = __ldg(reinterpret_cast<const float4*>(Zs + ((size_t)b * K + k0) * D) + i);
+    for (int i = tid; i < m * 8; i += kPpcBwdThreads) st[i] = __ldg(stats + (size_t)b * m * 8 + i);
     __syncthreads();
-    const float g_cov = __ldg(g_losses) / ((float)B * (float)m);
-    const float g_mean = __ldg(g_losses + 1) / ((float)B * (float)m * (float)m);
-
+    const float up_cov = g_losses ? __ldg(g_losses) * g_scale_cov : g_scale_cov;
+    const float up_mean = g_losses ? __ldg(g_losses + 1) * g_scale_mean : g_scale_mean;
+    const float g_cov = up_cov / ((float)B * (float)m);
+    const float g_mean = up_mean / ((float)B * (float)m * (float)m);
     // d loss / d mu_i from the pairwise term (both (i,j) and (j,i) depend on mu_i)
     if (tid < m) {
         const int i = tid;
@@ -175,61 +231,84 @@ ppc_bwd_kernel(const float* __restrict__ Zs, const float* __restrict__ Pl, const
     }
     __syncthreads();
     const float scale = (float)N / (float)(N - 1);
-    for (int t = tid; t < m * K; t += kPpcThreads) {
-        const int j = t / K, k = t - j * K;
+    for (int t = tid; t < m * n; t += kPpcBwdThreads) {
+        const int j = t / n, r = t - j * n;
         const float S = st[j * 8], mr = st[j * 8 + 1], mc = st[j * 8 + 2], Vr = st[j * 8 + 3], Vc = st[j * 8 + 4];
         const float dV = st[j * 8 + 5] > 0.0f ? 0.5f * g_cov * scale : 0.0f;
-        const int n = __ldg(idx + (size_t)b * K + k);
-        const float dr = (float)(n / side) - mr, dc = (float)(n % side) - mc;
+        const int tok = __ldg(idx + (size_t)b * K + k0 + r);
+        const float dr = (float)(tok / side) - mr, dc = (float)(tok % side) - mc;
         const float dw = (dV * ((dr * dr - Vr) + (dc * dc - Vc)) + st[j * 8 + 6] * dr + st[j * 8 + 7] * dc) / S;
-        const float d = __ldg(dslice + ((size_t)b * m + j) * K + k);
-        dd[t] = dw * dact_of_dist(d, act_fn, eps);
+        const float d = __ldg(dslice + ((size_t)b * m + j) * K + k0 + r);
+        dd[j * kPpcBwdTok + r] = 2.0f * dw * dact_of_dist(d, act_fn, eps);      // factor 2 of d|z-p|^2 folded in
     }
     __syncthreads();
-
-    // token gradient rows: one warp per token, dZ[b,k,:] = sum_j dd[j,k] * 2 (Z[b,k,:] - P_j)
-    for (int k = warp; k < K; k += nwarp) {
-        const float* zr = Zs + ((size_t)b * K + k) * D;
-        float z[kPpcMaxDV], acc[kPpcMaxDV];
+    // token gradient rows: one warp per token, dZ[b,k,:] (+)= sum_j dd[j,k] (Z[b,k,:] - P_j)
+    for (int r = warp; r < n; r += nwarp) {
+        float z[DV], acc[DV];
 #pragma unroll
-        for (int i = 0; i < kPpcMaxDV; ++i) {
-            z[i] = (i * 32 + lane < D) ? __ldg(zr + i * 32 + lane) : 0.f;
+        for (int i = 0; i < DV; ++i) {
+            z[i] = (i * 32 + lane < D) ? Zt[r * D + i * 32 + lane] : 0.f;
             acc[i] = 0.f;
         }
         for (int j = 0; j < m; ++j) {
-            const float c2 = 2.0f * dd[j * K + k];
+            const float c2 = dd[j * kPpcBwdTok + r];
 #pragma unroll
-            for (int i = 0; i < kPpcMaxDV; ++i)
+            for (int i = 0; i < DV; ++i)
                 if (i * 32 + lane < D) acc[i] = fmaf(c2, z[i] - Prow[j * D + i * 32 + lane], acc[i]);
         }
+        float* out = dZs + ((size_t)b * K + k0 + r) * D;
 #pragma unroll
-        for (int i = 0; i < kPpcMaxDV; ++i)
-            if (i * 32 + lane < D) dZs[((size_t)b * K + k) * D + i * 32 + lane] = acc[i];
+        for (int i = 0; i < DV; ++i)
+            if (i * 32 + lane < D) out[i * 32 + lane] = accumulate ? out[i * 32 + lane] + acc[i] : acc[i];
     }
-    // prototype gradient rows: one warp per label-class prototype, dP_j += sum_k dd[j,k] * 2 (P_j - Z[b,k,:])
+    // prototype gradient rows: one warp per label-class prototype, dP_j += sum_k dd[j,k] (P_j - Z[b,k,:])
     for (int j = warp; j < m; j += nwarp) {
-        float acc[kPpcMaxDV];
+        float pj[DV], acc[DV];
 #pragma unroll
-        for (int i = 0; i < kPpcMaxDV; ++i) acc[i] = 0.f;
-        for (int k = 0; k < K; ++k) {
-            const float c2 = 2.0f * dd[j * K + k];
-            const float* zr = Zs + ((size_t)b * K + k) * D;
+        for (int i = 0; i < DV; ++i) {
+            pj[i] = (i * 32 + lane < D) ? Prow[j * D + i * 32 + lane] : 0.f;
+            acc[i] = 0.f;
+        }
+        for (int r = 0; r < n; ++r) {
+            const float c2 = dd[j * kPpcBwdTok + r];
 #pragma unroll
-            for (int i = 0; i < kPpcMaxDV; ++i)
-                if (i * 32 + lane < D) acc[i] = fmaf(c2, Prow[j * D + i * 32 + lane] - __ldg(zr + i * 32 + lane), acc[i]);
+            for (int i = 0; i < DV; ++i)
+                if (i * 32 + lane < D) acc[i] = fmaf(c2, pj[i] - Zt[r * D + i * 32 + lane], acc[i]);
         }
 #pragma unroll
-        for (int i = 0; i < kPpcMaxDV; ++i)
+        for (int i = 0; i < DV; ++i)
             if (i * 32 + lane < D) atomicAdd(dP + (size_t)(prow0 + j) * D + i * 32 + lane, acc[i]);
     }
 }
 
-static int ppc_check(int B, int K, int D, int P, int m, int N, int* side) {
-    PPH_REQUIRE(B >= 0 && K >= 1 && D >= 1 && D <= 32 * kPpcMaxDV && m >= 1 && P >= m && N >= 2, PPH_EINVAL,
-                "pph_ppc: bad dims B=%d K=%d D=%d P=%d m=%d N=%d", B, K, D, P, m, N);
+template <int DV>
+static int launch_ppc_bwd(dim3 grid, size_t smem, cudaStream_t st, const float* Zs, const float* Pl,
+                          const int32_t* idx32, const int64_t* labels, const float* dslice, const float* stats,
+                          const float* g_losses, float gs_cov, float gs_mean, int B, int K, int D, int P, int m, int N,
+                          int side, int act_fn, float eps, float mean_thresh, int accumulate, float* dZs, float* dP) {
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(ppc_bwd_kernel<DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("pph_ppc_bwd: %s", cudaGetErrorString(e)); return (int)e; }
+    }
+    ppc_bwd_kernel<DV><<<grid, kPpcBwdThreads, smem, st>>>(Zs, Pl, idx32, labels, dslice, stats, g_losses, gs_cov,
+                                                          gs_mean, B, K, D, P, m, N, side, act_fn, eps, mean_thresh,
+                                                          accumulate, dZs, dP);
+    return launch_status("pph_ppc_bwd");
+}
+
+static int ppc_check(int B, int K, int D, int P, int m, int N, int* side, int* kc, size_t* smem) {
+    PPH_REQUIRE(B >= 0 && K >= 1 && D >= 4 && D % 4 == 0 && D <= 32 * kPpcMaxDV && m >= 1 && P >= m && N >= 2,
+                PPH_EINVAL, "pph_ppc: bad dims B=%d K=%d D=%d P=%d m=%d N=%d (D must be a multiple of 4, <= 512)", B,
+                K, D, P, m, N);
     int s = (int)lrint(sqrt((double)N));
     PPH_REQUIRE(s * s == N, PPH_EINVAL, "pph_ppc: N=%d is not a perfect square", N);
     *side = s;
+    // token chunk that fits ~200 KB of shared memory next to the prototype rows and the two (m,K) slices
+    int c = K;
+    while (c > 1 && ppc_smem_bytes(m, D, K, c) > 200 * 1024) c = (c + 1) / 2;
+    PPH_REQUIRE(ppc_smem_bytes(m, D, K, c) <= 200 * 1024, PPH_EUNSUP, "pph_ppc: m*D / m*K too large for shared memory");
+    *kc = c;
+    *smem = ppc_smem_bytes(m, D, K, c);
     return 0;
 }
 
@@ -244,39 +323,45 @@ extern "C" int pph_ppc_fwd(const float* Zs, const float* z2s, const float* Pl, c
     using namespace pph;
     PPH_REQUIRE(Zs && z2s && Pl && p2l && idx32 && labels && dslice && stats && partial && counter && losses,
                 PPH_EINVAL, "pph_ppc_fwd: null pointer");
-    int side = 0, rc = ppc_check(B, K, D, P, m, N, &side);
+    int side = 0, kc = 0;
+    size_t smem = 0;
+    int rc = ppc_check(B, K, D, P, m, N, &side, &kc, &smem);
     if (rc) return rc;
     if (B == 0) return 0;
-    const size_t smem = sizeof(float) * ((size_t)m * D + (size_t)m * K + 2 * (size_t)m);
-    PPH_REQUIRE(smem <= 200 * 1024, PPH_EUNSUP, "pph_ppc_fwd: m*D too large for shared memory");
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(ppc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("pph_ppc_fwd: %s", cudaGetErrorString(e)); return (int)e; }
     }
     ppc_fwd_kernel<<<B, kPpcThreads, smem, as_stream(stream)>>>(Zs, z2s, Pl, p2l, idx32, labels, B, K, D, P, m, N,
-                                                               side, act_fn, eps, cov_thresh, mean_thresh, dslice,
+                                                               side, kc, act_fn, eps, cov_thresh, mean_thresh, dslice,
                                                                stats, partial, counter, losses);
     return launch_status("pph_ppc_fwd");
 }
 
 extern "C" int pph_ppc_bwd(const float* Zs, const float* Pl, const int32_t* idx32, const int64_t* labels,
                            const float* dslice, const float* stats, const float* g_losses,
+                           float g_scale_cov, float g_scale_mean,
                            int B, int K, int D, int P, int m, int N, int act_fn, float eps,
-                           float cov_thresh, float mean_thresh, float* dZs, float* dP, pph_stream_t stream) {
+                           float cov_thresh, float mean_thresh, int accumulate, float* dZs, float* dP,
+                           pph_stream_t stream) {
     using namespace pph;
     (void)cov_thresh;
-    PPH_REQUIRE(Zs && Pl && idx32 && labels && dslice && stats && g_losses && dZs && dP, PPH_EINVAL,
-                "pph_ppc_bwd: null pointer");
-    int side = 0, rc = ppc_check(B, K, D, P, m, N, &side);
+    PPH_REQUIRE(Zs && Pl && idx32 && labels && dslice && stats && dZs && dP, PPH_EINVAL, "pph_ppc_bwd: null pointer");
+    int side = 0, kc = 0;
+    size_t smem_fwd = 0;
+    int rc = ppc_check(B, K, D, P, m, N, &side, &kc, &smem_fwd);
     if (rc) return rc;
     if (B == 0) return 0;
-    const size_t smem = sizeof(float) * ((size_t)m * D + (size_t)m * K + 8 * (size_t)m);
+    const size_t smem = sizeof(float) * ((size_t)m * D + (size_t)kPpcBwdTok * D + (size_t)m * kPpcBwdTok + 8 * (size_t)m);
     PPH_REQUIRE(smem <= 200 * 1024, PPH_EUNSUP, "pph_ppc_bwd: m*D too large for shared memory");
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(ppc_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) { set_error("pph_ppc_bwd: %s", cudaGetErrorString(e)); return (int)e; }
-    }
-    ppc_bwd_kernel<<<B, kPpcThreads, smem, as_stream(stream)>>>(Zs, Pl, idx32, labels, dslice, stats, g_losses, B, K,
-                                                               D, P, m, N, side, act_fn, eps, mean_thresh, dZs, dP);
-    return launch_status("pph_ppc_bwd");
+    dim3 grid(B, ceil_div(K, kPpcBwdTok));
+    cudaStream_t st = as_stream(stream);
+    const int dv = ceil_div(D, 32);
+#define PPH_PPC_BWD(DV) launch_ppc_bwd<DV>(grid, smem, st, Zs, Pl, idx32, labels, dslice, stats, g_losses, g_scale_cov, \
+                                           g_scale_mean, B, K, D, P, m, N, side, act_fn, eps, mean_thresh, accumulate, dZs, dP)
+    if (dv <= 2) return PPH_PPC_BWD(2);
+    if (dv <= 6) return PPH_PPC_BWD(6);
+    if (dv <= 12) return PPH_PPC_BWD(12);
+    return PPH_PPC_BWD(16);
+#undef PPH_PPC_BWD
 }

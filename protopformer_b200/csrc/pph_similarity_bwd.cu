@@ -1,18 +1,104 @@
 // (a8, part 2) Backward of max-pool + log-similarity + squared-L2 distance in its argmin-routed (sparse) form,
 // SURVEY.md 8(d)(iv).  Autograd of protopformer.py:201-247 would mirror ~10 passes over the (B,P,K) map; here the
 // upstream gradient is one scalar g[b,p] placed at token argmin[b,p]:
-//   dPl[p,:]   = 2 (Pl[p,:] sum_b g[b,p] - sum_b g[b,p] Zs[b,argmin[b,p],:])          proto_grad_kernel (gather of token rows)
-//   dZs[b,k,:] = 2 (Zs[b,k,:] sum_{p in bin(b,k)} g[b,p] - sum_{p in bin(b,k)} g[b,p] Pl[p,:])   token_grad_kernel
-//   dPg, dZc   : same with one token per image (dense; dZc through the generic GEMM)
-// Byte-bound: every (b,p) pair moves one D-float row (L2-resident operands); rows are read as coalesced 128B lines.
+//   dPl[p,:]   = 2 (Pl[p,:] sum_b g[b,p] - sum_b g[b,p] Zs[b,argmin[b,p],:])                      proto_grad_kernel
+//   dZs[b,k,:] = 2 (Zs[b,k,:] sum_{p in bin(b,k)} g[b,p] - sum_{p in bin(b,k)} g[b,p] Pl[p,:])     token_grad_kernel
+//   dPg, dZc   : same with one token per image (dense)                               proto_grad_kernel / cls_grad_kernel
+// Byte-bound on L2: every (b,p) pair moves one D-float row twice (2*B*P*D*4 B = 197 MB at the CUB shape, B = 64).
+// The gather kernels are one warp per output row with 8 independent 128B-line row loads in flight per lane group.
+//   bin_tokens_kernel : per image, stable counting sort of the prototypes by argmin token (one warp, match.any) ->
+//                       deterministic bins, so every gradient row is summed in a fixed order (bit-reproducible).
 #include "pph_common.cuh"
-#include "pph_sgemm.cuh"
 
 namespace pph {
 
-constexpr int kBwdMaxDV = 16;   // D <= 512
+// ---- binning ---------------------------------------------------------------------------------------------------
+// Stable counting sort of an image's prototypes by argmin token.  8 warps own 8 contiguous prototype ranges:
+// pass A builds per-warp histograms (match.any groups equal tokens inside a 32-prototype step), an exclusive scan
+// over (token, warp) turns them into per-warp write cursors, pass B replays the same steps and places every
+// prototype -> inside a bin prototypes are in ascending order, independent of scheduling (deterministic sums).
+// Also emits, per token, the first work item of the bin when bins are cut into chunks of kBinChunk entries.
+constexpr int kBinChunk = 32;
 
-// ---- prototype gradients: one warp per prototype row (local rows first, then global rows) ----------------------
+__global__ void __launch_bounds__(256)
+bin_tokens_kernel(const int32_t* __restrict__ argmin_l, int K, int P, int32_t* __restrict__ bin_start,
+                  int32_t* __restrict__ item_start, int32_t* __restrict__ bin_list) {
+    extern __shared__ int smi[];
+    int* hist = smi;                      // [8][K]   per-warp histogram, then per-warp cursor
+    int* tot = smi + 8 * K;               // [K+1]    bin offsets
+    int* itm = tot + K + 1;               // [K+1]    work-item offsets
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int32_t* am = argmin_l + (size_t)b * P;
+    const int per = ((P + 7) / 8 + 31) & ~31;            // prototypes per warp, multiple of 32
+    const int pa = warp * per, pb = min(P, pa + per);
+    for (int i = tid; i < 8 * K; i += 256) hist[i] = 0;
+    __syncthreads();
+    for (int p0 = pa; p0 < pb; p0 += 32) {               // pass A
+        const int p = p0 + lane;
+        const bool valid = p < pb;
+        const int a = valid ? __ldg(am + p) : -1 - lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, a);
+        if (valid && lane == __ffs(peers) - 1) hist[warp * K + a] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    if (warp == 0) {                                      // scan over tokens of the 8-warp totals
+        int carry = 0, icarry = 0;
+        for (int k0 = 0; k0 < K; k0 += 32) {
+            const int k = k0 + lane;
+            int n = 0;
+            if (k < K)
+                for (int w = 0; w < 8; ++w) n += hist[w * K + k];
+            int v = n, c = (n + kBinChunk - 1) / kBinChunk;
+            if (k < K && c == 0) c = 1;                   // empty bins still own one item (they write zeros)
+            int ci = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, v, o);
+                const int ui = __shfl_up_sync(0xffffffffu, ci, o);
+                if (lane >= o) { v += u; ci += ui; }
+            }
+            if (k < K) { tot[k] = carry + v - n; itm[k] = icarry + ci - c; }
+            carry += __shfl_sync(0xffffffffu, v, 31);
+            icarry += __shfl_sync(0xffffffffu, ci, 31);
+        }
+        if (lane == 0) { tot[K] = carry; itm[K] = icarry; }
+    }
+    __syncthreads();
+    for (int k = tid; k < K; k += 256) {                  // per-warp cursors: bin offset + counts of earlier warps
+        int run = tot[k];
+        for (int w = 0; w < 8; ++w) {
+            const int n = hist[w * K + k];
+            hist[w * K + k] = run;
+            run += n;
+        }
+    }
+    for (int k = tid; k <= K; k += 256) {
+        bin_start[(size_t)b * (K + 1) + k] = tot[k];
+        item_start[(size_t)b * (K + 1) + k] = itm[k];
+    }
+    __syncthreads();
+    int32_t* list = bin_list + (size_t)b * P;
+    for (int p0 = pa; p0 < pb; p0 += 32) {               // pass B
+        const int p = p0 + lane;
+        const bool valid = p < pb;
+        const int a = valid ? __ldg(am + p) : -1 - lane;
+        const unsigned peers = __match_any_sync(0xffffffffu, a);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        const int leader = __ffs(peers) - 1;
+        int base = 0;
+        if (valid && lane == leader) {
+            base = hist[warp * K + a];
+            hist[warp * K + a] = base + __popc(peers);
+        }
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (valid) list[base + rank] = p;
+        __syncwarp();
+    }
+}
+
+// ---- gather kernels (templated on DV = ceil(D / 32) register slots per lane) ---------------------------------------
+template <int DV>
 __global__ void __launch_bounds__(256)
 proto_grad_kernel(const float* __restrict__ g_l, const float* __restrict__ g_g, const int32_t* __restrict__ argmin_l,
                   const float* __restrict__ Zs, const float* __restrict__ Zc, const float* __restrict__ Pl,
@@ -24,120 +110,275 @@ proto_grad_kernel(const float* __restrict__ g_l, const float* __restrict__ g_g, 
     const int p = global ? row - P : row;
     const int np = global ? Pg : P;
     const float* g = global ? g_g : g_l;
-    float acc[kBwdMaxDV];
+    float acc[DV];
 #pragma unroll
-    for (int i = 0; i < kBwdMaxDV; ++i) acc[i] = 0.f;
+    for (int i = 0; i < DV; ++i) acc[i] = 0.f;
     float gsum = 0.f;
     for (int b0 = 0; b0 < B; b0 += 32) {
         const int bl = b0 + lane;
         const float gv = bl < B ? __ldg(g + (size_t)bl * np + p) : 0.f;
         const int av = (!global && bl < B) ? __ldg(argmin_l + (size_t)bl * P + p) : 0;
         const int cnt = min(32, B - b0);
-#pragma unroll 4
-        for (int t = 0; t < cnt; ++t) {
-            const float gg = __shfl_sync(0xffffffffu, gv, t);
-            const int aa = __shfl_sync(0xffffffffu, av, t);
-            const float* zr = global ? Zc + (size_t)(b0 + t) * D : Zs + ((size_t)(b0 + t) * K + aa) * D;
-            gsum += gg;
+        for (int t0 = 0; t0 < cnt; t0 += 8) {
+            float gg[8];
+            const float* zr[8];
 #pragma unroll
-            for (int i = 0; i < kBwdMaxDV; ++i)
-                if (i * 32 + lane < D) acc[i] = fmaf(gg, __ldg(zr + i * 32 + lane), acc[i]);
+            for (int u = 0; u < 8; ++u) {
+                const int t = t0 + u;                                   // shuffles stay warp-uniform; masked by gg = 0
+                gg[u] = __shfl_sync(0xffffffffu, gv, t & 31);
+                const int aa = __shfl_sync(0xffffffffu, av, t & 31);
+                const int bb = min(b0 + t, B - 1);
+                if (t >= cnt) gg[u] = 0.f;
+                zr[u] = global ? Zc + (size_t)bb * D : Zs + ((size_t)bb * K + aa) * D;
+            }
+            float v[8][DV];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int i = 0; i < DV; ++i) v[u][i] = (i * 32 + lane < D) ? __ldg(zr[u] + i * 32 + lane) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                gsum += gg[u];
+#pragma unroll
+                for (int i = 0; i < DV; ++i) acc[i] = fmaf(gg[u], v[u][i], acc[i]);
+            }
         }
     }
     const float* pr = (global ? Pgl : Pl) + (size_t)p * D;
     float* out = (global ? dPg : dPl) + (size_t)p * D;
 #pragma unroll
-    for (int i = 0; i < kBwdMaxDV; ++i)
+    for (int i = 0; i < DV; ++i)
         if (i * 32 + lane < D) out[i * 32 + lane] = 2.0f * (__ldg(pr + i * 32 + lane) * gsum - acc[i]);
 }
 
-// ---- token gradients: CTA = (image, token range); prototypes binned by their argmin token in shared memory ------
-constexpr int kTokThreads = 256;
-
-__global__ void __launch_bounds__(kTokThreads)
-token_grad_kernel(const float* __restrict__ g_l, const int32_t* __restrict__ argmin_l, const float* __restrict__ Zs,
-                  const float* __restrict__ Pl, int K, int D, int P, int tok_per_cta, float* __restrict__ dZs) {
-    extern __shared__ int smi[];
-    int* start = smi;              // [K+1] bin offsets
-    int* cursor = start + K + 1;   // [K]
-    int* list = cursor + K;        // [P] prototype ids grouped by token
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int k_begin = blockIdx.y * tok_per_cta, k_end = min(K, k_begin + tok_per_cta);
-    const int32_t* am = argmin_l + (size_t)b * P;
-    for (int k = tid; k <= K; k += kTokThreads) start[k] = 0;
-    __syncthreads();
-    for (int p = tid; p < P; p += kTokThreads) {
-        const int a = __ldg(am + p);
-        if (a >= k_begin && a < k_end) atomicAdd(&start[a + 1], 1);
+// One warp per work item = (image, token, chunk of <= kBinChunk bin entries).  Single-chunk bins write their row
+// directly; multi-chunk bins (skewed argmin distributions put hundreds of prototypes on one token) write partials
+// and the last warp to finish adds them in chunk order -> balanced AND deterministic.
+template <int DV>
+__global__ void __launch_bounds__(256)
+token_grad_kernel(const float* __restrict__ g_l, const int32_t* __restrict__ bin_start,
+                  const int32_t* __restrict__ item_start, const int32_t* __restrict__ bin_list,
+                  const float* __restrict__ Zs, const float* __restrict__ Pl, int B, int K, int D, int P,
+                  int items_per_image, float* part, float* part_gsum, unsigned int* counters,
+                  float* __restrict__ dZs) {
+    const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    const int b = gw / items_per_image, item = gw - b * items_per_image;
+    if (b >= B) return;
+    const int32_t* ist = item_start + (size_t)b * (K + 1);
+    if (item >= __ldg(ist + K)) return;
+    // token of this item: the last k with item_start[k] <= item   (lane-parallel search over <= 256 tokens)
+    int k = 0;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        const int kk = k0 + lane;
+        const bool le = kk < K && __ldg(ist + kk) <= item;
+        const unsigned m = __ballot_sync(0xffffffffu, le);
+        if (m) k = k0 + 31 - __clz(m);
+        if (m != 0xffffffffu) break;
     }
-    __syncthreads();
-    if (warp == 0) {               // inclusive scan of the counts -> bin offsets
-        int carry = 0;
-        for (int k0 = 0; k0 <= K; k0 += 32) {
-            const int k = k0 + lane;
-            int v = k <= K ? start[k] : 0;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int u = __shfl_up_sync(0xffffffffu, v, o);
-                if (lane >= o) v += u;
-            }
-            if (k <= K) start[k] = v + carry;
-            carry += __shfl_sync(0xffffffffu, v, 31);
-        }
-    }
-    __syncthreads();
-    for (int k = tid; k < K; k += kTokThreads) cursor[k] = start[k];
-    __syncthreads();
-    for (int p = tid; p < P; p += kTokThreads) {
-        const int a = __ldg(am + p);
-        if (a >= k_begin && a < k_end) list[atomicAdd(&cursor[a], 1)] = p;
-    }
-    __syncthreads();
+    const int chunk = item - __ldg(ist + k);
+    const int nchunks = __ldg(ist + k + 1) - __ldg(ist + k);
+    const int e0 = __ldg(bin_start + (size_t)b * (K + 1) + k) + chunk * kBinChunk;
+    const int e1 = min(__ldg(bin_start + (size_t)b * (K + 1) + k + 1), e0 + kBinChunk);
+    const int32_t* list = bin_list + (size_t)b * P;
     const float* gb = g_l + (size_t)b * P;
-    for (int k = k_begin + warp; k < k_end; k += kTokThreads / 32) {
-        float acc[kBwdMaxDV];
+    float acc[DV];
 #pragma unroll
-        for (int i = 0; i < kBwdMaxDV; ++i) acc[i] = 0.f;
-        float gsum = 0.f;
-        const int e0 = start[k], e1 = start[k + 1];
-#pragma unroll 4
-        for (int e = e0; e < e1; ++e) {
-            const int p = list[e];
-            const float gg = __ldg(gb + p);
-            const float* pr = Pl + (size_t)p * D;
-            gsum += gg;
+    for (int i = 0; i < DV; ++i) acc[i] = 0.f;
+    float gsum = 0.f;
+    {
+        const int e = e0 + lane;
+        const int pv = e < e1 ? __ldg(list + e) : 0;
+        const float gv = e < e1 ? __ldg(gb + pv) : 0.f;
+        const int cnt = max(0, e1 - e0);
+        for (int t0 = 0; t0 < cnt; t0 += 8) {
+            float gg[8];
+            const float* pr[8];
 #pragma unroll
-            for (int i = 0; i < kBwdMaxDV; ++i)
-                if (i * 32 + lane < D) acc[i] = fmaf(gg, __ldg(pr + i * 32 + lane), acc[i]);
+            for (int u = 0; u < 8; ++u) {
+                const int t = t0 + u;
+                gg[u] = __shfl_sync(0xffffffffu, gv, t & 31);
+                const int pp = __shfl_sync(0xffffffffu, pv, t & 31);
+                if (t >= cnt) gg[u] = 0.f;
+                pr[u] = Pl + (size_t)pp * D;
+            }
+            float v[8][DV];
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+                for (int i = 0; i < DV; ++i) v[u][i] = (i * 32 + lane < D) ? __ldg(pr[u] + i * 32 + lane) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                gsum += gg[u];
+#pragma unroll
+                for (int i = 0; i < DV; ++i) acc[i] = fmaf(gg[u], v[u][i], acc[i]);
+            }
         }
-        const float* zr = Zs + ((size_t)b * K + k) * D;
-        float* out = dZs + ((size_t)b * K + k) * D;
+    }
+    const size_t row = (size_t)b * K + k;
+    const float* zr = Zs + row * D;
+    float* out = dZs + row * D;
+    if (nchunks == 1) {
 #pragma unroll
-        for (int i = 0; i < kBwdMaxDV; ++i)
+        for (int i = 0; i < DV; ++i)
             if (i * 32 + lane < D) out[i * 32 + lane] = 2.0f * (__ldg(zr + i * 32 + lane) * gsum - acc[i]);
+        return;
+    }
+    const size_t slot = (size_t)b * items_per_image + item;                 // partial slot of this chunk
+#pragma unroll
+    for (int i = 0; i < DV; ++i)
+        if (i * 32 + lane < D) part[slot * D + i * 32 + lane] = acc[i];
+    if (lane == 0) part_gsum[slot] = gsum;
+    __threadfence();
+    __syncwarp();
+    unsigned int ticket = 0;
+    if (lane == 0) ticket = atomicAdd(counters + row, 1u);
+    ticket = __shfl_sync(0xffffffffu, ticket, 0);
+    if (ticket != (unsigned int)(nchunks - 1)) return;
+    __threadfence();
+    const size_t slot0 = (size_t)b * items_per_image + __ldg(ist + k);
+    float tot[DV];
+#pragma unroll
+    for (int i = 0; i < DV; ++i) tot[i] = 0.f;
+    float gt = 0.f;
+    for (int c = 0; c < nchunks; ++c) {
+        gt += __ldcg(part_gsum + slot0 + c);
+#pragma unroll
+        for (int i = 0; i < DV; ++i)
+            if (i * 32 + lane < D) tot[i] += __ldcg(part + (slot0 + c) * D + i * 32 + lane);
+    }
+#pragma unroll
+    for (int i = 0; i < DV; ++i)
+        if (i * 32 + lane < D) out[i * 32 + lane] = 2.0f * (__ldg(zr + i * 32 + lane) * gt - tot[i]);
+    if (lane == 0) counters[row] = 0u;                                       // self-resetting (graph replay)
+}
+
+// CLS-token gradient: dZc[b,:] = 2 (Zc[b,:] sum_p g_g[b,p] - sum_p g_g[b,p] Pg[p,:]).  CTA = 8 images x a slice of
+// the global prototypes (rows read once per CTA, coalesced), fixed-order two-level sum: per-slice partials in
+// `part` [slices][B][D], then the last CTA of each image group adds the slices in order (deterministic).
+constexpr int kClsTB = 8, kClsThreads = 256;
+
+__global__ void __launch_bounds__(kClsThreads)
+cls_grad_kernel(const float* __restrict__ g_g, const float* __restrict__ Zc, const float* __restrict__ Pgl,
+                int B, int D, int Pg, int p_per_slice, float* part, unsigned int* counters,
+                float* __restrict__ dZc) {
+    __shared__ float gs[kClsTB][64];
+    __shared__ unsigned int s_ticket;
+    const int tid = threadIdx.x, b0 = blockIdx.y * kClsTB, slice = blockIdx.x, nslices = gridDim.x;
+    const int pa = slice * p_per_slice, pb = min(Pg, pa + p_per_slice);
+    float acc[kClsTB][2];           // D <= 512: each thread owns columns tid, tid + 256
+    float gsum[kClsTB];
+#pragma unroll
+    for (int i = 0; i < kClsTB; ++i) { acc[i][0] = acc[i][1] = 0.f; gsum[i] = 0.f; }
+    for (int p0 = pa; p0 < pb; p0 += 64) {
+        __syncthreads();
+        for (int i = tid; i < kClsTB * 64; i += kClsThreads) {
+            const int bi = i >> 6, pp = p0 + (i & 63);
+            gs[bi][i & 63] = (b0 + bi < B && pp < pb) ? __ldg(g_g + (size_t)(b0 + bi) * Pg + pp) : 0.f;
+        }
+        __syncthreads();
+        const int n = min(64, pb - p0);
+#pragma unroll 8
+        for (int q = 0; q < n; ++q) {
+            const float* pr = Pgl + (size_t)(p0 + q) * D;
+            const float v0 = tid < D ? __ldg(pr + tid) : 0.f;
+            const float v1 = tid + 256 < D ? __ldg(pr + tid + 256) : 0.f;
+#pragma unroll
+            for (int i = 0; i < kClsTB; ++i) {
+                const float gq = gs[i][q];
+                gsum[i] += gq;
+                acc[i][0] = fmaf(gq, v0, acc[i][0]);
+                acc[i][1] = fmaf(gq, v1, acc[i][1]);
+            }
+        }
+    }
+    // partial of this slice: 2 (Zc * gsum - acc)
+#pragma unroll
+    for (int i = 0; i < kClsTB; ++i) {
+        const int b = b0 + i;
+        if (b >= B) continue;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int d = tid + 256 * h;
+            if (d < D) part[((size_t)slice * B + b) * D + d] = 2.0f * (__ldg(Zc + (size_t)b * D + d) * gsum[i] - acc[i][h]);
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_ticket = atomicAdd(counters + blockIdx.y, 1u);
+    __syncthreads();
+    if (s_ticket == (unsigned int)(nslices - 1)) {
+        __threadfence();
+        for (int i = 0; i < kClsTB; ++i) {
+            const int b = b0 + i;
+            if (b >= B) continue;
+            for (int d = tid; d < D; d += kClsThreads) {
+                float s = 0.f;
+                for (int sl = 0; sl < nslices; ++sl) s += __ldcg(part + ((size_t)sl * B + b) * D + d);
+                dZc[(size_t)b * D + d] = s;
+            }
+        }
+        if (tid == 0) counters[blockIdx.y] = 0u;       // self-resetting (graph replay)
     }
 }
 
-struct ClsGradEpi {   // dZc[b,d] += 2 (Zc[b,d] * rowsum_part - acc_part)     (split over prototypes)
-    const float* Zc;
-    float* dZc;
-    int D;
-    __device__ __forceinline__ void operator()(int b, int d, float acc, float rs) const {
-        const size_t o = (size_t)b * D + d;
-        atomicAdd(dZc + o, 2.0f * (__ldg(Zc + o) * rs - acc));
-    }
+struct BwdWorkspace {
+    int32_t *bin_start, *item_start, *bin_list;
+    unsigned int *tok_counters, *cls_counters;
+    float *tok_part, *tok_gsum, *cls_part;
+    int items_per_image;
+    size_t bytes;
 };
+
+static BwdWorkspace carve_ws(void* base, int B, int K, int D, int P, int Pg) {
+    BwdWorkspace w;
+    char* p = static_cast<char*>(base);
+    size_t off = 0;
+    auto take = [&](size_t n) { char* r = p ? p + off : nullptr; off += (n + 255) / 256 * 256; return r; };
+    w.items_per_image = K + (P + kBinChunk - 1) / kBinChunk;
+    // counters first: they are the part that must start zeroed
+    w.tok_counters = reinterpret_cast<unsigned int*>(take(sizeof(int) * (size_t)B * K));
+    w.cls_counters = reinterpret_cast<unsigned int*>(take(sizeof(int) * (size_t)((B + kClsTB - 1) / kClsTB + 1)));
+    w.bin_start = reinterpret_cast<int32_t*>(take(sizeof(int) * (size_t)B * (K + 1)));
+    w.item_start = reinterpret_cast<int32_t*>(take(sizeof(int) * (size_t)B * (K + 1)));
+    w.bin_list = reinterpret_cast<int32_t*>(take(sizeof(int) * (size_t)B * P));
+    w.tok_part = reinterpret_cast<float*>(take(sizeof(float) * (size_t)B * w.items_per_image * D));
+    w.tok_gsum = reinterpret_cast<float*>(take(sizeof(float) * (size_t)B * w.items_per_image));
+    w.cls_part = reinterpret_cast<float*>(take(Pg > 0 ? sizeof(float) * (size_t)16 * B * D : 0));
+    w.bytes = off + 256;
+    return w;
+}
+
+template <int DV>
+static int launch_bwd(const float* g_l, const float* g_g, const int32_t* argmin_l, const BwdWorkspace& w,
+                      const float* Zs, const float* Zc, const float* Pl, const float* Pgl,
+                      int B, int K, int D, int P, int Pg, float* dZs, float* dPl, float* dPg, cudaStream_t st) {
+    proto_grad_kernel<DV><<<ceil_div(P + Pg, 8), 256, 0, st>>>(g_l, g_g, argmin_l, Zs, Zc, Pl, Pgl, B, K, D, P, Pg,
+                                                               dPl, dPg);
+    int rc = launch_status("pph_similarity_bwd(proto)");
+    if (rc) return rc;
+    token_grad_kernel<DV><<<ceil_div(B * w.items_per_image, 8), 256, 0, st>>>(
+        g_l, w.bin_start, w.item_start, w.bin_list, Zs, Pl, B, K, D, P, w.items_per_image, w.tok_part, w.tok_gsum,
+        w.tok_counters, dZs);
+    return launch_status("pph_similarity_bwd(token)");
+}
 
 }  // namespace pph
 
+extern "C" int pph_similarity_bwd_ws_bytes(int B, int K, int D, int P, int Pg, long long* bytes) {
+    using namespace pph;
+    PPH_REQUIRE(bytes && B >= 0 && K >= 1 && D >= 1 && P >= 1 && Pg >= 0, PPH_EINVAL, "pph_similarity_bwd_ws_bytes: bad args");
+    *bytes = (long long)carve_ws(nullptr, B > 0 ? B : 1, K, D, P, Pg).bytes;
+    return 0;
+}
+
 extern "C" int pph_similarity_bwd(const float* g_l, const float* g_g, const int32_t* argmin_l,
                                   const float* Zs, const float* Zc, const float* Pl, const float* Pgl,
-                                  int B, int K, int D, int P, int Pg,
+                                  int B, int K, int D, int P, int Pg, void* workspace,
                                   float* dZs, float* dZc, float* dPl, float* dPg, pph_stream_t stream) {
     using namespace pph;
     PPH_REQUIRE(g_l && argmin_l && Zs && Pl && dZs && dPl, PPH_EINVAL, "pph_similarity_bwd: null local pointer");
     PPH_REQUIRE(Pg == 0 || (g_g && Zc && Pgl && dZc && dPg), PPH_EINVAL, "pph_similarity_bwd: null global pointer");
-    PPH_REQUIRE(B >= 0 && K >= 1 && D >= 1 && D <= 32 * kBwdMaxDV && P >= 1 && Pg >= 0, PPH_EINVAL,
+    PPH_REQUIRE(B >= 0 && K >= 1 && D >= 1 && D <= 512 && P >= 1 && Pg >= 0, PPH_EINVAL,
                 "pph_similarity_bwd: bad dims B=%d K=%d D=%d P=%d Pg=%d", B, K, D, P, Pg);
     cudaStream_t st = as_stream(stream);
     if (B == 0) {
@@ -145,35 +386,25 @@ extern "C" int pph_similarity_bwd(const float* g_l, const float* g_g, const int3
         if (Pg > 0) cudaMemsetAsync(dPg, 0, sizeof(float) * (size_t)Pg * D, st);
         return launch_status("pph_similarity_bwd(empty)");
     }
-    proto_grad_kernel<<<ceil_div(P + Pg, 8), 256, 0, st>>>(g_l, g_g, argmin_l, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, dPl,
-                                                           dPg);
-    int rc = launch_status("pph_similarity_bwd(proto)");
+    PPH_REQUIRE(workspace, PPH_EINVAL, "pph_similarity_bwd: null workspace (size it with pph_similarity_bwd_ws_bytes)");
+    const size_t bin_smem = sizeof(int) * ((size_t)8 * K + 2 * (size_t)(K + 1));
+    PPH_REQUIRE(bin_smem <= 48 * 1024, PPH_EUNSUP, "pph_similarity_bwd: K too large");
+    const BwdWorkspace w = carve_ws(workspace, B, K, D, P, Pg);
+    bin_tokens_kernel<<<B, 256, bin_smem, st>>>(argmin_l, K, P, w.bin_start, w.item_start, w.bin_list);
+    int rc = launch_status("pph_similarity_bwd(bin)");
     if (rc) return rc;
-    {
-        // enough (image, token range) CTAs for ~2 per SM
-        int parts = ceil_div(2 * 148, B);
-        if (parts > K) parts = K;
-        if (parts < 1) parts = 1;
-        const int tok_per_cta = ceil_div(K, parts);
-        parts = ceil_div(K, tok_per_cta);
-        const size_t smem = sizeof(int) * ((size_t)2 * K + 1 + P);
-        PPH_REQUIRE(smem <= 200 * 1024, PPH_EUNSUP, "pph_similarity_bwd: P=%d too large for the bin list", P);
-        if (smem > 48 * 1024) {
-            cudaError_t e = cudaFuncSetAttribute(token_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) { set_error("pph_similarity_bwd: %s", cudaGetErrorString(e)); return (int)e; }
-        }
-        token_grad_kernel<<<dim3(B, parts), kTokThreads, smem, st>>>(g_l, argmin_l, Zs, Pl, K, D, P, tok_per_cta, dZs);
-        rc = launch_status("pph_similarity_bwd(token)");
-        if (rc) return rc;
-    }
+    const int dv = ceil_div(D, 32);
+    if (dv <= 2) rc = launch_bwd<2>(g_l, g_g, argmin_l, w, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, dZs, dPl, dPg, st);
+    else if (dv <= 6) rc = launch_bwd<6>(g_l, g_g, argmin_l, w, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, dZs, dPl, dPg, st);
+    else if (dv <= 12) rc = launch_bwd<12>(g_l, g_g, argmin_l, w, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, dZs, dPl, dPg, st);
+    else rc = launch_bwd<16>(g_l, g_g, argmin_l, w, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, dZs, dPl, dPg, st);
+    if (rc) return rc;
     if (Pg > 0) {
-        cudaError_t e = cudaMemsetAsync(dZc, 0, sizeof(float) * (size_t)B * D, st);
-        if (e != cudaSuccess) { set_error("pph_similarity_bwd: memset: %s", cudaGetErrorString(e)); return (int)e; }
-        StridedOp<true> a{g_g, B, Pg, 1};
-        StridedOp<false> bop{Pgl, D, 1, D};       // (row = d, k = p) -> Pg[p*D + d]
-        ClsGradEpi epi{Zc, dZc, D};
-        const int tiles = ceil_div(B, kGemmBM) * ceil_div(D, kGemmBN);
-        launch_sgemm<true>(B, D, Pg, ceil_div(148, tiles), a, bop, epi, st);
+        const int slices = 16;
+        const int p_per_slice = ceil_div(ceil_div(Pg, slices), 64) * 64;
+        const int nsl = ceil_div(Pg, p_per_slice);
+        cls_grad_kernel<<<dim3(nsl, ceil_div(B, kClsTB)), kClsThreads, 0, st>>>(g_g, Zc, Pgl, B, D, Pg, p_per_slice,
+                                                                            w.cls_part, w.cls_counters, dZc);
         rc = launch_status("pph_similarity_bwd(cls)");
         if (rc) return rc;
     }

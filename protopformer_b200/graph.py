@@ -25,7 +25,7 @@ from .dist import FlatGradReducer
 class GraphedHeadStep:
     def __init__(self, params: dict, cfg: ops.HeadConfig, B: int, N: int, C: int, m: int, n_slots: int = 1,
                  heads: int = 0, ppc_cov_coe: float = 0.1, ppc_mean_coe: float = 0.5, train: bool = True,
-                 process_group=None, device=None):
+                 process_group=None, device=None, fused: bool = True):
         """params: dict with Wa (D,Din), ba (D), P (P,D), Pg (Pg,D) [leaf tensors, requires_grad in training] and
         the frozen Wl (C,P), Wg (C,Pg).  ppc_*_coe follow scripts/train_cub.sh:43-44."""
         self.p, self.cfg, self.B, self.N, self.C, self.m = params, cfg, B, N, C, m
@@ -47,9 +47,29 @@ class GraphedHeadStep:
             named = [(k, params[k]) for k in ("P", "Pg", "Wa", "ba")]
             self.reducer = FlatGradReducer(named, process_group)
         self.kernel_launches_per_step = 0
+        self.fused = None
+        if fused:
+            # one set of intermediate buffers shared by all slots (replays are serial on one stream)
+            D, P, Pg = params["Wa"].shape[0], params["P"].shape[0], params["Pg"].shape[0]
+            self.fused = ops.FusedHeadStep(cfg, B, N, Din, D, P, Pg, C, m, dev, heads=heads, ppc_cov_coe=ppc_cov_coe,
+                                           ppc_mean_coe=ppc_mean_coe, train=train)
+            if train:
+                self.grads = dict(zip(("P", "Pg", "Wa", "ba"), self.reducer.views))
 
     # --------------------------------------------------------------------------------------------------------
+    def _step_fused(self, slot: int):
+        p, f = self.p, self.fused
+        with torch.no_grad():
+            f.step(self.tokens[slot], self.scores[slot], self.labels[slot], p["Wa"], p["ba"], p["P"], p["Pg"],
+                   p["Wl"], p["Wg"], self.grads if self.train else None)
+        self.loss[slot] = f.losses[0]
+        self.logits[slot] = f.logits
+        self.ppc[slot] = (f.losses[2], f.losses[3])
+        self.dtokens[slot] = f.dtokens if self.train else None
+
     def _step(self, slot: int):
+        if self.fused is not None:
+            return self._step_fused(slot)
         p, cfg = self.p, self.cfg
         tok = self.tokens[slot]
         if self.train:

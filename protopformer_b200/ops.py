@@ -235,8 +235,19 @@ class _SimilarityLogits(torch.autograd.Function):
                   float(cfg.global_coe), cfg.act_id, float(cfg.eps), g_l, g_g)
         dZs, dZc = torch.empty_like(Zs), torch.empty_like(Zc)
         dPl, dPg = torch.empty_like(Pl), torch.empty_like(Pgl)
-        _lib.call("pph_similarity_bwd", g_l, g_g, argmin, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, dZs, dZc, dPl, dPg)
+        ws = bwd_workspace(B, K, D, P, Pg, Zs.device)
+        _lib.call("pph_similarity_bwd", g_l, g_g, argmin, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, ws, dZs, dZc, dPl, dPg)
         return dZs, dZc, dPl, dPg, None, None, None, None
+
+
+def bwd_workspace(B, K, D, P, Pg, device) -> torch.Tensor:
+    """Zero-filled scratch for pph_similarity_bwd (token bins + self-resetting counters)."""
+    import ctypes
+    n = ctypes.c_longlong(0)
+    rc = _lib.load().pph_similarity_bwd_ws_bytes(B, K, D, P, Pg, ctypes.byref(n))
+    if rc != 0:
+        raise RuntimeError("pph_similarity_bwd_ws_bytes failed")
+    return torch.zeros(max(int(n.value), 256), dtype=torch.uint8, device=device)
 
 
 @dataclasses.dataclass
@@ -323,8 +334,8 @@ class _PPC(torch.autograd.Function):
         zero = torch.zeros((), dtype=torch.float32, device=Zs.device)
         g = torch.stack([zero if g_cov is None else g_cov.float(), zero if g_mean is None else g_mean.float()])
         dZs, dP = torch.empty_like(Zs), torch.zeros_like(Pl)
-        _lib.call("pph_ppc_bwd", Zs, Pl, idx32, labels, dslice, stats, g, B, K, D, P, m, N, cfg.act_id,
-                  float(cfg.eps), float(cfg.ppc_cov_thresh), float(cfg.ppc_mean_thresh), dZs, dP)
+        _lib.call("pph_ppc_bwd", Zs, Pl, idx32, labels, dslice, stats, g, 1.0, 1.0, B, K, D, P, m, N, cfg.act_id,
+                  float(cfg.eps), float(cfg.ppc_cov_thresh), float(cfg.ppc_mean_thresh), 0, dZs, dP)
         return dZs, dP, None, None, None, None, None, None, None
 
 
@@ -336,3 +347,93 @@ def ppc_loss(cfg: HeadConfig, tf: TokenFeatures, P, p2l, labels, m: int, N: int)
     if p2l is None:
         p2l = prepare_prototypes(P2d, False).p2
     return _PPC.apply(tf.Zs, P2d, tf.z2s, p2l, tf.idx32, labels, m, N, cfg)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Fused training / inference step: the same entry points in a fixed sequence over pre-allocated buffers, no autograd
+# graph and no PyTorch glue kernels in between (what tools/engine_proto.py:49-76 amounts to for the head).
+# ------------------------------------------------------------------------------------------------------------------
+class FusedHeadStep:
+    """forward (+ PPC + cross-entropy + backward) of the head for a fixed shape.
+
+    step(tokens, scores, labels, Wa, ba, P, Pg, Wl, Wg, grads) launches, in order:
+      select_topk, addon_fwd, split_rows x2, similarity_fwd, logits_fwd, [ppc_fwd,] loss_tail,
+      [logits_bwd, similarity_bwd, ppc_bwd(accumulate), addon_bwd]
+    Results live in attributes: losses (4,) = (total, ce, ppc_cov, ppc_mean), logits, logits_g, logits_l, act_l,
+    dmin_l, argmin, idx32, dtokens; parameter gradients are OVERWRITTEN in the tensors of `grads`
+    (keys Wa, ba, P, Pg -- e.g. views of one flat all-reduce buffer)."""
+
+    def __init__(self, cfg: HeadConfig, B, N, Din, D, P, Pg, C, m, device, heads: int = 0, ppc_cov_coe: float = 0.1,
+                 ppc_mean_coe: float = 0.5, train: bool = True, use_ppc: bool = True):
+        self.cfg, self.train, self.use_ppc = cfg, train, use_ppc
+        self.dims = (B, N, Din, D, P, Pg, C, m, heads)
+        self.cov_coe, self.mean_coe = float(ppc_cov_coe), float(ppc_mean_coe)
+        K = cfg.K
+        f32, bf, i32 = torch.float32, torch.bfloat16, torch.int32
+        e = lambda *s, dt=f32: torch.empty(s, dtype=dt, device=device)  # noqa: E731
+        z = lambda *s, dt=f32: torch.zeros(s, dtype=dt, device=device)  # noqa: E731
+        self.split = cfg.mode_id != _lib.MODE_FP32_FMA
+        self.idx32 = e(B, K, dt=i32)
+        self.Zs, self.Zc, self.z2s, self.z2c = e(B, K, D), e(B, D), e(B, K), e(B)
+        if self.split:
+            self.z2s_ctr, self.z2c_ctr, self.z2s_hi, self.z2c_hi = e(B, K), e(B), e(B, K), e(B)
+            self.Zs_hi, self.Zs_lo, self.Zc_hi, self.Zc_lo = e(B * K, D, dt=bf), e(B * K, D, dt=bf), e(B, D, dt=bf), e(B, D, dt=bf)
+            self.P_hi, self.P_lo, self.Pg_hi, self.Pg_lo = e(P, D, dt=bf), e(P, D, dt=bf), e(Pg, D, dt=bf), e(Pg, D, dt=bf)
+            self.p2_ctr, self.p2_hi, self.pg2_ctr, self.pg2_hi = e(P), e(P), e(Pg), e(Pg)
+        else:
+            for n in ("z2s_ctr", "z2c_ctr", "z2s_hi", "z2c_hi", "Zs_hi", "Zs_lo", "Zc_hi", "Zc_lo", "P_hi", "P_lo",
+                      "Pg_hi", "Pg_lo", "p2_ctr", "p2_hi", "pg2_ctr", "pg2_hi"):
+                setattr(self, n, None)
+        self.p2, self.pg2 = e(P), e(Pg)
+        self.dmin_l, self.act_l, self.argmin = e(B, P), e(B, P), e(B, P, dt=i32)
+        self.dmin_g, self.act_g = e(B, Pg), e(B, Pg)
+        self.logits, self.logits_g, self.logits_l = e(B, C), e(B, C), e(B, C)
+        self.dslice, self.stats, self.ppc_partial = e(B, m, K), e(B, m, 8), e(B, 2)
+        self.ppc_counter, self.ppc_losses = z(1, dt=i32), z(2)
+        self.ce_partial, self.ce_counter, self.losses = e(B), z(1, dt=i32), z(4)
+        if train:
+            self.dlogits, self.g_l, self.g_g = e(B, C), e(B, P), e(B, Pg)
+            self.dZs, self.dZc = e(B, K, D), e(B, D)
+            self.dtokens = e(B, 1 + N, Din)
+            self.ws = bwd_workspace(B, K, D, P, Pg, device)
+
+    def step(self, tokens, scores, labels, Wa, ba, P, Pg, Wl, Wg, grads=None, upstream: float = 1.0):
+        B, N, Din, D, Pn, Pgn, C, m, H = self.dims
+        cfg, K = self.cfg, self.cfg.K
+        c = _lib.call
+        c("pph_select_topk", scores, B, max(H, 1), N, K, self.idx32, None)
+        c("pph_addon_fwd", tokens, self.idx32, Wa, ba, B, N, Din, D, K, self.Zs, self.Zc, self.z2s, self.z2c,
+          float(cfg.center), self.z2s_ctr, self.z2c_ctr, self.z2s_hi, self.z2c_hi, self.Zs_hi, self.Zs_lo,
+          self.Zc_hi, self.Zc_lo)
+        c("pph_split_rows", P, Pn, D, float(cfg.center), self.P_hi, self.P_lo, self.p2, self.p2_ctr, self.p2_hi)
+        c("pph_split_rows", Pg, Pgn, D, float(cfg.center), self.Pg_hi, self.Pg_lo, self.pg2, self.pg2_ctr, self.pg2_hi)
+        mode = cfg.mode_id
+        sel = {_lib.MODE_FP32_FMA: 0, _lib.MODE_BF16X3: 1, _lib.MODE_BF16: 2}[mode]
+        c("pph_similarity_fwd", mode, cfg.act_id, float(cfg.eps), B, K, D, Pn, Pgn, self.Zs, self.Zc,
+          (self.z2s, self.z2s_ctr, self.z2s_hi)[sel], (self.z2c, self.z2c_ctr, self.z2c_hi)[sel],
+          self.Zs_hi, self.Zs_lo, self.Zc_hi, self.Zc_lo, P, Pg,
+          (self.p2, self.p2_ctr, self.p2_hi)[sel], (self.pg2, self.pg2_ctr, self.pg2_hi)[sel],
+          self.P_hi, self.P_lo, self.Pg_hi, self.Pg_lo,
+          self.dmin_l, self.argmin, self.act_l, self.dmin_g, self.act_g, None, None)
+        c("pph_logits_fwd", self.act_l, self.act_g, Wl, Wg, B, Pn, Pgn, C, float(cfg.global_coe), self.logits,
+          self.logits_g, self.logits_l)
+        ppc = self.use_ppc and self.train
+        if ppc:
+            c("pph_ppc_fwd", self.Zs, self.z2s, P, self.p2, self.idx32, labels, B, K, D, Pn, m, N, cfg.act_id,
+              float(cfg.eps), float(cfg.ppc_cov_thresh), float(cfg.ppc_mean_thresh), self.dslice, self.stats,
+              self.ppc_partial, self.ppc_counter, self.ppc_losses)
+        c("pph_loss_tail", self.logits, labels, self.ppc_losses if ppc else None, self.cov_coe, self.mean_coe,
+          float(upstream), B, C, self.ce_partial, self.ce_counter, self.losses, self.dlogits if self.train else None)
+        if not self.train:
+            return self.losses
+        c("pph_logits_bwd", self.dlogits, None, None, Wl, Wg, self.dmin_l, self.dmin_g, B, Pn, Pgn, C,
+          float(cfg.global_coe), cfg.act_id, float(cfg.eps), self.g_l, self.g_g)
+        c("pph_similarity_bwd", self.g_l, self.g_g, self.argmin, self.Zs, self.Zc, P, Pg, B, K, D, Pn, Pgn, self.ws,
+          self.dZs, self.dZc, grads["P"], grads["Pg"])
+        if ppc:
+            c("pph_ppc_bwd", self.Zs, P, self.idx32, labels, self.dslice, self.stats, None,
+              self.cov_coe * float(upstream), self.mean_coe * float(upstream), B, K, D, Pn, m, N, cfg.act_id,
+              float(cfg.eps), float(cfg.ppc_cov_thresh), float(cfg.ppc_mean_thresh), 1, self.dZs, grads["P"])
+        c("pph_addon_bwd", tokens, self.idx32, Wa, self.Zs, self.Zc, self.dZs, self.dZc, B, N, Din, D, K,
+          grads["Wa"], grads["ba"], self.dtokens)
+        return self.losses

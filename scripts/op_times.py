@@ -55,12 +55,15 @@ with torch.no_grad():
     res["ppc_fwd"] = timeit("ppc_fwd", lambda: _lib.call("pph_ppc_fwd", tf.Zs, tf.z2s, pl.P, pl.p2, idx, labels, B, K, D, P, s.m, N, 0, 1e-4, 1.0, 2.0, dsl, st, part, cnt, losses))
     gl = torch.ones(2, device=dev)
     dZp = torch.empty_like(tf.Zs); dPp = torch.zeros_like(pl.P)
-    res["ppc_bwd"] = timeit("ppc_bwd", lambda: _lib.call("pph_ppc_bwd", tf.Zs, pl.P, idx, labels, dsl, st, gl, B, K, D, P, s.m, N, 0, 1e-4, 1.0, 2.0, dZp, dPp))
+    res["ppc_bwd"] = timeit("ppc_bwd", lambda: _lib.call("pph_ppc_bwd", tf.Zs, pl.P, idx, labels, dsl, st, gl, 1.0, 1.0, B, K, D, P, s.m, N, 0, 1e-4, 1.0, 2.0, 1, dZp, dPp))
     dlog = torch.randn(B, C, device=dev) / B
     g_l = torch.empty(B, P, device=dev); g_g = torch.empty(B, Pg, device=dev)
     res["logits_bwd"] = timeit("logits_bwd", lambda: _lib.call("pph_logits_bwd", dlog, None, None, case["Wl"], case["Wg"], dmin_l, dmin_g, B, P, Pg, C, 0.5, 0, 1e-4, g_l, g_g))
     dZs = torch.empty_like(tf.Zs); dZc = torch.empty_like(tf.Zc); dPl = torch.empty_like(pl.P); dPg = torch.empty_like(pg.P)
-    res["similarity_bwd"] = timeit("similarity_bwd", lambda: _lib.call("pph_similarity_bwd", g_l, g_g, argmin, tf.Zs, tf.Zc, pl.P, pg.P, B, K, D, P, Pg, dZs, dZc, dPl, dPg))
+    ws = ops.bwd_workspace(B, K, D, P, Pg, dev)
+    res["similarity_bwd"] = timeit("similarity_bwd", lambda: _lib.call("pph_similarity_bwd", g_l, g_g, argmin, tf.Zs, tf.Zc, pl.P, pg.P, B, K, D, P, Pg, ws, dZs, dZc, dPl, dPg))
+    lt_part = torch.empty(B, device=dev); lt_cnt = torch.zeros(1, dtype=torch.int32, device=dev); lt_out = torch.empty(4, device=dev)
+    res["loss_tail"] = timeit("loss_tail", lambda: _lib.call("pph_loss_tail", logits, labels, losses, 0.1, 0.5, 1.0, B, C, lt_part, lt_cnt, lt_out, dlog))
     dWa = torch.empty_like(case["Wa"]); dba = torch.empty(D, device=dev); dtok = torch.empty_like(tok)
     res["addon_bwd"] = timeit("addon_bwd", lambda: _lib.call("pph_addon_bwd", tok, idx, case["Wa"], tf.Zs, tf.Zc, dZs, dZc, B, N, Din, D, K, dWa, dba, dtok))
     res["torch_cross_entropy_fwd"] = timeit("torch CE fwd", lambda: F.cross_entropy(logits, labels))
