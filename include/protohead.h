@@ -150,10 +150,13 @@ int pph_similarity_bwd(const float* g_l, const float* g_g, const int32_t* argmin
 
 /* (a8, part 3) backward of pph_addon_fwd: dpre = dZ * Z * (1-Z);  dWa = dpre^T X_sel;  dba = sum dpre;
  * dtokens[b, 1+idx] = dpre Wa (CLS row 0 likewise), every other row zero.
- * dWa [D,Din], dba [D], dtokens [B,1+N,Din] are OVERWRITTEN (dtokens may be NULL: no gradient to the backbone). */
+ * dWa [D,Din], dba [D], dtokens [B,1+N,Din] are OVERWRITTEN (dtokens may be NULL: no gradient to the backbone).
+ * `workspace`: caller-owned device scratch of pph_addon_bwd_ws_bytes() bytes (split-K partials of the weight
+ * gradient, summed in a fixed order). */
+int pph_addon_bwd_ws_bytes(int B, int N, int Din, int D, int K, long long* bytes /* host */);
 int pph_addon_bwd(const float* tokens, const int32_t* idx32, const float* Wa,
                   const float* Zs, const float* Zc, const float* dZs, const float* dZc,
-                  int B, int N, int Din, int D, int K,
+                  int B, int N, int Din, int D, int K, void* workspace,
                   float* dWa, float* dba, float* dtokens, pph_stream_t stream);
 
 /* loss tail adjacent to the head (engine_proto.py:51, 61-64): ce = CrossEntropy(logits, labels) (mean over B),

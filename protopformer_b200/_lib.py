@@ -36,14 +36,15 @@ SIGNATURES = {
     "pph_similarity_bwd_ws_bytes": [_i, _i, _i, _i, _i, C.POINTER(C.c_longlong)],
     "pph_similarity_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],
     "pph_loss_tail": [_p, _p, _p, _f, _f, _f, _i, _i, _p, _p, _p, _p, _p],
-    "pph_addon_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p],
+    "pph_addon_bwd_ws_bytes": [_i, _i, _i, _i, _i, C.POINTER(C.c_longlong)],
+    "pph_addon_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p],
 }
 _RESTYPES = {"pph_last_error_string": C.c_char_p}
 
 # kernels launched per entry-point call (memset nodes are not counted); used for the bench's `gpu_launches` claim
 KERNELS_PER_CALL = {
     "pph_select_topk": 1, "pph_addon_fwd": 1, "pph_split_rows": 1, "pph_logits_fwd": 1, "pph_ppc_fwd": 1,
-    "pph_ppc_bwd": 1, "pph_logits_bwd": 1, "pph_similarity_bwd": 4, "pph_addon_bwd": 2, "pph_loss_tail": 1,
+    "pph_ppc_bwd": 1, "pph_logits_bwd": 1, "pph_similarity_bwd": 4, "pph_addon_bwd": 3, "pph_loss_tail": 1,
 }
 
 _lib = None

@@ -7,6 +7,7 @@
 //   j == K : CLS token             -> source row 0,                         output Zc[b,:]
 #include "pph_common.cuh"
 #include "pph_sgemm.cuh"
+#include "pph_tcgemm.cuh"
 
 namespace pph {
 
@@ -229,6 +230,223 @@ struct DxEpi {      // scatter of the token gradient rows
     }
 };
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// tensor-core path (tcgen05, bf16x3, operands prepared in-kernel: pph_tcgemm.cuh).  Used when Din % 8 == 0 and
+// D % 8 == 0; the CUDA-core kernels above remain for other shapes.
+// ---------------------------------------------------------------------------------------------------------------
+struct RowSrc {     // r -> element offset of the source token row
+    const int32_t* idx;
+    int B, N, Din, K, R;
+    __device__ __forceinline__ long operator()(int r) const {
+        const int b = r / (K + 1), j = r - b * (K + 1);
+        const int tok = j < K ? 1 + __ldg(idx + (size_t)b * K + j) : 0;
+        return ((long)b * (1 + N) + tok) * Din;
+    }
+};
+
+__device__ __forceinline__ void ld8(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void zero8(float (&v)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+}
+
+// ---- forward: Z = sigmoid(Xsel Wa^T + ba) --------------------------------------------------------------------------
+struct FwdAOp {     // (row = r, k = din): gathered token rows
+    static constexpr bool kContigK = true;
+    const float* tokens;
+    RowSrc src;
+    __device__ __forceinline__ void load8(int r, int k0, float (&v)[8]) const {
+        if (r < src.R && k0 < src.Din) ld8(tokens + src(r) + k0, v); else zero8(v);
+    }
+};
+struct FwdBOp {     // (row = n, k = din): Wa[n, din]
+    static constexpr bool kContigK = true;
+    const float* Wa;
+    int D, Din;
+    __device__ __forceinline__ void load8(int n, int k0, float (&v)[8]) const {
+        if (n < D && k0 < Din) ld8(Wa + (size_t)n * Din + k0, v); else zero8(v);
+    }
+};
+struct FwdEpi {
+    const float* ba;
+    float *Zs, *Zc, *z2s, *z2c, *z2s_ctr, *z2c_ctr, *z2s_hi, *z2c_hi;
+    uint16_t *Zs_hi, *Zs_lo, *Zc_hi, *Zc_lo;
+    float center;
+    int K, D;
+    struct State { float sq, sq_ctr, sq_hi; };
+    __device__ __forceinline__ void init(State& s) const { s.sq = s.sq_ctr = s.sq_hi = 0.f; }
+    // >= 0: element offset of the row inside Zs;  < 0: -(1 + offset inside Zc)
+    __device__ __forceinline__ long row_offset(int r) const {
+        const int b = r / (K + 1), j = r - b * (K + 1);
+        return j < K ? ((long)b * K + j) * D : -(1 + (long)b * D);
+    }
+    __device__ __forceinline__ void transform(State& s, int, int n0, uint32_t (&acc)[32]) const {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+            if (n0 + i < D) {
+                const float pre = __uint_as_float(acc[i]) + __ldg(ba + n0 + i);
+                const float z = __fdividef(1.0f, 1.0f + __expf(-pre));     // ex2.approx / rcp.approx: ~2^-21 relative
+                const float zc = z - center;
+                const float hf = bf16_to_float(bf16_bits(zc));
+                s.sq = fmaf(z, z, s.sq);
+                s.sq_ctr = fmaf(zc, zc, s.sq_ctr);
+                s.sq_hi = fmaf(hf, hf, s.sq_hi);
+                acc[i] = __float_as_uint(z);
+            }
+        }
+    }
+    __device__ __forceinline__ void store(long off, int, int n, float z) const {
+        const float zc = z - center;        // tensor-core operands are centred (translation-invariant distance)
+        const uint16_t hb = bf16_bits(zc);
+        const uint16_t lb = bf16_bits(zc - bf16_to_float(hb));
+        if (off >= 0) {
+            Zs[off + n] = z;
+            if (Zs_hi) Zs_hi[off + n] = hb;
+            if (Zs_lo) Zs_lo[off + n] = lb;
+        } else {
+            const long o = -off - 1 + n;
+            Zc[o] = z;
+            if (Zc_hi) Zc_hi[o] = hb;
+            if (Zc_lo) Zc_lo[o] = lb;
+        }
+    }
+    __device__ __forceinline__ void finish(State& s, int r, int row_local, int cgroup, float* scratch, bool valid) const {
+        if (cgroup > 0) {
+            float* p = scratch + row_local * 16 + (cgroup - 1) * 3;
+            p[0] = s.sq; p[1] = s.sq_ctr; p[2] = s.sq_hi;
+        }
+        __syncthreads();
+        if (cgroup == 0 && valid) {
+            float a = s.sq, c = s.sq_ctr, h = s.sq_hi;
+#pragma unroll
+            for (int g = 0; g < kTgWarps / 4 - 1; ++g) {
+                const float* p = scratch + row_local * 16 + g * 3;
+                a += p[0]; c += p[1]; h += p[2];
+            }
+            const int b = r / (K + 1), j = r - b * (K + 1);
+            if (j < K) {
+                const size_t o = (size_t)b * K + j;
+                z2s[o] = a;
+                if (z2s_ctr) z2s_ctr[o] = c;
+                if (z2s_hi) z2s_hi[o] = h;
+            } else {
+                z2c[b] = a;
+                if (z2c_ctr) z2c_ctr[b] = c;
+                if (z2c_hi) z2c_hi[b] = h;
+            }
+        }
+    }
+};
+
+// ---- backward operands ------------------------------------------------------------------------------------------------
+struct DpreRowOp {  // (row = r, k = d): dpre = dZ * Z * (1 - Z), contiguous along d
+    static constexpr bool kContigK = true;
+    const float *Zs, *Zc, *dZs, *dZc;
+    int K, D, R;
+    __device__ __forceinline__ void load8(int r, int d0, float (&v)[8]) const {
+        if (r >= R || d0 >= D) { zero8(v); return; }
+        const int b = r / (K + 1), j = r - b * (K + 1);
+        const bool cls = (j == K);
+        const size_t o = (cls ? (size_t)b * D : ((size_t)b * K + j) * D) + d0;
+        float z[8], g[8];
+        ld8((cls ? Zc : Zs) + o, z);
+        ld8((cls ? dZc : dZs) + o, g);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = g[i] * z[i] * (1.0f - z[i]);
+    }
+};
+struct DpreColOp {  // (row = d, k = r): the same matrix, transposed access (consecutive lanes = consecutive d)
+    static constexpr bool kContigK = false;
+    const float *Zs, *Zc, *dZs, *dZc;
+    int K, D, R;
+    __device__ __forceinline__ void load8(int d, int r0, float (&v)[8]) const {
+        if (d >= D) { zero8(v); return; }
+        int b = r0 / (K + 1), j = r0 - b * (K + 1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float val = 0.f;
+            if (r0 + i < R) {
+                const bool cls = (j == K);
+                const size_t o = (cls ? (size_t)b * D : ((size_t)b * K + j) * D) + d;
+                const float z = __ldg((cls ? Zc : Zs) + o), g = __ldg((cls ? dZc : dZs) + o);
+                val = g * z * (1.0f - z);
+            }
+            v[i] = val;
+            if (++j > K) { j = 0; ++b; }
+        }
+    }
+};
+struct WaTOp {      // (row = din, k = d): Wa[d, din]
+    static constexpr bool kContigK = false;
+    const float* Wa;
+    int D, Din;
+    __device__ __forceinline__ void load8(int din, int d0, float (&v)[8]) const {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = (din < Din && d0 + i < D) ? __ldg(Wa + (size_t)(d0 + i) * Din + din) : 0.f;
+    }
+};
+struct XselColOp {  // (row = din, k = r): gathered token rows transposed; row Din is the all-ones column (-> dba)
+    static constexpr bool kContigK = false;
+    const float* tokens;
+    RowSrc src;
+    __device__ __forceinline__ void load8(int din, int r0, float (&v)[8]) const {
+        const int K = src.K;
+        int b = r0 / (K + 1), j = r0 - b * (K + 1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float val = 0.f;
+            if (r0 + i < src.R) {
+                if (din < src.Din) {
+                    const int tok = j < K ? 1 + __ldg(src.idx + (size_t)b * K + j) : 0;
+                    val = __ldg(tokens + ((size_t)b * (1 + src.N) + tok) * src.Din + din);
+                } else if (din == src.Din) {
+                    val = 1.0f;
+                }
+            }
+            v[i] = val;
+            if (++j > K) { j = 0; ++b; }
+        }
+    }
+};
+struct DxTcEpi {    // scatter rows of dX into the (zero-filled) token gradient
+    float* dtokens;
+    RowSrc src;
+    struct State { int dummy; };
+    __device__ __forceinline__ void init(State& s) const { s.dummy = 0; }
+    __device__ __forceinline__ long row_offset(int r) const { return src(r); }
+    __device__ __forceinline__ void transform(State&, int, int, uint32_t (&)[32]) const {}
+    __device__ __forceinline__ void store(long off, int, int n, float v) const { dtokens[off + n] = v; }
+    __device__ __forceinline__ void finish(State&, int, int, int, float*, bool) const {}
+};
+struct WgradPartEpi {   // per-split partial tile [split][D][ldn]
+    float* part;
+    int D, ldn;
+    struct State { int dummy; };
+    __device__ __forceinline__ void init(State& s) const { s.dummy = 0; }
+    __device__ __forceinline__ long row_offset(int d) const { return ((long)blockIdx.y * D + d) * ldn; }
+    __device__ __forceinline__ void transform(State&, int, int, uint32_t (&)[32]) const {}
+    __device__ __forceinline__ void store(long off, int, int n, float v) const { part[off + n] = v; }
+    __device__ __forceinline__ void finish(State&, int, int, int, float*, bool) const {}
+};
+// dWa[d,din] = sum_s part[s][d][din];  dba[d] = sum_s part[s][d][Din]     (fixed order: deterministic)
+__global__ void __launch_bounds__(256)
+wgrad_reduce_kernel(const float* __restrict__ part, int splits, int D, int Din, int ldn, float* __restrict__ dWa,
+                    float* __restrict__ dba) {
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= D * (Din + 1)) return;
+    const int d = i / (Din + 1), n = i - d * (Din + 1);
+    float s = 0.f;
+    for (int sp = 0; sp < splits; ++sp) s += __ldg(part + ((size_t)sp * D + d) * ldn + n);
+    if (n < Din) dWa[(size_t)d * Din + n] = s; else dba[d] = s;
+}
+
+static bool addon_tc_ok(int Din, int D) { return Din % 8 == 0 && D % 8 == 0 && Din >= 8 && D >= 16; }
+static int wgrad_splits(int R) { int s = ceil_div(R, 2 * kTgBK); return s < 1 ? 1 : (s > 64 ? 64 : s); }
+
 }  // namespace pph
 
 extern "C" int pph_addon_fwd(const float* tokens, const int32_t* idx32, const float* Wa, const float* ba,
@@ -242,6 +460,14 @@ extern "C" int pph_addon_fwd(const float* tokens, const int32_t* idx32, const fl
                 "pph_addon_fwd: bad dims B=%d N=%d Din=%d D=%d K=%d", B, N, Din, D, K);
     if (B == 0) return 0;
     const int R = B * (K + 1);
+    if (pph::addon_tc_ok(Din, D)) {
+        using namespace pph;
+        RowSrc src{idx32, B, N, Din, K, R};
+        FwdAOp a{tokens, src};
+        FwdBOp b{Wa, D, Din};
+        FwdEpi e{ba, Zs, Zc, z2s, z2c, z2s_ctr, z2c_ctr, z2s_hi, z2c_hi, Zs_hi, Zs_lo, Zc_hi, Zc_lo, center, K, D};
+        return launch_tcgemm(R, D, Din, tcgemm_pick_bn(D), 1, a, b, e, as_stream(stream), "pph_addon_fwd(tcgen05)");
+    }
     pph::addon_fwd_kernel<<<pph::ceil_div(R, pph::kAddBM), pph::kAddThreads, 0, pph::as_stream(stream)>>>(
         tokens, idx32, Wa, ba, B, N, Din, D, K, Zs, Zc, z2s, z2c, center, z2s_ctr, z2c_ctr, z2s_hi, z2c_hi, Zs_hi,
         Zs_lo, Zc_hi, Zc_lo);
@@ -258,9 +484,24 @@ extern "C" int pph_split_rows(const float* V, int R, int D, float center, uint16
     return pph::launch_status("pph_split_rows");
 }
 
+// development aid (not part of the drop-in surface): phase timestamps (ns) of CTA 0 of the last tcgemm launch
+extern "C" int pph_debug_read(long long* out32) {
+    cudaError_t e = cudaMemcpyFromSymbol(out32, pph::g_dbg_ts, sizeof(long long) * 32);
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+extern "C" int pph_addon_bwd_ws_bytes(int B, int N, int Din, int D, int K, long long* bytes) {
+    using namespace pph;
+    PPH_REQUIRE(bytes && B >= 0 && Din >= 1 && D >= 1 && K >= 1, PPH_EINVAL, "pph_addon_bwd_ws_bytes: bad args");
+    (void)N;
+    const int ldn = ceil_div(Din + 1, 4) * 4;
+    *bytes = addon_tc_ok(Din, D) ? (long long)sizeof(float) * wgrad_splits(B * (K + 1)) * D * ldn + 256 : 256;
+    return 0;
+}
+
 extern "C" int pph_addon_bwd(const float* tokens, const int32_t* idx32, const float* Wa,
                              const float* Zs, const float* Zc, const float* dZs, const float* dZc,
-                             int B, int N, int Din, int D, int K,
+                             int B, int N, int Din, int D, int K, void* workspace,
                              float* dWa, float* dba, float* dtokens, pph_stream_t stream) {
     using namespace pph;
     PPH_REQUIRE(tokens && idx32 && Wa && Zs && Zc && dZs && dZc && dWa && dba, PPH_EINVAL,
@@ -268,8 +509,12 @@ extern "C" int pph_addon_bwd(const float* tokens, const int32_t* idx32, const fl
     PPH_REQUIRE(B >= 0 && N >= 1 && Din >= 1 && D >= 1 && K >= 1 && K <= N, PPH_EINVAL,
                 "pph_addon_bwd: bad dims B=%d N=%d Din=%d D=%d K=%d", B, N, Din, D, K);
     cudaStream_t st = as_stream(stream);
-    cudaError_t e = cudaMemsetAsync(dWa, 0, sizeof(float) * (size_t)D * Din, st);
-    if (e == cudaSuccess) e = cudaMemsetAsync(dba, 0, sizeof(float) * (size_t)D, st);
+    const bool tc = addon_tc_ok(Din, D) && B > 0;
+    cudaError_t e = cudaSuccess;
+    if (!tc) {
+        e = cudaMemsetAsync(dWa, 0, sizeof(float) * (size_t)D * Din, st);
+        if (e == cudaSuccess) e = cudaMemsetAsync(dba, 0, sizeof(float) * (size_t)D, st);
+    }
     if (e == cudaSuccess && dtokens)
         e = cudaMemsetAsync(dtokens, 0, sizeof(float) * (size_t)B * (1 + N) * Din, st);
     if (e != cudaSuccess) {
@@ -278,6 +523,33 @@ extern "C" int pph_addon_bwd(const float* tokens, const int32_t* idx32, const fl
     }
     if (B == 0) return 0;
     const int R = B * (K + 1);
+    if (tc) {
+        PPH_REQUIRE(workspace, PPH_EINVAL, "pph_addon_bwd: null workspace (size it with pph_addon_bwd_ws_bytes)");
+        RowSrc src{idx32, B, N, Din, K, R};
+        {   // dWa / dba: [D x (Din+1)] = dpre^T [D x R] * [Xsel | 1]^T, split over r, partials + ordered reduction
+            const int ldn = ceil_div(Din + 1, 4) * 4;
+            int splits = wgrad_splits(R);
+            const int k_per_split = ceil_div(ceil_div(R, splits), kTgBK) * kTgBK;
+            splits = ceil_div(R, k_per_split);
+            float* part = static_cast<float*>(workspace);
+            DpreColOp a{Zs, Zc, dZs, dZc, K, D, R};
+            XselColOp b{tokens, src};
+            WgradPartEpi epi{part, D, ldn};
+            int rc = launch_tcgemm(D, ldn, R, tcgemm_pick_bn(ldn), splits, a, b, epi, st, "pph_addon_bwd(wgrad tcgen05)");
+            if (rc) return rc;
+            wgrad_reduce_kernel<<<ceil_div(D * (Din + 1), 256), 256, 0, st>>>(part, splits, D, Din, ldn, dWa, dba);
+            rc = launch_status("pph_addon_bwd(wgrad reduce)");
+            if (rc) return rc;
+        }
+        if (dtokens) {   // dX [R x Din] = dpre [R x D] * Wa [D x Din]
+            DpreRowOp a{Zs, Zc, dZs, dZc, K, D, R};
+            WaTOp b{Wa, D, Din};
+            DxTcEpi epi{dtokens, src};
+            int rc = launch_tcgemm(R, Din, D, tcgemm_pick_bn(Din), 1, a, b, epi, st, "pph_addon_bwd(dgrad tcgen05)");
+            if (rc) return rc;
+        }
+        return 0;
+    }
     RowMap map{B, K, D};
     {   // dWa[d, din] = sum_r dpre[r,d] * X[r,din];  dba[d] = sum_r dpre[r,d]   (split over r)
         DpreOp<true> a{Zs, Zc, dZs, dZc, map, R};

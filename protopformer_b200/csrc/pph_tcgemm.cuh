@@ -10,9 +10,11 @@
 // This removes every "convert / transpose / gather into a staging buffer" pre-pass the add-on layer GEMMs would
 // otherwise need in front of a TMA-fed kernel.
 //
-// CTA = 128 output rows (UMMA M = 128) x all N columns in tiles of BN <= 256, one k-split (blockIdx.y); 256 threads:
-// all 8 warps fill, thread 0 issues MMAs, all 8 warps drain TMEM (warp w: lane quarter w & 3, column half w >> 2).
-// Two shared-memory stages (fill of k-block i+1 overlaps the MMAs of k-block i).
+// CTA = 128 output rows (UMMA M = 128) x all N columns in tiles of BN <= 256, one k-split (blockIdx.y); 512 threads:
+// all 16 warps fill (two shared-memory stages: the fill of k-block i+1 overlaps the MMAs of k-block i), thread 0
+// issues the MMAs, all 16 warps drain TMEM (warp w: lane quarter w & 3, column group w >> 2).  The epilogue
+// transforms its 32 accumulators per row in registers (thread = row), then transposes them through shared memory so
+// that global stores are row-contiguous (lane = column): 32 lanes write one 128-byte line per instruction.
 #pragma once
 
 #include "pph_common.cuh"
@@ -20,13 +22,24 @@
 
 namespace pph {
 
-constexpr int kTgThreads = 256;
+// phase timestamps (globaltimer ns) of CTA 0 of the most recent tcgemm launch: development aid, read by pph_debug_read
+static __device__ long long g_dbg_ts[32];   // one copy per translation unit (the add-on kernels live in pph_addon.cu)
+__device__ __forceinline__ void dbg_stamp(int slot) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && slot < 32) {
+        long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_dbg_ts[slot] = t;
+    }
+}
+
+constexpr int kTgThreads = 512;
+constexpr int kTgWarps = kTgThreads / 32;
 constexpr int kTgBM = 128;
 constexpr int kTgBK = 64;
 constexpr int kTgMaxBN = 256;
 
 __host__ __device__ inline size_t tcgemm_stage_bytes(int BN) { return (size_t)2 * (kTgBM + BN) * kTgBK * 2; }
-inline size_t tcgemm_smem_bytes(int BN) { return 1024 + 2 * tcgemm_stage_bytes(BN) + 128 * 8 * 4 + 256; }
+inline size_t tcgemm_smem_bytes(int BN) { return 1024 + 2 * tcgemm_stage_bytes(BN) + 128 * 16 * 4 + 128 * 8 + 256; }
 
 __device__ __forceinline__ void tg_store_split8(uint8_t* hi_tile, uint8_t* lo_tile, int row, int c, const float (&v)[8]) {
     uint32_t h[4], l[4];
@@ -47,8 +60,10 @@ __device__ __forceinline__ void tg_store_split8(uint8_t* hi_tile, uint8_t* lo_ti
 //   __device__ void load8(int row, int k0, float (&v)[8]) const; // values (row, k0..k0+7); zeros outside the operand
 // Epilogue functor contract:
 //   struct State;  __device__ void init(State&) const;
-//   __device__ void chunk(State&, int m, int n0, const uint32_t (&acc)[32]) const;   // columns n0..n0+31 of row m
-//   __device__ void finish(State&, int m, int row_local, int half, float* scratch) const;  // after all column tiles
+//   __device__ long row_offset(int m) const;                                   // any per-row value store() needs
+//   __device__ void transform(State&, int m, int n0, uint32_t (&acc)[32]) const;  // thread = row m, in place
+//   __device__ void store(long row_off, int m, int n, float v) const;           // lane = column n (coalesced)
+//   __device__ void finish(State&, int m, int row_local, int cgroup, float* scratch, bool valid) const;
 template <class AOp, class BOp, class Epi>
 __global__ void __launch_bounds__(kTgThreads, 1)
 tcgemm_kernel(int M, int N, int Kd, int BN, int k_per_split, AOp a_op, BOp b_op, Epi epi) {
@@ -56,8 +71,9 @@ tcgemm_kernel(int M, int N, int Kd, int BN, int k_per_split, AOp a_op, BOp b_op,
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const size_t stage_bytes = tcgemm_stage_bytes(BN);
     const int a_bytes = kTgBM * kTgBK * 2, b_bytes = BN * kTgBK * 2;
-    float* scratch = reinterpret_cast<float*>(smem + 2 * stage_bytes);            // [128][8]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes + 128 * 8 * 4);
+    float* scratch = reinterpret_cast<float*>(smem + 2 * stage_bytes);                        // [128][16]
+    long* rowoff = reinterpret_cast<long*>(smem + 2 * stage_bytes + 128 * 16 * 4);            // [128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes + 128 * 16 * 4 + 128 * 8);
     uint64_t* empty = bars;            // [2]
     uint64_t* acc_done = bars + 2;     // [1]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
@@ -66,6 +82,7 @@ tcgemm_kernel(int M, int N, int Kd, int BN, int k_per_split, AOp a_op, BOp b_op,
     const int m0 = blockIdx.x * kTgBM;
     const int kz0 = blockIdx.y * k_per_split, kz1 = min(Kd, kz0 + k_per_split);
 
+    dbg_stamp(0);
     if (tid == 0) {
         ptx::mbar_init(&empty[0], 1);
         ptx::mbar_init(&empty[1], 1);
@@ -73,16 +90,19 @@ tcgemm_kernel(int M, int N, int Kd, int BN, int k_per_split, AOp a_op, BOp b_op,
         ptx::fence_mbar_init();
     }
     if (warp == 1) ptx::tmem_alloc(tmem_ptr, 256);
+    if (tid >= 128 && tid < 256) rowoff[tid - 128] = (m0 + tid - 128 < M) ? epi.row_offset(m0 + tid - 128) : 0;
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
     const uint32_t idesc = ptx::umma_idesc_bf16(kTgBM, BN);
+    dbg_stamp(1);
 
     typename Epi::State st;
     epi.init(st);
-    const int quarter = warp & 3, half = warp >> 2;
+    const int quarter = warp & 3, cgroup = warp >> 2;
     const int m_row = m0 + quarter * 32 + lane;
+    float* tstage = reinterpret_cast<float*>(smem) + warp * (32 * 33);     // per-warp transpose tile (stages are idle then)
     int fill = 0;                                   // k-blocks filled so far (stage = fill & 1)
     int ntile = 0;
     for (int n0 = 0; n0 < N; n0 += BN, ++ntile) {
@@ -93,26 +113,68 @@ tcgemm_kernel(int M, int N, int Kd, int BN, int k_per_split, AOp a_op, BOp b_op,
             uint8_t* sA_lo = sA_hi + a_bytes;
             uint8_t* sB_hi = sA_lo + a_bytes;
             uint8_t* sB_lo = sB_hi + b_bytes;
-            // ---- fill A: 128 rows x 8 chunks
-#pragma unroll 2
-            for (int g = tid; g < kTgBM * 8; g += kTgThreads) {
-                const int row = AOp::kContigK ? (g >> 3) : (g & (kTgBM - 1));
-                const int c = AOp::kContigK ? (g & 7) : (g >> 7);
-                float v[8];
-                a_op.load8(m0 + row, kb + c * 8, v);
-                tg_store_split8(sA_hi, sA_lo, row, c, v);
+            // ---- fill A (128 rows x 8 chunks = 2 groups per thread) and the first 2 groups of B: all global loads
+            //      are issued before the first conversion, so one memory latency is exposed per batch, not per group
+            {
+                float va[2][8], vb[2][8];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int g = tid + i * kTgThreads;
+                    const int row = AOp::kContigK ? (g >> 3) : (g & (kTgBM - 1));
+                    const int c = AOp::kContigK ? (g & 7) : (g >> 7);
+                    a_op.load8(m0 + row, kb + c * 8, va[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int g = tid + i * kTgThreads;
+                    if (g < BN * 8) {
+                        const int row = BOp::kContigK ? (g >> 3) : (g % BN);
+                        const int c = BOp::kContigK ? (g & 7) : (g / BN);
+                        b_op.load8(n0 + row, kb + c * 8, vb[i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int g = tid + i * kTgThreads;
+                    const int row = AOp::kContigK ? (g >> 3) : (g & (kTgBM - 1));
+                    const int c = AOp::kContigK ? (g & 7) : (g >> 7);
+                    tg_store_split8(sA_hi, sA_lo, row, c, va[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int g = tid + i * kTgThreads;
+                    if (g < BN * 8) {
+                        const int row = BOp::kContigK ? (g >> 3) : (g % BN);
+                        const int c = BOp::kContigK ? (g & 7) : (g / BN);
+                        tg_store_split8(sB_hi, sB_lo, row, c, vb[i]);
+                    }
+                }
             }
-            // ---- fill B: BN rows x 8 chunks
-#pragma unroll 2
-            for (int g = tid; g < BN * 8; g += kTgThreads) {
-                const int row = BOp::kContigK ? (g >> 3) : (g % BN);
-                const int c = BOp::kContigK ? (g & 7) : (g / BN);
-                float v[8];
-                b_op.load8(n0 + row, kb + c * 8, v);
-                tg_store_split8(sB_hi, sB_lo, row, c, v);
+            // ---- rest of B in batches of 2 groups per thread
+            for (int g0 = 2 * kTgThreads; g0 < BN * 8; g0 += 2 * kTgThreads) {
+                float vb[2][8];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int g = g0 + tid + i * kTgThreads;
+                    if (g < BN * 8) {
+                        const int row = BOp::kContigK ? (g >> 3) : (g % BN);
+                        const int c = BOp::kContigK ? (g & 7) : (g / BN);
+                        b_op.load8(n0 + row, kb + c * 8, vb[i]);
+                    }
+                }
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const int g = g0 + tid + i * kTgThreads;
+                    if (g < BN * 8) {
+                        const int row = BOp::kContigK ? (g >> 3) : (g % BN);
+                        const int c = BOp::kContigK ? (g & 7) : (g / BN);
+                        tg_store_split8(sB_hi, sB_lo, row, c, vb[i]);
+                    }
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncthreads();
+            dbg_stamp(2 + fill);
             if (tid == 0) {
                 ptx::tc_fence_after();
                 const uint32_t a_hi = ptx::smem_u32(sA_hi), a_lo = ptx::smem_u32(sA_lo);
@@ -129,24 +191,39 @@ tcgemm_kernel(int M, int N, int Kd, int BN, int k_per_split, AOp a_op, BOp b_op,
                 if (kb + kTgBK >= kz1) ptx::mma_commit(acc_done);
             }
         }
-        // ---- epilogue of this column tile
+        // ---- epilogue of this column tile (all MMAs retired -> the stage buffers double as transpose tiles)
         ptx::mbar_wait(acc_done, (uint32_t)ntile & 1u);
         ptx::tc_fence_after();
+        dbg_stamp(20 + ntile);
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16);
         const int ncols = min(BN, N - n0);
-        for (int c0 = half * 32; c0 < ncols; c0 += 64) {
+        for (int c0 = cgroup * 32; c0 < ncols; c0 += 32 * (kTgWarps / 4)) {
             uint32_t v[32];
             ptx::tmem_ld_32x32(taddr + c0, v);
             ptx::tmem_ld_wait(v);
-            if (m_row < M) epi.chunk(st, m_row, n0 + c0, v);
+            if (m_row < M) epi.transform(st, m_row, n0 + c0, v);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) tstage[lane * 33 + j] = __uint_as_float(v[j]);
+            __syncwarp();
+            const int n = n0 + c0 + lane;
+            if (n < N) {
+#pragma unroll 8
+                for (int r = 0; r < 32; ++r) {
+                    const int m = m0 + quarter * 32 + r;
+                    if (m < M) epi.store(rowoff[quarter * 32 + r], m, n, tstage[r * 33 + lane]);
+                }
+            }
         }
         ptx::tc_fence_before();
-        __syncthreads();                           // every TMEM read done before the next tile's MMAs overwrite
+        __syncthreads();                           // TMEM reads + transpose tiles done before the next tile's fill / MMAs
         ptx::tc_fence_after();
     }
-    epi.finish(st, m_row, quarter * 32 + lane, half, scratch, m_row < M);
+    dbg_stamp(28);
+    epi.finish(st, m_row, quarter * 32 + lane, cgroup, scratch, m_row < M);
     ptx::tc_fence_before();
     __syncthreads();
+    dbg_stamp(29);
     if (warp == 1) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, 256);

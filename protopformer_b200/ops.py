@@ -104,7 +104,8 @@ class _Addon(torch.autograd.Function):
         dZc = torch.zeros_like(Zc) if dZc is None else dZc.contiguous()
         dWa, dba = torch.empty_like(Wa), _empty((D,), torch.float32, Wa)
         dtok = torch.empty_like(tokens) if ctx.needs_input_grad[0] else None
-        _lib.call("pph_addon_bwd", tokens, idx32, Wa, Zs, Zc, dZs, dZc, B, N, Din, D, K, dWa, dba, dtok)
+        ws = addon_bwd_workspace(B, N, Din, D, K, tokens.device)
+        _lib.call("pph_addon_bwd", tokens, idx32, Wa, Zs, Zc, dZs, dZc, B, N, Din, D, K, ws, dWa, dba, dtok)
         return dtok, None, dWa, dba, None, None
 
 
@@ -238,6 +239,15 @@ class _SimilarityLogits(torch.autograd.Function):
         ws = bwd_workspace(B, K, D, P, Pg, Zs.device)
         _lib.call("pph_similarity_bwd", g_l, g_g, argmin, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, ws, dZs, dZc, dPl, dPg)
         return dZs, dZc, dPl, dPg, None, None, None, None
+
+
+def addon_bwd_workspace(B, N, Din, D, K, device) -> torch.Tensor:
+    """Scratch for pph_addon_bwd (split-K partials of the add-on weight gradient)."""
+    import ctypes
+    n = ctypes.c_longlong(0)
+    if _lib.load().pph_addon_bwd_ws_bytes(B, N, Din, D, K, ctypes.byref(n)) != 0:
+        raise RuntimeError("pph_addon_bwd_ws_bytes failed")
+    return torch.empty(max(int(n.value), 256), dtype=torch.uint8, device=device)
 
 
 def bwd_workspace(B, K, D, P, Pg, device) -> torch.Tensor:
@@ -396,6 +406,7 @@ class FusedHeadStep:
             self.dZs, self.dZc = e(B, K, D), e(B, D)
             self.dtokens = e(B, 1 + N, Din)
             self.ws = bwd_workspace(B, K, D, P, Pg, device)
+            self.ws_addon = addon_bwd_workspace(B, N, Din, D, K, device)
 
     def step(self, tokens, scores, labels, Wa, ba, P, Pg, Wl, Wg, grads=None, upstream: float = 1.0):
         B, N, Din, D, Pn, Pgn, C, m, H = self.dims
@@ -435,5 +446,5 @@ class FusedHeadStep:
               self.cov_coe * float(upstream), self.mean_coe * float(upstream), B, K, D, Pn, m, N, cfg.act_id,
               float(cfg.eps), float(cfg.ppc_cov_thresh), float(cfg.ppc_mean_thresh), 1, self.dZs, grads["P"])
         c("pph_addon_bwd", tokens, self.idx32, Wa, self.Zs, self.Zc, self.dZs, self.dZc, B, N, Din, D, K,
-          grads["Wa"], grads["ba"], self.dtokens)
+          self.ws_addon, grads["Wa"], grads["ba"], self.dtokens)
         return self.losses

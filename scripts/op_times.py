@@ -65,7 +65,8 @@ with torch.no_grad():
     lt_part = torch.empty(B, device=dev); lt_cnt = torch.zeros(1, dtype=torch.int32, device=dev); lt_out = torch.empty(4, device=dev)
     res["loss_tail"] = timeit("loss_tail", lambda: _lib.call("pph_loss_tail", logits, labels, losses, 0.1, 0.5, 1.0, B, C, lt_part, lt_cnt, lt_out, dlog))
     dWa = torch.empty_like(case["Wa"]); dba = torch.empty(D, device=dev); dtok = torch.empty_like(tok)
-    res["addon_bwd"] = timeit("addon_bwd", lambda: _lib.call("pph_addon_bwd", tok, idx, case["Wa"], tf.Zs, tf.Zc, dZs, dZc, B, N, Din, D, K, dWa, dba, dtok))
+    wsa = ops.addon_bwd_workspace(B, N, Din, D, K, dev)
+    res["addon_bwd"] = timeit("addon_bwd", lambda: _lib.call("pph_addon_bwd", tok, idx, case["Wa"], tf.Zs, tf.Zc, dZs, dZc, B, N, Din, D, K, wsa, dWa, dba, dtok))
     res["torch_cross_entropy_fwd"] = timeit("torch CE fwd", lambda: F.cross_entropy(logits, labels))
     res["torch_zeros_like(P)"] = timeit("torch zeros_like(P)", lambda: torch.zeros_like(pl.P))
     res["torch_add(Zs)"] = timeit("torch add (B,K,D)", lambda: dZs + dZp)

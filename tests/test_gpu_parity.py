@@ -106,7 +106,8 @@ def test_addon_matches_oracle(name):
     idx = ops.select_topk(d["scores"], shape.K)
     tf = ops.addon(d["tokens"], idx, d["Wa"], d["ba"], True)
     Zs, Zc = O.addon(case["tokens"], torch.as_tensor(g["idx"]).long(), case["Wa"], case["ba"])
-    assert rel_close(tf.Zs.cpu(), Zs, 2e-6) and rel_close(tf.Zc.cpu(), Zc, 2e-6)
+    # the add-on GEMM runs as a 3-term bf16 split on tcgen05 (~1e-5 on the pre-activation), sigmoid via ex2/rcp.approx
+    assert rel_close(tf.Zs.cpu(), Zs, 2e-5) and rel_close(tf.Zc.cpu(), Zc, 2e-5)
     assert rel_close(tf.z2s.cpu(), (Zs * Zs).sum(-1), 1e-5)
     assert rel_close(tf.z2c.cpu(), (Zc * Zc).sum(-1), 1e-5)
     # bf16 split of the centred features reconstructs z - 0.5 to ~2^-17 of its magnitude
