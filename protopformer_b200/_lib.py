@@ -44,7 +44,7 @@ _RESTYPES = {"pph_last_error_string": C.c_char_p}
 # kernels launched per entry-point call (memset nodes are not counted); used for the bench's `gpu_launches` claim
 KERNELS_PER_CALL = {
     "pph_select_topk": 1, "pph_addon_fwd": 1, "pph_split_rows": 1, "pph_logits_fwd": 1, "pph_ppc_fwd": 1,
-    "pph_ppc_bwd": 1, "pph_logits_bwd": 1, "pph_similarity_bwd": 4, "pph_addon_bwd": 3, "pph_loss_tail": 1,
+    "pph_ppc_bwd": 1, "pph_logits_bwd": 1, "pph_similarity_bwd": 2, "pph_addon_bwd": 3, "pph_loss_tail": 1,
 }
 
 _lib = None

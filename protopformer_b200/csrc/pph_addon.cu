@@ -279,40 +279,41 @@ struct FwdEpi {
     int K, D;
     struct State { float sq, sq_ctr, sq_hi; };
     __device__ __forceinline__ void init(State& s) const { s.sq = s.sq_ctr = s.sq_hi = 0.f; }
-    // >= 0: element offset of the row inside Zs;  < 0: -(1 + offset inside Zc)
-    __device__ __forceinline__ long row_offset(int r) const {
+    __device__ __forceinline__ void row_ptrs(int r, void* (&p)[3]) const {
         const int b = r / (K + 1), j = r - b * (K + 1);
-        return j < K ? ((long)b * K + j) * D : -(1 + (long)b * D);
+        if (j < K) {
+            const size_t o = ((size_t)b * K + j) * D;
+            p[0] = Zs + o; p[1] = Zs_hi ? Zs_hi + o : nullptr; p[2] = Zs_lo ? Zs_lo + o : nullptr;
+        } else {
+            const size_t o = (size_t)b * D;
+            p[0] = Zc + o; p[1] = Zc_hi ? Zc_hi + o : nullptr; p[2] = Zc_lo ? Zc_lo + o : nullptr;
+        }
     }
     __device__ __forceinline__ void transform(State& s, int, int n0, uint32_t (&acc)[32]) const {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-            if (n0 + i < D) {
-                const float pre = __uint_as_float(acc[i]) + __ldg(ba + n0 + i);
-                const float z = __fdividef(1.0f, 1.0f + __expf(-pre));     // ex2.approx / rcp.approx: ~2^-21 relative
-                const float zc = z - center;
-                const float hf = bf16_to_float(bf16_bits(zc));
-                s.sq = fmaf(z, z, s.sq);
-                s.sq_ctr = fmaf(zc, zc, s.sq_ctr);
-                s.sq_hi = fmaf(hf, hf, s.sq_hi);
-                acc[i] = __float_as_uint(z);
+        for (int i = 0; i < 32; i += 2) {
+            if (n0 + i < D) {          // D is even: columns come in pairs (packed bf16 conversion, F2FP not F2F)
+                const float2 bb = __ldg(reinterpret_cast<const float2*>(ba + n0 + i));
+                const float z0 = __fdividef(1.0f, 1.0f + __expf(-(__uint_as_float(acc[i]) + bb.x)));
+                const float z1 = __fdividef(1.0f, 1.0f + __expf(-(__uint_as_float(acc[i + 1]) + bb.y)));
+                const float c0 = z0 - center, c1 = z1 - center;
+                const __nv_bfloat162 h = __floats2bfloat162_rn(c0, c1);
+                const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+                const float h0 = __uint_as_float(hb << 16), h1 = __uint_as_float(hb & 0xffff0000u);
+                s.sq = fmaf(z0, z0, fmaf(z1, z1, s.sq));
+                s.sq_ctr = fmaf(c0, c0, fmaf(c1, c1, s.sq_ctr));
+                s.sq_hi = fmaf(h0, h0, fmaf(h1, h1, s.sq_hi));
+                acc[i] = __float_as_uint(z0);
+                acc[i + 1] = __float_as_uint(z1);
             }
         }
     }
-    __device__ __forceinline__ void store(long off, int, int n, float z) const {
-        const float zc = z - center;        // tensor-core operands are centred (translation-invariant distance)
-        const uint16_t hb = bf16_bits(zc);
-        const uint16_t lb = bf16_bits(zc - bf16_to_float(hb));
-        if (off >= 0) {
-            Zs[off + n] = z;
-            if (Zs_hi) Zs_hi[off + n] = hb;
-            if (Zs_lo) Zs_lo[off + n] = lb;
-        } else {
-            const long o = -off - 1 + n;
-            Zc[o] = z;
-            if (Zc_hi) Zc_hi[o] = hb;
-            if (Zc_lo) Zc_lo[o] = lb;
-        }
+    __device__ __forceinline__ void store2(void* const* p, int n, float z0, float z1) const {
+        uint32_t hi, lo;
+        tg_split2(z0 - center, z1 - center, hi, lo);      // tensor-core operands are centred
+        *reinterpret_cast<float2*>(static_cast<float*>(p[0]) + n) = make_float2(z0, z1);
+        if (p[1]) *reinterpret_cast<uint32_t*>(static_cast<uint16_t*>(p[1]) + n) = hi;
+        if (p[2]) *reinterpret_cast<uint32_t*>(static_cast<uint16_t*>(p[2]) + n) = lo;
     }
     __device__ __forceinline__ void finish(State& s, int r, int row_local, int cgroup, float* scratch, bool valid) const {
         if (cgroup > 0) {
@@ -417,9 +418,11 @@ struct DxTcEpi {    // scatter rows of dX into the (zero-filled) token gradient
     RowSrc src;
     struct State { int dummy; };
     __device__ __forceinline__ void init(State& s) const { s.dummy = 0; }
-    __device__ __forceinline__ long row_offset(int r) const { return src(r); }
+    __device__ __forceinline__ void row_ptrs(int r, void* (&p)[3]) const { p[0] = dtokens + src(r); }
     __device__ __forceinline__ void transform(State&, int, int, uint32_t (&)[32]) const {}
-    __device__ __forceinline__ void store(long off, int, int n, float v) const { dtokens[off + n] = v; }
+    __device__ __forceinline__ void store2(void* const* p, int n, float v0, float v1) const {
+        *reinterpret_cast<float2*>(static_cast<float*>(p[0]) + n) = make_float2(v0, v1);
+    }
     __device__ __forceinline__ void finish(State&, int, int, int, float*, bool) const {}
 };
 struct WgradPartEpi {   // per-split partial tile [split][D][ldn]
@@ -427,9 +430,11 @@ struct WgradPartEpi {   // per-split partial tile [split][D][ldn]
     int D, ldn;
     struct State { int dummy; };
     __device__ __forceinline__ void init(State& s) const { s.dummy = 0; }
-    __device__ __forceinline__ long row_offset(int d) const { return ((long)blockIdx.y * D + d) * ldn; }
+    __device__ __forceinline__ void row_ptrs(int d, void* (&p)[3]) const { p[0] = part + ((size_t)blockIdx.y * D + d) * ldn; }
     __device__ __forceinline__ void transform(State&, int, int, uint32_t (&)[32]) const {}
-    __device__ __forceinline__ void store(long off, int, int n, float v) const { part[off + n] = v; }
+    __device__ __forceinline__ void store2(void* const* p, int n, float v0, float v1) const {
+        *reinterpret_cast<float2*>(static_cast<float*>(p[0]) + n) = make_float2(v0, v1);
+    }
     __device__ __forceinline__ void finish(State&, int, int, int, float*, bool) const {}
 };
 // dWa[d,din] = sum_s part[s][d][din];  dba[d] = sum_s part[s][d][Din]     (fixed order: deterministic)

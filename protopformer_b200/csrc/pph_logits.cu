@@ -31,16 +31,25 @@ logits_fwd_kernel(const float* __restrict__ act_l, const float* __restrict__ act
         for (int i = 0; i < kLogTB; ++i)
 #pragma unroll
             for (int j = 0; j < kLogTC; ++j) acc[i][j] = 0.f;
+        // register double buffering: the 16 operand loads of iteration i+1 are in flight during the 64 FMAs of iteration i
+        float a[kLogTB], w[kLogTC], an[kLogTB], wn[kLogTC];
+        auto fetch = [&](int p, float (&av)[kLogTB], float (&wv)[kLogTC]) {
+#pragma unroll
+            for (int i = 0; i < kLogTB; ++i) av[i] = (p < Kd && b0 + i < B) ? __ldg(A + (size_t)(b0 + i) * Kd + p) : 0.f;
+#pragma unroll
+            for (int j = 0; j < kLogTC; ++j) wv[j] = (p < Kd && c0 + j < C) ? __ldg(W + (size_t)(c0 + j) * Kd + p) : 0.f;
+        };
+        fetch(tid, a, w);
         for (int p = tid; p < Kd; p += kLogThreads) {
-            float a[kLogTB], w[kLogTC];
-#pragma unroll
-            for (int i = 0; i < kLogTB; ++i) a[i] = (b0 + i < B) ? __ldg(A + (size_t)(b0 + i) * Kd + p) : 0.f;
-#pragma unroll
-            for (int j = 0; j < kLogTC; ++j) w[j] = (c0 + j < C) ? __ldg(W + (size_t)(c0 + j) * Kd + p) : 0.f;
+            fetch(p + kLogThreads, an, wn);
 #pragma unroll
             for (int i = 0; i < kLogTB; ++i)
 #pragma unroll
                 for (int j = 0; j < kLogTC; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+#pragma unroll
+            for (int i = 0; i < kLogTB; ++i) a[i] = an[i];
+#pragma unroll
+            for (int j = 0; j < kLogTC; ++j) w[j] = wn[j];
         }
         // block reduction of the 64 accumulators: warp shuffles, then a fixed-order sum over the 8 warps
 #pragma unroll
@@ -91,8 +100,13 @@ logits_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ d
     const float coef = global ? gc : 1.0f - gc;
     const int tb = tid & 31, tp = tid >> 5;      // images 2*tb, 2*tb+1; prototypes 4*tp .. 4*tp+3
     float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    for (int cc = 0; cc < C; cc += kLbCC) {
-        for (int i = tid; i < kLbCC * kLbTB; i += kLogThreads) {
+    // the next class chunk is fetched into registers while the current one is contracted from shared memory
+    constexpr int NU = kLbCC * kLbTB / kLogThreads, NW = kLbCC * kLbTP / kLogThreads;     // 16, 8
+    float ru[NU], rw[NW];
+    auto fetch = [&](int cc) {
+#pragma unroll
+        for (int q = 0; q < NU; ++q) {
+            const int i = tid + q * kLogThreads;
             const int b = i / kLbCC, c = i - b * kLbCC;       // consecutive threads: consecutive classes (coalesced)
             float v = 0.f;
             if (b0 + b < B && cc + c < C) {
@@ -100,13 +114,31 @@ logits_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ d
                 v = coef * __ldg(dlogits + o);
                 if (extra) v += __ldg(extra + o);
             }
-            up[c][b] = v;
+            ru[q] = v;
         }
-        for (int i = tid; i < kLbCC * kLbTP; i += kLogThreads) {
+#pragma unroll
+        for (int q = 0; q < NW; ++q) {
+            const int i = tid + q * kLogThreads;
             const int c = i / kLbTP, p = i - c * kLbTP;
-            wt[c][p] = (cc + c < C && p0 + p < np) ? __ldg(W + (size_t)(cc + c) * np + p0 + p) : 0.f;
+            rw[q] = (cc + c < C && p0 + p < np) ? __ldg(W + (size_t)(cc + c) * np + p0 + p) : 0.f;
+        }
+    };
+    fetch(0);
+    for (int cc = 0; cc < C; cc += kLbCC) {
+#pragma unroll
+        for (int q = 0; q < NU; ++q) {
+            const int i = tid + q * kLogThreads;
+            const int b = i / kLbCC, c = i - b * kLbCC;
+            up[c][b] = ru[q];
+        }
+#pragma unroll
+        for (int q = 0; q < NW; ++q) {
+            const int i = tid + q * kLogThreads;
+            const int c = i / kLbTP, p = i - c * kLbTP;
+            wt[c][p] = rw[q];
         }
         __syncthreads();
+        if (cc + kLbCC < C) fetch(cc + kLbCC);
 #pragma unroll 8
         for (int c = 0; c < kLbCC; ++c) {
             const float2 u = *reinterpret_cast<const float2*>(&up[c][2 * tb]);

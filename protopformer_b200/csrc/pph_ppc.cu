@@ -54,14 +54,26 @@ static size_t ppc_smem_bytes(int m, int D, int K, int kc) {
     return sizeof(float) * ((size_t)m * D + (size_t)kc * (D + 4) + 2 * (size_t)m * K + 8 * (size_t)m);
 }
 
-// stage token rows [k0, k0+n) of image b into shared memory (float4, coalesced)
+// stage token rows [k0, k0+n) of image b into shared memory (float4, coalesced).  Thread = (row lane, float4 column);
+// 8 independent loads are in flight per thread before the first shared store (one L2 latency per 8 rows).
 __device__ __forceinline__ void ppc_stage_tokens(const float* __restrict__ Zb, float* Zt, int zstride, int D, int k0,
                                                  int n) {
-    const int d4 = D >> 2;
-    for (int i = threadIdx.x; i < n * d4; i += kPpcThreads) {
-        const int r = i / d4, c = i - r * d4;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(Zb + (size_t)(k0 + r) * D) + c);
-        *reinterpret_cast<float4*>(Zt + (size_t)r * zstride + 4 * c) = v;
+    const int d4 = D >> 2;                              // <= 128
+    const int rpp = kPpcThreads / d4;                   // rows per pass
+    const int c = threadIdx.x % d4, r0 = threadIdx.x / d4;
+    if (r0 >= rpp) return;
+    for (int rb = r0; rb < n; rb += 8 * rpp) {
+        float4 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int r = rb + u * rpp;
+            if (r < n) v[u] = __ldg(reinterpret_cast<const float4*>(Zb + (size_t)(k0 + r) * D) + c);
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int r = rb + u * rpp;
+            if (r < n) *reinterpret_cast<float4*>(Zt + (size_t)r * zstride + 4 * c) = v[u];
+        }
     }
 }
 

@@ -98,13 +98,13 @@ bin_tokens_kernel(const int32_t* __restrict__ argmin_l, int K, int P, int32_t* _
 }
 
 // ---- gather kernels (templated on DV = ceil(D / 32) register slots per lane) ---------------------------------------
-template <int DV>
-__global__ void __launch_bounds__(256)
-proto_grad_kernel(const float* __restrict__ g_l, const float* __restrict__ g_g, const int32_t* __restrict__ argmin_l,
-                  const float* __restrict__ Zs, const float* __restrict__ Zc, const float* __restrict__ Pl,
-                  const float* __restrict__ Pgl, int B, int K, int D, int P, int Pg,
-                  float* __restrict__ dPl, float* __restrict__ dPg) {
-    const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+template <int DV, bool FULL>
+__device__ __forceinline__ void
+proto_grad_body(int vb, const float* __restrict__ g_l, const float* __restrict__ g_g, const int32_t* __restrict__ argmin_l,
+                const float* __restrict__ Zs, const float* __restrict__ Zc, const float* __restrict__ Pl,
+                const float* __restrict__ Pgl, int B, int K, int D, int P, int Pg,
+                float* __restrict__ dPl, float* __restrict__ dPg) {
+    const int row = vb * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= P + Pg) return;
     const bool global = row >= P;
     const int p = global ? row - P : row;
@@ -135,7 +135,7 @@ proto_grad_kernel(const float* __restrict__ g_l, const float* __restrict__ g_g, 
 #pragma unroll
             for (int u = 0; u < 8; ++u)
 #pragma unroll
-                for (int i = 0; i < DV; ++i) v[u][i] = (i * 32 + lane < D) ? __ldg(zr[u] + i * 32 + lane) : 0.f;
+                for (int i = 0; i < DV; ++i) v[u][i] = (FULL || i * 32 + lane < D) ? __ldg(zr[u] + i * 32 + lane) : 0.f;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 gsum += gg[u];
@@ -148,20 +148,20 @@ proto_grad_kernel(const float* __restrict__ g_l, const float* __restrict__ g_g, 
     float* out = (global ? dPg : dPl) + (size_t)p * D;
 #pragma unroll
     for (int i = 0; i < DV; ++i)
-        if (i * 32 + lane < D) out[i * 32 + lane] = 2.0f * (__ldg(pr + i * 32 + lane) * gsum - acc[i]);
+        if (FULL || i * 32 + lane < D) out[i * 32 + lane] = 2.0f * (__ldg(pr + i * 32 + lane) * gsum - acc[i]);
 }
 
 // One warp per work item = (image, token, chunk of <= kBinChunk bin entries).  Single-chunk bins write their row
 // directly; multi-chunk bins (skewed argmin distributions put hundreds of prototypes on one token) write partials
 // and the last warp to finish adds them in chunk order -> balanced AND deterministic.
-template <int DV>
-__global__ void __launch_bounds__(256)
-token_grad_kernel(const float* __restrict__ g_l, const int32_t* __restrict__ bin_start,
-                  const int32_t* __restrict__ item_start, const int32_t* __restrict__ bin_list,
-                  const float* __restrict__ Zs, const float* __restrict__ Pl, int B, int K, int D, int P,
-                  int items_per_image, float* part, float* part_gsum, unsigned int* counters,
-                  float* __restrict__ dZs) {
-    const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+template <int DV, bool FULL>
+__device__ __forceinline__ void
+token_grad_body(int vb, const float* __restrict__ g_l, const int32_t* __restrict__ bin_start,
+                const int32_t* __restrict__ item_start, const int32_t* __restrict__ bin_list,
+                const float* __restrict__ Zs, const float* __restrict__ Pl, int B, int K, int D, int P,
+                int items_per_image, float* part, float* part_gsum, unsigned int* counters,
+                float* __restrict__ dZs) {
+    const int gw = vb * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int b = gw / items_per_image, item = gw - b * items_per_image;
     if (b >= B) return;
     const int32_t* ist = item_start + (size_t)b * (K + 1);
@@ -205,7 +205,7 @@ token_grad_kernel(const float* __restrict__ g_l, const int32_t* __restrict__ bin
 #pragma unroll
             for (int u = 0; u < 8; ++u)
 #pragma unroll
-                for (int i = 0; i < DV; ++i) v[u][i] = (i * 32 + lane < D) ? __ldg(pr[u] + i * 32 + lane) : 0.f;
+                for (int i = 0; i < DV; ++i) v[u][i] = (FULL || i * 32 + lane < D) ? __ldg(pr[u] + i * 32 + lane) : 0.f;
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 gsum += gg[u];
@@ -220,13 +220,13 @@ token_grad_kernel(const float* __restrict__ g_l, const int32_t* __restrict__ bin
     if (nchunks == 1) {
 #pragma unroll
         for (int i = 0; i < DV; ++i)
-            if (i * 32 + lane < D) out[i * 32 + lane] = 2.0f * (__ldg(zr + i * 32 + lane) * gsum - acc[i]);
+            if (FULL || i * 32 + lane < D) out[i * 32 + lane] = 2.0f * (__ldg(zr + i * 32 + lane) * gsum - acc[i]);
         return;
     }
     const size_t slot = (size_t)b * items_per_image + item;                 // partial slot of this chunk
 #pragma unroll
     for (int i = 0; i < DV; ++i)
-        if (i * 32 + lane < D) part[slot * D + i * 32 + lane] = acc[i];
+        if (FULL || i * 32 + lane < D) part[slot * D + i * 32 + lane] = acc[i];
     if (lane == 0) part_gsum[slot] = gsum;
     __threadfence();
     __syncwarp();
@@ -244,11 +244,11 @@ token_grad_kernel(const float* __restrict__ g_l, const int32_t* __restrict__ bin
         gt += __ldcg(part_gsum + slot0 + c);
 #pragma unroll
         for (int i = 0; i < DV; ++i)
-            if (i * 32 + lane < D) tot[i] += __ldcg(part + (slot0 + c) * D + i * 32 + lane);
+            if (FULL || i * 32 + lane < D) tot[i] += __ldcg(part + (slot0 + c) * D + i * 32 + lane);
     }
 #pragma unroll
     for (int i = 0; i < DV; ++i)
-        if (i * 32 + lane < D) out[i * 32 + lane] = 2.0f * (__ldg(zr + i * 32 + lane) * gt - tot[i]);
+        if (FULL || i * 32 + lane < D) out[i * 32 + lane] = 2.0f * (__ldg(zr + i * 32 + lane) * gt - tot[i]);
     if (lane == 0) counters[row] = 0u;                                       // self-resetting (graph replay)
 }
 
@@ -257,13 +257,13 @@ token_grad_kernel(const float* __restrict__ g_l, const int32_t* __restrict__ bin
 // `part` [slices][B][D], then the last CTA of each image group adds the slices in order (deterministic).
 constexpr int kClsTB = 8, kClsThreads = 256;
 
-__global__ void __launch_bounds__(kClsThreads)
-cls_grad_kernel(const float* __restrict__ g_g, const float* __restrict__ Zc, const float* __restrict__ Pgl,
-                int B, int D, int Pg, int p_per_slice, float* part, unsigned int* counters,
-                float* __restrict__ dZc) {
-    __shared__ float gs[kClsTB][64];
+__device__ __forceinline__ void
+cls_grad_body(int slice, int bgroup, int nslices, const float* __restrict__ g_g, const float* __restrict__ Zc,
+              const float* __restrict__ Pgl, int B, int D, int Pg, int p_per_slice, float* part,
+              unsigned int* counters, float* __restrict__ dZc) {
+    __shared__ __align__(16) float gs[64][kClsTB];      // [prototype][image]: two 128-bit broadcast reads per prototype
     __shared__ unsigned int s_ticket;
-    const int tid = threadIdx.x, b0 = blockIdx.y * kClsTB, slice = blockIdx.x, nslices = gridDim.x;
+    const int tid = threadIdx.x, b0 = bgroup * kClsTB;
     const int pa = slice * p_per_slice, pb = min(Pg, pa + p_per_slice);
     float acc[kClsTB][2];           // D <= 512: each thread owns columns tid, tid + 256
     float gsum[kClsTB];
@@ -273,7 +273,7 @@ cls_grad_kernel(const float* __restrict__ g_g, const float* __restrict__ Zc, con
         __syncthreads();
         for (int i = tid; i < kClsTB * 64; i += kClsThreads) {
             const int bi = i >> 6, pp = p0 + (i & 63);
-            gs[bi][i & 63] = (b0 + bi < B && pp < pb) ? __ldg(g_g + (size_t)(b0 + bi) * Pg + pp) : 0.f;
+            gs[i & 63][bi] = (b0 + bi < B && pp < pb) ? __ldg(g_g + (size_t)(b0 + bi) * Pg + pp) : 0.f;
         }
         __syncthreads();
         const int n = min(64, pb - p0);
@@ -282,12 +282,13 @@ cls_grad_kernel(const float* __restrict__ g_g, const float* __restrict__ Zc, con
             const float* pr = Pgl + (size_t)(p0 + q) * D;
             const float v0 = tid < D ? __ldg(pr + tid) : 0.f;
             const float v1 = tid + 256 < D ? __ldg(pr + tid + 256) : 0.f;
+            const float4 ga = *reinterpret_cast<const float4*>(&gs[q][0]), gb2 = *reinterpret_cast<const float4*>(&gs[q][4]);
+            const float gq8[8] = {ga.x, ga.y, ga.z, ga.w, gb2.x, gb2.y, gb2.z, gb2.w};
 #pragma unroll
             for (int i = 0; i < kClsTB; ++i) {
-                const float gq = gs[i][q];
-                gsum[i] += gq;
-                acc[i][0] = fmaf(gq, v0, acc[i][0]);
-                acc[i][1] = fmaf(gq, v1, acc[i][1]);
+                gsum[i] += gq8[i];
+                acc[i][0] = fmaf(gq8[i], v0, acc[i][0]);
+                acc[i][1] = fmaf(gq8[i], v1, acc[i][1]);
             }
         }
     }
@@ -304,7 +305,7 @@ cls_grad_kernel(const float* __restrict__ g_g, const float* __restrict__ Zc, con
     }
     __threadfence();
     __syncthreads();
-    if (tid == 0) s_ticket = atomicAdd(counters + blockIdx.y, 1u);
+    if (tid == 0) s_ticket = atomicAdd(counters + bgroup, 1u);
     __syncthreads();
     if (s_ticket == (unsigned int)(nslices - 1)) {
         __threadfence();
@@ -317,7 +318,7 @@ cls_grad_kernel(const float* __restrict__ g_g, const float* __restrict__ Zc, con
                 dZc[(size_t)b * D + d] = s;
             }
         }
-        if (tid == 0) counters[blockIdx.y] = 0u;       // self-resetting (graph replay)
+        if (tid == 0) counters[bgroup] = 0u;       // self-resetting (graph replay)
     }
 }
 
@@ -348,18 +349,49 @@ static BwdWorkspace carve_ws(void* base, int B, int K, int D, int P, int Pg) {
     return w;
 }
 
-template <int DV>
+// One launch for the three independent gradient pieces (CLS-token slices, prototype rows, token work items): their
+// CTAs share the machine instead of running as three partially filled waves back to back.
+template <int DV, bool FULL>
+__global__ void __launch_bounds__(256)
+sim_grads_kernel(const float* __restrict__ g_l, const float* __restrict__ g_g, const int32_t* __restrict__ argmin_l,
+                 const int32_t* __restrict__ bin_start, const int32_t* __restrict__ item_start,
+                 const int32_t* __restrict__ bin_list, const float* __restrict__ Zs, const float* __restrict__ Zc,
+                 const float* __restrict__ Pl, const float* __restrict__ Pgl, int B, int K, int D, int P, int Pg,
+                 int items_per_image, int n_cls, int n_slices, int p_per_slice, int n_proto,
+                 float* tok_part, float* tok_gsum, unsigned int* tok_counters, float* cls_part,
+                 unsigned int* cls_counters, float* __restrict__ dZs, float* __restrict__ dZc,
+                 float* __restrict__ dPl, float* __restrict__ dPg) {
+    int vb = blockIdx.x;
+    if (vb < n_cls) {
+        cls_grad_body(vb % n_slices, vb / n_slices, n_slices, g_g, Zc, Pgl, B, D, Pg, p_per_slice, cls_part, cls_counters, dZc);
+        return;
+    }
+    vb -= n_cls;
+    if (vb < n_proto) {
+        proto_grad_body<DV, FULL>(vb, g_l, g_g, argmin_l, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, dPl, dPg);
+        return;
+    }
+    vb -= n_proto;
+    token_grad_body<DV, FULL>(vb, g_l, bin_start, item_start, bin_list, Zs, Pl, B, K, D, P, items_per_image, tok_part,
+                              tok_gsum, tok_counters, dZs);
+}
+
+template <int DV, bool FULL>
 static int launch_bwd(const float* g_l, const float* g_g, const int32_t* argmin_l, const BwdWorkspace& w,
                       const float* Zs, const float* Zc, const float* Pl, const float* Pgl,
-                      int B, int K, int D, int P, int Pg, float* dZs, float* dPl, float* dPg, cudaStream_t st) {
-    proto_grad_kernel<DV><<<ceil_div(P + Pg, 8), 256, 0, st>>>(g_l, g_g, argmin_l, Zs, Zc, Pl, Pgl, B, K, D, P, Pg,
-                                                               dPl, dPg);
-    int rc = launch_status("pph_similarity_bwd(proto)");
-    if (rc) return rc;
-    token_grad_kernel<DV><<<ceil_div(B * w.items_per_image, 8), 256, 0, st>>>(
-        g_l, w.bin_start, w.item_start, w.bin_list, Zs, Pl, B, K, D, P, w.items_per_image, w.tok_part, w.tok_gsum,
-        w.tok_counters, dZs);
-    return launch_status("pph_similarity_bwd(token)");
+                      int B, int K, int D, int P, int Pg, float* dZs, float* dZc, float* dPl, float* dPg,
+                      cudaStream_t st) {
+    const int slices = 16;
+    const int p_per_slice = Pg > 0 ? ceil_div(ceil_div(Pg, slices), 64) * 64 : 64;
+    const int nsl = Pg > 0 ? ceil_div(Pg, p_per_slice) : 0;
+    const int n_cls = nsl * ceil_div(B, kClsTB);
+    const int n_proto = ceil_div(P + Pg, 8);
+    const int n_tok = ceil_div(B * w.items_per_image, 8);
+    sim_grads_kernel<DV, FULL><<<n_cls + n_proto + n_tok, 256, 0, st>>>(
+        g_l, g_g, argmin_l, w.bin_start, w.item_start, w.bin_list, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, w.items_per_image,
+        n_cls, nsl, p_per_slice, n_proto, w.tok_part, w.tok_gsum, w.tok_counters, w.cls_part, w.cls_counters, dZs, dZc,
+        dPl, dPg);
+    return launch_status("pph_similarity_bwd(grads)");
 }
 
 }  // namespace pph
@@ -394,19 +426,15 @@ extern "C" int pph_similarity_bwd(const float* g_l, const float* g_g, const int3
     int rc = launch_status("pph_similarity_bwd(bin)");
     if (rc) return rc;
     const int dv = ceil_div(D, 32);
-    if (dv <= 2) rc = launch_bwd<2>(g_l, g_g, argmin_l, w, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, dZs, dPl, dPg, st);
-    else if (dv <= 6) rc = launch_bwd<6>(g_l, g_g, argmin_l, w, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, dZs, dPl, dPg, st);
-    else if (dv <= 12) rc = launch_bwd<12>(g_l, g_g, argmin_l, w, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, dZs, dPl, dPg, st);
-    else rc = launch_bwd<16>(g_l, g_g, argmin_l, w, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, dZs, dPl, dPg, st);
-    if (rc) return rc;
-    if (Pg > 0) {
-        const int slices = 16;
-        const int p_per_slice = ceil_div(ceil_div(Pg, slices), 64) * 64;
-        const int nsl = ceil_div(Pg, p_per_slice);
-        cls_grad_kernel<<<dim3(nsl, ceil_div(B, kClsTB)), kClsThreads, 0, st>>>(g_g, Zc, Pgl, B, D, Pg, p_per_slice,
-                                                                            w.cls_part, w.cls_counters, dZc);
-        rc = launch_status("pph_similarity_bwd(cls)");
-        if (rc) return rc;
-    }
-    return 0;
+    const bool full = (D % 32 == 0);
+#define PPH_BWD(DV, FULL) launch_bwd<DV, FULL>(g_l, g_g, argmin_l, w, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, dZs, dZc, dPl, dPg, st)
+    if (full && dv == 2) rc = PPH_BWD(2, true);
+    else if (full && dv == 6) rc = PPH_BWD(6, true);
+    else if (full && dv == 12) rc = PPH_BWD(12, true);
+    else if (dv <= 2) rc = PPH_BWD(2, false);
+    else if (dv <= 6) rc = PPH_BWD(6, false);
+    else if (dv <= 12) rc = PPH_BWD(12, false);
+    else rc = PPH_BWD(16, false);
+#undef PPH_BWD
+    return rc;
 }

@@ -74,6 +74,95 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Drain one accumulator tile: thread = prototype row (TMEM lane), walks its columns with tcgen05.ld.
+template <int KT>
+__device__ __forceinline__ void tc_epilogue_tile(const TcParams& prm, const TcTile& t, uint32_t taddr, const float* x2,
+                                                 const float4* x2v, int quarter, int lane) {
+    const int p = t.mt * kTcBlockM + quarter * 32 + lane;
+    if (!t.is_global) {
+        const bool pv = p < prm.P;
+        const float p2 = pv ? __ldg(prm.p2l + p) : 0.f;
+        const int b0 = t.grp * prm.G;
+        auto store = [&](int g, float best, int bk) {
+            const int b = b0 + g;
+            if (pv && b < prm.B) {
+                const float d = fmaxf(best + p2, 0.0f);
+                const size_t o = (size_t)b * prm.P + p;
+                prm.dmin_l[o] = d;
+                prm.argmin_l[o] = bk;
+                prm.act_l[o] = act_of_dist(d, prm.act_fn, prm.eps);
+            }
+        };
+        float best = INFINITY;
+        int bk = 0;
+        if constexpr (KT > 0) {
+            constexpr int GS = kTcMaxN / KT, TC = GS * KT;
+#pragma unroll
+            for (int ch = 0; ch < (TC + 31) / 32; ++ch) {
+                uint32_t v[32];
+                ptx::tmem_ld_32x32(taddr + ch * 32, v);
+                float4 xq[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) xq[i] = x2v[ch * 8 + i];
+                ptx::tmem_ld_wait(v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int col = ch * 32 + j;
+                    if (col < TC) {
+                        const int k = col % KT, g = col / KT;
+                        const float4 q = xq[j >> 2];
+                        const float xx = (j & 3) == 0 ? q.x : (j & 3) == 1 ? q.y : (j & 3) == 2 ? q.z : q.w;
+                        const float d = fmaf(-2.0f, __uint_as_float(v[j]), xx);
+                        if (k == 0) { best = d; bk = 0; }
+                        else if (d < best) { best = d; bk = k; }
+                        if (k == KT - 1) store(g, best, bk);
+                    }
+                }
+            }
+        } else {
+            const int Kc = prm.K;
+            const int gcnt = min(prm.G, prm.B - b0);
+            const int ncols = gcnt * Kc;
+            int g = 0, k = 0;
+            for (int c0 = 0; c0 < ncols; c0 += 32) {
+                uint32_t v[32];
+                ptx::tmem_ld_32x32(taddr + c0, v);
+                ptx::tmem_ld_wait(v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    if (c0 + j < ncols) {
+                        const float d = fmaf(-2.0f, __uint_as_float(v[j]), x2[c0 + j]);
+                        if (d < best) { best = d; bk = k; }
+                        if (++k == Kc) {
+                            store(g, best, bk);
+                            ++g; k = 0; best = INFINITY; bk = 0;
+                        }
+                    }
+                }
+            }
+        }
+    } else {
+        const bool pv = p < prm.Pg;
+        const float p2 = pv ? __ldg(prm.p2g + p) : 0.f;
+        const int b0 = t.grp * kTcMaxN;
+        const int ncols = min(prm.B - b0, kTcMaxN);
+        for (int c0 = 0; c0 < ncols; c0 += 32) {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32(taddr + c0, v);
+            ptx::tmem_ld_wait(v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (c0 + j < ncols && pv) {
+                    const float d = fmaxf(fmaf(-2.0f, __uint_as_float(v[j]), x2[c0 + j]) + p2, 0.0f);
+                    const size_t o = (size_t)(b0 + c0 + j) * prm.Pg + p;
+                    prm.dmin_g[o] = d;
+                    prm.act_g[o] = act_of_dist(d, prm.act_fn, prm.eps);
+                }
+            }
+        }
+    }
+}
+
 template <int NTERMS, int KT>
 __global__ void __launch_bounds__(kTcThreads, 1)
 similarity_tc_kernel(const __grid_constant__ CUtensorMap tmAl_hi, const __grid_constant__ CUtensorMap tmAl_lo,
@@ -199,94 +288,11 @@ similarity_tc_kernel(const __grid_constant__ CUtensorMap tmAl_hi, const __grid_c
                 for (int c = gtid; c < kTcMaxN; c += 128) x2[c] = (b0 + c < prm.B) ? __ldg(prm.z2c + b0 + c) : 0.f;
             }
             named_bar_sync(1 + grp_id, 128);
-            const int p = t.mt * kTcBlockM + quarter * 32 + lane;
             const uint32_t taddr = tmem_base + (uint32_t)grp_id * kTcMaxN + ((uint32_t)(quarter * 32) << 16);
 
             ptx::mbar_wait(&tmem_full[grp_id], acc_phase);
             ptx::tc_fence_after();
-
-            if (!t.is_global) {
-                const bool pv = p < prm.P;
-                const float p2 = pv ? __ldg(prm.p2l + p) : 0.f;
-                const int b0 = t.grp * prm.G;
-                auto store = [&](int g, float best, int bk) {
-                    const int b = b0 + g;
-                    if (pv && b < prm.B) {
-                        const float d = fmaxf(best + p2, 0.0f);
-                        const size_t o = (size_t)b * prm.P + p;
-                        prm.dmin_l[o] = d;
-                        prm.argmin_l[o] = bk;
-                        prm.act_l[o] = act_of_dist(d, prm.act_fn, prm.eps);
-                    }
-                };
-                float best = INFINITY;
-                int bk = 0;
-                if constexpr (KT > 0) {
-                    constexpr int GS = kTcMaxN / KT, TC = GS * KT;
-#pragma unroll
-                    for (int ch = 0; ch < (TC + 31) / 32; ++ch) {
-                        uint32_t v[32];
-                        ptx::tmem_ld_32x32(taddr + ch * 32, v);
-                        float4 xq[8];
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) xq[i] = x2v[ch * 8 + i];
-                        ptx::tmem_ld_wait(v);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const int col = ch * 32 + j;
-                            if (col < TC) {
-                                const int k = col % KT, g = col / KT;
-                                const float4 q = xq[j >> 2];
-                                const float xx = (j & 3) == 0 ? q.x : (j & 3) == 1 ? q.y : (j & 3) == 2 ? q.z : q.w;
-                                const float d = fmaf(-2.0f, __uint_as_float(v[j]), xx);
-                                if (k == 0) { best = d; bk = 0; }
-                                else if (d < best) { best = d; bk = k; }
-                                if (k == KT - 1) store(g, best, bk);
-                            }
-                        }
-                    }
-                } else {
-                    const int Kc = prm.K;
-                    const int gcnt = min(prm.G, prm.B - b0);
-                    const int ncols = gcnt * Kc;
-                    int g = 0, k = 0;
-                    for (int c0 = 0; c0 < ncols; c0 += 32) {
-                        uint32_t v[32];
-                        ptx::tmem_ld_32x32(taddr + c0, v);
-                        ptx::tmem_ld_wait(v);
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            if (c0 + j < ncols) {
-                                const float d = fmaf(-2.0f, __uint_as_float(v[j]), x2[c0 + j]);
-                                if (d < best) { best = d; bk = k; }
-                                if (++k == Kc) {
-                                    store(g, best, bk);
-                                    ++g; k = 0; best = INFINITY; bk = 0;
-                                }
-                            }
-                        }
-                    }
-                }
-            } else {
-                const bool pv = p < prm.Pg;
-                const float p2 = pv ? __ldg(prm.p2g + p) : 0.f;
-                const int b0 = t.grp * kTcMaxN;
-                const int ncols = min(prm.B - b0, kTcMaxN);
-                for (int c0 = 0; c0 < ncols; c0 += 32) {
-                    uint32_t v[32];
-                    ptx::tmem_ld_32x32(taddr + c0, v);
-                    ptx::tmem_ld_wait(v);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        if (c0 + j < ncols && pv) {
-                            const float d = fmaxf(fmaf(-2.0f, __uint_as_float(v[j]), x2[c0 + j]) + p2, 0.0f);
-                            const size_t o = (size_t)(b0 + c0 + j) * prm.Pg + p;
-                            prm.dmin_g[o] = d;
-                            prm.act_g[o] = act_of_dist(d, prm.act_fn, prm.eps);
-                        }
-                    }
-                }
-            }
+            tc_epilogue_tile<KT>(prm, t, taddr, x2, x2v, quarter, lane);
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&tmem_empty[grp_id]);

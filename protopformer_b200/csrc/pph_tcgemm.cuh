@@ -39,17 +39,21 @@ constexpr int kTgBK = 64;
 constexpr int kTgMaxBN = 256;
 
 __host__ __device__ inline size_t tcgemm_stage_bytes(int BN) { return (size_t)2 * (kTgBM + BN) * kTgBK * 2; }
-inline size_t tcgemm_smem_bytes(int BN) { return 1024 + 2 * tcgemm_stage_bytes(BN) + 128 * 16 * 4 + 128 * 8 + 256; }
+inline size_t tcgemm_smem_bytes(int BN) { return 1024 + 2 * tcgemm_stage_bytes(BN) + 128 * 16 * 4 + 128 * 3 * 8 + 256; }
+
+// (v0, v1) -> packed bf16x2 hi word and bf16x2 lo word (cvt.rn.bf16x2.f32: one instruction per pair)
+__device__ __forceinline__ void tg_split2(float v0, float v1, uint32_t& hi, uint32_t& lo) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const float r0 = v0 - __uint_as_float(hi << 16), r1 = v1 - __uint_as_float(hi & 0xffff0000u);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 __device__ __forceinline__ void tg_store_split8(uint8_t* hi_tile, uint8_t* lo_tile, int row, int c, const float (&v)[8]) {
     uint32_t h[4], l[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const uint16_t h0 = bf16_bits(v[2 * i]), h1 = bf16_bits(v[2 * i + 1]);
-        const uint16_t l0 = bf16_bits(v[2 * i] - bf16_to_float(h0)), l1 = bf16_bits(v[2 * i + 1] - bf16_to_float(h1));
-        h[i] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-        l[i] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-    }
+    for (int i = 0; i < 4; ++i) tg_split2(v[2 * i], v[2 * i + 1], h[i], l[i]);
     const int off = row * 128 + ((c ^ (row & 7)) << 4);
     *reinterpret_cast<uint4*>(hi_tile + off) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(lo_tile + off) = make_uint4(l[0], l[1], l[2], l[3]);
@@ -60,9 +64,9 @@ __device__ __forceinline__ void tg_store_split8(uint8_t* hi_tile, uint8_t* lo_ti
 //   __device__ void load8(int row, int k0, float (&v)[8]) const; // values (row, k0..k0+7); zeros outside the operand
 // Epilogue functor contract:
 //   struct State;  __device__ void init(State&) const;
-//   __device__ long row_offset(int m) const;                                   // any per-row value store() needs
+//   __device__ void row_ptrs(int m, void* (&p)[3]) const;                      // up to 3 output row base pointers
 //   __device__ void transform(State&, int m, int n0, uint32_t (&acc)[32]) const;  // thread = row m, in place
-//   __device__ void store(long row_off, int m, int n, float v) const;           // lane = column n (coalesced)
+//   __device__ void store2(void* const* p, int n, float v0, float v1) const;   // columns n, n+1 (n even), coalesced
 //   __device__ void finish(State&, int m, int row_local, int cgroup, float* scratch, bool valid) const;
 template <class AOp, class BOp, class Epi>
 __global__ void __launch_bounds__(kTgThreads, 1)
@@ -72,8 +76,8 @@ tcgemm_kernel(int M, int N, int Kd, int BN, int k_per_split, AOp a_op, BOp b_op,
     const size_t stage_bytes = tcgemm_stage_bytes(BN);
     const int a_bytes = kTgBM * kTgBK * 2, b_bytes = BN * kTgBK * 2;
     float* scratch = reinterpret_cast<float*>(smem + 2 * stage_bytes);                        // [128][16]
-    long* rowoff = reinterpret_cast<long*>(smem + 2 * stage_bytes + 128 * 16 * 4);            // [128]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes + 128 * 16 * 4 + 128 * 8);
+    void** rowptr = reinterpret_cast<void**>(smem + 2 * stage_bytes + 128 * 16 * 4);          // [128][3]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes + 128 * 16 * 4 + 128 * 3 * 8);
     uint64_t* empty = bars;            // [2]
     uint64_t* acc_done = bars + 2;     // [1]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 3);
@@ -90,7 +94,11 @@ tcgemm_kernel(int M, int N, int Kd, int BN, int k_per_split, AOp a_op, BOp b_op,
         ptx::fence_mbar_init();
     }
     if (warp == 1) ptx::tmem_alloc(tmem_ptr, 256);
-    if (tid >= 128 && tid < 256) rowoff[tid - 128] = (m0 + tid - 128 < M) ? epi.row_offset(m0 + tid - 128) : 0;
+    if (tid >= 128 && tid < 256) {
+        void* p3[3] = {nullptr, nullptr, nullptr};
+        if (m0 + tid - 128 < M) epi.row_ptrs(m0 + tid - 128, p3);
+        rowptr[(tid - 128) * 3 + 0] = p3[0]; rowptr[(tid - 128) * 3 + 1] = p3[1]; rowptr[(tid - 128) * 3 + 2] = p3[2];
+    }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -102,57 +110,63 @@ tcgemm_kernel(int M, int N, int Kd, int BN, int k_per_split, AOp a_op, BOp b_op,
     epi.init(st);
     const int quarter = warp & 3, cgroup = warp >> 2;
     const int m_row = m0 + quarter * 32 + lane;
-    float* tstage = reinterpret_cast<float*>(smem) + warp * (32 * 33);     // per-warp transpose tile (stages are idle then)
+    float* tstage = reinterpret_cast<float*>(smem) + warp * (32 * 34);     // per-warp transpose tile (stages are idle then)
     int fill = 0;                                   // k-blocks filled so far (stage = fill & 1)
     int ntile = 0;
+    // A values of the NEXT k-block are fetched one iteration ahead (its rows are usually the HBM-latency operand)
+    float va[2][8];
+    auto load_a = [&](int kb) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int g = tid + i * kTgThreads;
+            const int row = AOp::kContigK ? (g >> 3) : (g & (kTgBM - 1));
+            const int c = AOp::kContigK ? (g & 7) : (g >> 7);
+            a_op.load8(m0 + row, kb + c * 8, va[i]);
+        }
+    };
+    load_a(kz0);
     for (int n0 = 0; n0 < N; n0 += BN, ++ntile) {
         for (int kb = kz0; kb < kz1; kb += kTgBK, ++fill) {
             const int stage = fill & 1, use = fill >> 1;
-            if (use > 0) ptx::mbar_wait(&empty[stage], (uint32_t)(use - 1) & 1u);   // MMAs that read this stage retired
             uint8_t* sA_hi = smem + stage * stage_bytes;
             uint8_t* sA_lo = sA_hi + a_bytes;
             uint8_t* sB_hi = sA_lo + a_bytes;
             uint8_t* sB_lo = sB_hi + b_bytes;
-            // ---- fill A (128 rows x 8 chunks = 2 groups per thread) and the first 2 groups of B: all global loads
-            //      are issued before the first conversion, so one memory latency is exposed per batch, not per group
+            // ---- issue the B loads of this k-block (first 2 groups) ...
+            float vb[2][8];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int g = tid + i * kTgThreads;
+                if (g < BN * 8) {
+                    const int row = BOp::kContigK ? (g >> 3) : (g % BN);
+                    const int c = BOp::kContigK ? (g & 7) : (g / BN);
+                    b_op.load8(n0 + row, kb + c * 8, vb[i]);
+                }
+            }
+            if (use > 0) ptx::mbar_wait(&empty[stage], (uint32_t)(use - 1) & 1u);   // MMAs that read this stage retired
+            // ---- ... convert + store the prefetched A, then fetch the next k-block's A behind it
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int g = tid + i * kTgThreads;
+                const int row = AOp::kContigK ? (g >> 3) : (g & (kTgBM - 1));
+                const int c = AOp::kContigK ? (g & 7) : (g >> 7);
+                tg_store_split8(sA_hi, sA_lo, row, c, va[i]);
+            }
             {
-                float va[2][8], vb[2][8];
+                const int kb_next = kb + kTgBK < kz1 ? kb + kTgBK : kz0;      // wraps to the next column tile
+                if (kb + kTgBK < kz1 || n0 + BN < N) load_a(kb_next);
+            }
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int g = tid + i * kTgThreads;
-                    const int row = AOp::kContigK ? (g >> 3) : (g & (kTgBM - 1));
-                    const int c = AOp::kContigK ? (g & 7) : (g >> 7);
-                    a_op.load8(m0 + row, kb + c * 8, va[i]);
-                }
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int g = tid + i * kTgThreads;
-                    if (g < BN * 8) {
-                        const int row = BOp::kContigK ? (g >> 3) : (g % BN);
-                        const int c = BOp::kContigK ? (g & 7) : (g / BN);
-                        b_op.load8(n0 + row, kb + c * 8, vb[i]);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int g = tid + i * kTgThreads;
-                    const int row = AOp::kContigK ? (g >> 3) : (g & (kTgBM - 1));
-                    const int c = AOp::kContigK ? (g & 7) : (g >> 7);
-                    tg_store_split8(sA_hi, sA_lo, row, c, va[i]);
-                }
-#pragma unroll
-                for (int i = 0; i < 2; ++i) {
-                    const int g = tid + i * kTgThreads;
-                    if (g < BN * 8) {
-                        const int row = BOp::kContigK ? (g >> 3) : (g % BN);
-                        const int c = BOp::kContigK ? (g & 7) : (g / BN);
-                        tg_store_split8(sB_hi, sB_lo, row, c, vb[i]);
-                    }
+            for (int i = 0; i < 2; ++i) {
+                const int g = tid + i * kTgThreads;
+                if (g < BN * 8) {
+                    const int row = BOp::kContigK ? (g >> 3) : (g % BN);
+                    const int c = BOp::kContigK ? (g & 7) : (g / BN);
+                    tg_store_split8(sB_hi, sB_lo, row, c, vb[i]);
                 }
             }
             // ---- rest of B in batches of 2 groups per thread
             for (int g0 = 2 * kTgThreads; g0 < BN * 8; g0 += 2 * kTgThreads) {
-                float vb[2][8];
 #pragma unroll
                 for (int i = 0; i < 2; ++i) {
                     const int g = g0 + tid + i * kTgThreads;
@@ -201,19 +215,28 @@ tcgemm_kernel(int M, int N, int Kd, int BN, int k_per_split, AOp a_op, BOp b_op,
             uint32_t v[32];
             ptx::tmem_ld_32x32(taddr + c0, v);
             ptx::tmem_ld_wait(v);
+            if (c0 == 0) dbg_stamp(21);
             if (m_row < M) epi.transform(st, m_row, n0 + c0, v);
             __syncwarp();
+            if (c0 == 0) dbg_stamp(22);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) tstage[lane * 33 + j] = __uint_as_float(v[j]);
+            for (int j = 0; j < 32; j += 2)
+                *reinterpret_cast<float2*>(&tstage[lane * 34 + j]) = make_float2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
             __syncwarp();
-            const int n = n0 + c0 + lane;
+            if (c0 == 0) dbg_stamp(23);
+            // half-warp per row, two adjacent columns per lane: 16 lanes x 8 B = one 128 B line per row
+            const int cn = 2 * (lane & 15), n = n0 + c0 + cn;
             if (n < N) {
-#pragma unroll 8
-                for (int r = 0; r < 32; ++r) {
-                    const int m = m0 + quarter * 32 + r;
-                    if (m < M) epi.store(rowoff[quarter * 32 + r], m, n, tstage[r * 33 + lane]);
+#pragma unroll 4
+                for (int r2 = 0; r2 < 32; r2 += 2) {
+                    const int r = r2 + (lane >> 4);
+                    if (m0 + quarter * 32 + r < M) {
+                        const float2 q = *reinterpret_cast<const float2*>(&tstage[r * 34 + cn]);
+                        epi.store2(rowptr + (quarter * 32 + r) * 3, n, q.x, q.y);
+                    }
                 }
             }
+            if (c0 == 0) dbg_stamp(24);
         }
         ptx::tc_fence_before();
         __syncthreads();                           // TMEM reads + transpose tiles done before the next tile's fill / MMAs

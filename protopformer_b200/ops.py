@@ -407,17 +407,28 @@ class FusedHeadStep:
             self.dtokens = e(B, 1 + N, Din)
             self.ws = bwd_workspace(B, K, D, P, Pg, device)
             self.ws_addon = addon_bwd_workspace(B, N, Din, D, K, device)
+        # independent kernels run on a forked stream (under CUDA-graph capture this becomes a parallel branch)
+        self.side = torch.cuda.Stream(device=device)
+        self.ev = [torch.cuda.Event() for _ in range(4)]
 
     def step(self, tokens, scores, labels, Wa, ba, P, Pg, Wl, Wg, grads=None, upstream: float = 1.0):
         B, N, Din, D, Pn, Pgn, C, m, H = self.dims
         cfg, K = self.cfg, self.cfg.K
         c = _lib.call
+        main, side, ev = torch.cuda.current_stream(), self.side, self.ev
+        # branch: prototype operand preparation || selection + add-on
+        ev[0].record(main)
+        side.wait_event(ev[0])
+        with torch.cuda.stream(side):
+            c("pph_split_rows", P, Pn, D, float(cfg.center), self.P_hi, self.P_lo, self.p2, self.p2_ctr, self.p2_hi)
+            c("pph_split_rows", Pg, Pgn, D, float(cfg.center), self.Pg_hi, self.Pg_lo, self.pg2, self.pg2_ctr, self.pg2_hi)
+            ev[1].record(side)
         c("pph_select_topk", scores, B, max(H, 1), N, K, self.idx32, None)
         c("pph_addon_fwd", tokens, self.idx32, Wa, ba, B, N, Din, D, K, self.Zs, self.Zc, self.z2s, self.z2c,
           float(cfg.center), self.z2s_ctr, self.z2c_ctr, self.z2s_hi, self.z2c_hi, self.Zs_hi, self.Zs_lo,
           self.Zc_hi, self.Zc_lo)
-        c("pph_split_rows", P, Pn, D, float(cfg.center), self.P_hi, self.P_lo, self.p2, self.p2_ctr, self.p2_hi)
-        c("pph_split_rows", Pg, Pgn, D, float(cfg.center), self.Pg_hi, self.Pg_lo, self.pg2, self.pg2_ctr, self.pg2_hi)
+        main.wait_event(ev[1])
+        ppc = self.use_ppc and self.train
         mode = cfg.mode_id
         sel = {_lib.MODE_FP32_FMA: 0, _lib.MODE_BF16X3: 1, _lib.MODE_BF16: 2}[mode]
         c("pph_similarity_fwd", mode, cfg.act_id, float(cfg.eps), B, K, D, Pn, Pgn, self.Zs, self.Zc,
@@ -426,13 +437,18 @@ class FusedHeadStep:
           (self.p2, self.p2_ctr, self.p2_hi)[sel], (self.pg2, self.pg2_ctr, self.pg2_hi)[sel],
           self.P_hi, self.P_lo, self.Pg_hi, self.Pg_lo,
           self.dmin_l, self.argmin, self.act_l, self.dmin_g, self.act_g, None, None)
+        if ppc:   # branch: PPC loss || last layers (forked after the persistent similarity kernel so it cannot delay it)
+            ev[2].record(main)
+            side.wait_event(ev[2])
+            with torch.cuda.stream(side):
+                c("pph_ppc_fwd", self.Zs, self.z2s, P, self.p2, self.idx32, labels, B, K, D, Pn, m, N, cfg.act_id,
+                  float(cfg.eps), float(cfg.ppc_cov_thresh), float(cfg.ppc_mean_thresh), self.dslice, self.stats,
+                  self.ppc_partial, self.ppc_counter, self.ppc_losses)
+                ev[3].record(side)
         c("pph_logits_fwd", self.act_l, self.act_g, Wl, Wg, B, Pn, Pgn, C, float(cfg.global_coe), self.logits,
           self.logits_g, self.logits_l)
-        ppc = self.use_ppc and self.train
         if ppc:
-            c("pph_ppc_fwd", self.Zs, self.z2s, P, self.p2, self.idx32, labels, B, K, D, Pn, m, N, cfg.act_id,
-              float(cfg.eps), float(cfg.ppc_cov_thresh), float(cfg.ppc_mean_thresh), self.dslice, self.stats,
-              self.ppc_partial, self.ppc_counter, self.ppc_losses)
+            main.wait_event(ev[3])
         c("pph_loss_tail", self.logits, labels, self.ppc_losses if ppc else None, self.cov_coe, self.mean_coe,
           float(upstream), B, C, self.ce_partial, self.ce_counter, self.losses, self.dlogits if self.train else None)
         if not self.train:
