@@ -170,6 +170,9 @@ def main():
                     help="similarity precision: fp32 = 3-term bf16 split (1e-4 parity), bf16 = single pass")
     ap.add_argument("--nbuf", type=int, default=16, help="distinct input batches the step rotates over")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--graph-allreduce", action="store_true",
+                    help="N>1 (experimental, unverified): record the NCCL gradient all-reduce inside the CUDA graph "
+                         "instead of issuing it after each replay")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -199,7 +202,8 @@ def main():
     cfg = ops.HeadConfig(K=shape.K, global_coe=shape.global_coe, mode=args.mode,
                          ppc_cov_thresh=shape.ppc_cov_thresh, ppc_mean_thresh=shape.ppc_mean_thresh)
     nbuf = args.nbuf
-    step = GraphedHeadStep(params, cfg, B=shape.B, N=shape.N, C=shape.C, m=shape.m, n_slots=nbuf)
+    step = GraphedHeadStep(params, cfg, B=shape.B, N=shape.N, C=shape.C, m=shape.m, n_slots=nbuf,
+                           allreduce_in_graph=(world > 1 and args.graph_allreduce))
     # distinct synthetic batches per slot and per rank (weak scaling: fixed per-GPU batch)
     host = []
     for i in range(nbuf):
@@ -354,7 +358,8 @@ def main():
             "config": {"workload": WORKLOAD, "per_gpu_batch": shape.B, "tokens": shape.K, "dim": shape.D,
                        "prototypes": shape.P, "global_prototypes": shape.Pg, "classes": shape.C, "mode": args.mode,
                        "step": "head fwd + PPC + CE + bwd (dtokens, dP, dPg, dWa, dba)"
-                               + (" + NCCL grad all-reduce" if world > 1 else ""),
+                               + ((" + NCCL grad all-reduce (" + ("in graph" if args.graph_allreduce else "after each replay") + ")")
+                                  if world > 1 else ""),
                        "l2": l2_note, "parallelism": f"dp{world}", "cuda_graph": True},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps, "last_loss": last_loss},

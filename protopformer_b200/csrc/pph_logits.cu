@@ -31,25 +31,16 @@ logits_fwd_kernel(const float* __restrict__ act_l, const float* __restrict__ act
         for (int i = 0; i < kLogTB; ++i)
 #pragma unroll
             for (int j = 0; j < kLogTC; ++j) acc[i][j] = 0.f;
-        // register double buffering: the 16 operand loads of iteration i+1 are in flight during the 64 FMAs of iteration i
-        float a[kLogTB], w[kLogTC], an[kLogTB], wn[kLogTC];
-        auto fetch = [&](int p, float (&av)[kLogTB], float (&wv)[kLogTC]) {
-#pragma unroll
-            for (int i = 0; i < kLogTB; ++i) av[i] = (p < Kd && b0 + i < B) ? __ldg(A + (size_t)(b0 + i) * Kd + p) : 0.f;
-#pragma unroll
-            for (int j = 0; j < kLogTC; ++j) wv[j] = (p < Kd && c0 + j < C) ? __ldg(W + (size_t)(c0 + j) * Kd + p) : 0.f;
-        };
-        fetch(tid, a, w);
         for (int p = tid; p < Kd; p += kLogThreads) {
-            fetch(p + kLogThreads, an, wn);
+            float a[kLogTB], w[kLogTC];
+#pragma unroll
+            for (int i = 0; i < kLogTB; ++i) a[i] = (b0 + i < B) ? __ldg(A + (size_t)(b0 + i) * Kd + p) : 0.f;
+#pragma unroll
+            for (int j = 0; j < kLogTC; ++j) w[j] = (c0 + j < C) ? __ldg(W + (size_t)(c0 + j) * Kd + p) : 0.f;
 #pragma unroll
             for (int i = 0; i < kLogTB; ++i)
 #pragma unroll
                 for (int j = 0; j < kLogTC; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
-#pragma unroll
-            for (int i = 0; i < kLogTB; ++i) a[i] = an[i];
-#pragma unroll
-            for (int j = 0; j < kLogTC; ++j) w[j] = wn[j];
         }
         // block reduction of the 64 accumulators: warp shuffles, then a fixed-order sum over the 8 warps
 #pragma unroll

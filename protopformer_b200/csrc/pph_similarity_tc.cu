@@ -307,6 +307,224 @@ similarity_tc_kernel(const __grid_constant__ CUtensorMap tmAl_hi, const __grid_c
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// v2: prototype tile resident in shared memory.
+// The v1 kernel above re-streams both operands for every (tile, term): 423 KB of L2->SM traffic per 128x243 tile in
+// BF16X3 mode, 156 MB per B=64 launch -- it is L2-bandwidth bound (ncu: tensor pipe 22 % of elapsed), not MMA bound.
+// Here a CTA keeps ONE prototype tile (hi and lo, all of D) in shared memory for its whole life and walks the image
+// groups assigned to it, streaming only the token operand, whose hi and lo k-blocks are loaded once per k-block and
+// shared by the three MMA terms: 186 KB per tile (2.3x less).  Used whenever the resident tile leaves room for >= 2
+// pipeline stages (D <= 192 in BF16X3, D <= 384 in BF16); larger D falls back to v1.
+//   CTA c < n_local_ctas : prototype tile c % MT_l, image groups c / MT_l, + lanes_l, ...
+//   remaining CTAs       : global prototype tiles, round robin (each reloads its resident tile per phase)
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kTc2MaxStages = 6;
+
+struct Tc2Job {
+    bool is_global;
+    int mt, t_begin, t_step, t_end;
+};
+
+__device__ __forceinline__ bool tc2_phase(const TcParams& prm, int cta, int p, int lanes_l, int n_local_ctas, int grid_g,
+                                          Tc2Job& j) {
+    if (cta < n_local_ctas) {
+        if (p > 0) return false;
+        j.is_global = false;
+        j.mt = cta % prm.MT_l;
+        j.t_begin = cta / prm.MT_l;
+        j.t_step = lanes_l;
+        j.t_end = prm.NG_l;
+        return true;
+    }
+    const int mt = (cta - n_local_ctas) + p * grid_g;
+    if (mt >= prm.MT_g) return false;
+    j.is_global = true;
+    j.mt = mt;
+    j.t_begin = 0;
+    j.t_step = 1;
+    j.t_end = prm.NB_g;
+    return true;
+}
+
+template <int NTERMS, int KT>
+__global__ void __launch_bounds__(kTcThreads, 1)
+similarity_tc2_kernel(const __grid_constant__ CUtensorMap tmAl_hi, const __grid_constant__ CUtensorMap tmAl_lo,
+                      const __grid_constant__ CUtensorMap tmBl_hi, const __grid_constant__ CUtensorMap tmBl_lo,
+                      const __grid_constant__ CUtensorMap tmAg_hi, const __grid_constant__ CUtensorMap tmAg_lo,
+                      const __grid_constant__ CUtensorMap tmBg_hi, const __grid_constant__ CUtensorMap tmBg_lo,
+                      const TcParams prm, int lanes_l, int n_local_ctas, int grid_g, int stages, int b_tile_bytes) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    constexpr int NOPS = NTERMS == 3 ? 2 : 1;                 // hi (+ lo) copies of each operand
+    const int kblocks = prm.D / kTcBlockK;
+    const int a_bytes = NOPS * kblocks * kTcABytes;
+    const int stage_bytes = NOPS * b_tile_bytes;
+    uint8_t* a_res = smem;                                    // [NOPS][kblocks][128 x 64 bf16]
+    uint8_t* ring = smem + a_bytes;                           // [stages][NOPS][b_tile_bytes]
+    float* x2s = reinterpret_cast<float*>(ring + (size_t)stages * stage_bytes);          // [2][256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(x2s) + 2 * kTcMaxN * 4);
+    uint64_t* full = bars;                                    // [kTc2MaxStages]
+    uint64_t* empty = bars + kTc2MaxStages;                   // [kTc2MaxStages]
+    uint64_t* tmem_full = bars + 2 * kTc2MaxStages;           // [2]
+    uint64_t* tmem_empty = tmem_full + 2;                     // [2]
+    uint64_t* a_full = tmem_empty + 2;                        // [1]
+    uint64_t* a_empty = a_full + 1;                           // [1]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_empty + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cta = blockIdx.x;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmAl_hi);
+        ptx::prefetch_tmap(&tmBl_hi);
+        if (NTERMS == 3) { ptx::prefetch_tmap(&tmAl_lo); ptx::prefetch_tmap(&tmBl_lo); }
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kTc2MaxStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
+        for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 4); }
+        ptx::mbar_init(a_full, 1);
+        ptx::mbar_init(a_empty, 1);
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) ptx::tmem_alloc(tmem_ptr, 512);
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        Tc2Job job;
+        for (int p = 0; tc2_phase(prm, cta, p, lanes_l, n_local_ctas, grid_g, job); ++p) {
+            if (lane == 0) {
+                if (p > 0) ptx::mbar_wait(a_empty, (uint32_t)(p - 1) & 1u);      // MMAs of the previous tile set retired
+                ptx::mbar_expect_tx(a_full, (uint32_t)a_bytes);
+                for (int op = 0; op < NOPS; ++op) {
+                    const CUtensorMap* ma = job.is_global ? (op ? &tmAg_lo : &tmAg_hi) : (op ? &tmAl_lo : &tmAl_hi);
+                    for (int kb = 0; kb < kblocks; ++kb)
+                        ptx::tma_load_2d(a_res + (size_t)(op * kblocks + kb) * kTcABytes, ma, a_full, kb * kTcBlockK,
+                                         job.mt * kTcBlockM);
+                }
+            }
+            __syncwarp();
+            const uint32_t bytes = (uint32_t)NOPS * (uint32_t)(job.is_global ? prm.box_rows_g : prm.box_rows_l) * kTcBlockK * 2;
+            for (int t = job.t_begin; t < job.t_end; t += job.t_step) {
+                const int rowB = job.is_global ? t * kTcMaxN : t * prm.G * prm.K;
+#pragma unroll 1
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    if (lane == 0) {
+                        ptx::mbar_wait(&empty[stage], phase ^ 1u);
+                        ptx::mbar_expect_tx(&full[stage], bytes);
+                        uint8_t* sB = ring + (size_t)stage * stage_bytes;
+                        ptx::tma_load_2d(sB, job.is_global ? &tmBg_hi : &tmBl_hi, &full[stage], kb * kTcBlockK, rowB);
+                        if (NTERMS == 3)
+                            ptx::tma_load_2d(sB + b_tile_bytes, job.is_global ? &tmBg_lo : &tmBl_lo, &full[stage],
+                                             kb * kTcBlockK, rowB);
+                    }
+                    __syncwarp();
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        const uint32_t idesc_l = ptx::umma_idesc_bf16(kTcBlockM, prm.umma_n_l);
+        const uint32_t idesc_g = ptx::umma_idesc_bf16(kTcBlockM, prm.umma_n_g);
+        const uint32_t a_base = ptx::smem_u32(a_res);
+        Tc2Job job;
+        for (int p = 0; tc2_phase(prm, cta, p, lanes_l, n_local_ctas, grid_g, job); ++p) {
+            if (lane == 0) ptx::mbar_wait(a_full, (uint32_t)p & 1u);
+            __syncwarp();
+            const uint32_t idesc = job.is_global ? idesc_g : idesc_l;
+            for (int t = job.t_begin; t < job.t_end; t += job.t_step, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+                const uint32_t d_tmem = tmem_base + (uint32_t)acc * kTcMaxN;
+                if (lane == 0) ptx::mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+                __syncwarp();
+                ptx::tc_fence_after();
+                const bool last_tile = (t + job.t_step >= job.t_end);
+#pragma unroll 1
+                for (int kb = 0; kb < kblocks; ++kb) {
+                    if (lane == 0) {
+                        ptx::mbar_wait(&full[stage], phase);
+                        ptx::tc_fence_after();
+                        const uint32_t b_hi = ptx::smem_u32(ring + (size_t)stage * stage_bytes);
+                        const uint32_t b_lo = b_hi + (uint32_t)b_tile_bytes;
+                        const uint32_t a_hi = a_base + (uint32_t)kb * kTcABytes;
+                        const uint32_t a_lo = a_base + (uint32_t)(kblocks + kb) * kTcABytes;
+#pragma unroll
+                        for (int kk = 0; kk < kTcBlockK / 16; ++kk) {
+                            const uint32_t o = kk * 32;
+                            if (NTERMS == 3) {
+                                ptx::mma_bf16_ss(d_tmem, ptx::umma_desc_k_sw128(a_lo + o), ptx::umma_desc_k_sw128(b_hi + o),
+                                                 idesc, (uint32_t)((kb | kk) != 0));
+                                ptx::mma_bf16_ss(d_tmem, ptx::umma_desc_k_sw128(a_hi + o), ptx::umma_desc_k_sw128(b_lo + o),
+                                                 idesc, 1u);
+                                ptx::mma_bf16_ss(d_tmem, ptx::umma_desc_k_sw128(a_hi + o), ptx::umma_desc_k_sw128(b_hi + o),
+                                                 idesc, 1u);
+                            } else {
+                                ptx::mma_bf16_ss(d_tmem, ptx::umma_desc_k_sw128(a_hi + o), ptx::umma_desc_k_sw128(b_hi + o),
+                                                 idesc, (uint32_t)((kb | kk) != 0));
+                            }
+                        }
+                        ptx::mma_commit(&empty[stage]);
+                        if (kb == kblocks - 1) {
+                            ptx::mma_commit(&tmem_full[acc]);
+                            if (last_tile) ptx::mma_commit(a_empty);            // resident tile may be replaced
+                        }
+                    }
+                    __syncwarp();
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue =====================
+        const int grp_id = (warp - 4) >> 2;
+        const int quarter = warp & 3;
+        const int gtid = threadIdx.x - 128 - grp_id * 128;
+        float* x2 = x2s + grp_id * kTcMaxN;
+        const float4* x2v = reinterpret_cast<const float4*>(x2);
+        int it = 0;
+        Tc2Job job;
+        for (int p = 0; tc2_phase(prm, cta, p, lanes_l, n_local_ctas, grid_g, job); ++p) {
+            for (int tt = job.t_begin; tt < job.t_end; tt += job.t_step, ++it) {
+                if ((it & 1) != grp_id) continue;
+                TcTile t;
+                t.is_global = job.is_global; t.mt = job.mt; t.grp = tt;
+                const uint32_t acc_phase = (uint32_t)(it >> 1) & 1u;
+                named_bar_sync(1 + grp_id, 128);
+                if (!t.is_global) {
+                    const long r0 = (long)t.grp * prm.G * prm.K, rmax = (long)prm.B * prm.K;
+                    for (int c = gtid; c < kTcMaxN; c += 128) x2[c] = (r0 + c < rmax) ? __ldg(prm.z2s + r0 + c) : 0.f;
+                } else {
+                    const int b0 = t.grp * kTcMaxN;
+                    for (int c = gtid; c < kTcMaxN; c += 128) x2[c] = (b0 + c < prm.B) ? __ldg(prm.z2c + b0 + c) : 0.f;
+                }
+                named_bar_sync(1 + grp_id, 128);
+                const uint32_t taddr = tmem_base + (uint32_t)grp_id * kTcMaxN + ((uint32_t)(quarter * 32) << 16);
+                ptx::mbar_wait(&tmem_full[grp_id], acc_phase);
+                ptx::tc_fence_after();
+                tc_epilogue_tile<KT>(prm, t, taddr, x2, x2v, quarter, lane);
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ptx::mbar_arrive(&tmem_empty[grp_id]);
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -344,6 +562,53 @@ static int make_map(CUtensorMap* m, const uint16_t* base, int rows, int D, int b
         return PPH_EDRIVER;
     }
     return 0;
+}
+
+constexpr int kTcSmemLimit = 232448;     // 227 KB opt-in maximum per CTA on sm_100
+
+struct Tc2Plan {
+    bool ok;
+    int stages, b_tile_bytes, lanes_l, n_local_ctas, grid_g, grid, smem;
+};
+
+static Tc2Plan plan_tc2(const TcParams& prm, int nterms, int sms) {
+    Tc2Plan pl{};
+    const int nops = nterms == 3 ? 2 : 1;
+    const int kblocks = prm.D / kTcBlockK;
+    const int a_bytes = nops * kblocks * kTcABytes;
+    const int rows = prm.box_rows_l > prm.box_rows_g ? prm.box_rows_l : prm.box_rows_g;
+    pl.b_tile_bytes = ceil_div(rows * kTcBlockK * 2, 1024) * 1024;
+    const int stage_bytes = nops * pl.b_tile_bytes;
+    const int fixed = 1024 + a_bytes + 2 * kTcMaxN * 4 + 512;
+    int stages = (kTcSmemLimit - fixed) / stage_bytes;
+    if (stages > kTc2MaxStages) stages = kTc2MaxStages;
+    pl.stages = stages;
+    pl.ok = stages >= 2;
+    pl.smem = fixed + stages * stage_bytes;
+    // one CTA per global prototype tile when they fit beside the local CTAs (each reload of the resident tile costs a
+    // full TMA latency, so serialising several global tiles on one CTA becomes the critical path)
+    pl.grid_g = prm.Pg > 0 ? (prm.MT_g <= sms / 4 ? prm.MT_g : sms / 4) : 0;
+    int lanes = (sms - pl.grid_g) / prm.MT_l;
+    if (lanes < 1) lanes = 1;
+    if (lanes > prm.NG_l) lanes = prm.NG_l;
+    pl.lanes_l = lanes;
+    pl.n_local_ctas = prm.MT_l * lanes;
+    pl.grid = pl.n_local_ctas + pl.grid_g;
+    return pl;
+}
+
+template <int NTERMS, int KT>
+static int launch_tc2(const CUtensorMap* maps, const TcParams& prm, const Tc2Plan& pl, cudaStream_t st) {
+    auto kern = similarity_tc2_kernel<NTERMS, KT>;
+    static int configured = 0;
+    if (configured < pl.smem) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
+        if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        configured = kTcSmemLimit;
+    }
+    kern<<<pl.grid, kTcThreads, pl.smem, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], prm,
+                                               pl.lanes_l, pl.n_local_ctas, pl.grid_g, pl.stages, pl.b_tile_bytes);
+    return launch_status("pph_similarity_fwd(tcgen05, resident prototypes)");
 }
 
 template <int NTERMS, int KT>
@@ -414,6 +679,17 @@ int similarity_fwd_tc(int mode, int act_fn, float eps, int B, int K, int D, int 
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
+    }
+    const Tc2Plan pl = plan_tc2(prm, x3 ? 3 : 1, sms);
+    if (pl.ok) {
+        if (x3) {
+            if (static81) return launch_tc2<3, 81>(maps, prm, pl, st);
+            if (static121) return launch_tc2<3, 121>(maps, prm, pl, st);
+            return launch_tc2<3, 0>(maps, prm, pl, st);
+        }
+        if (static81) return launch_tc2<1, 81>(maps, prm, pl, st);
+        if (static121) return launch_tc2<1, 121>(maps, prm, pl, st);
+        return launch_tc2<1, 0>(maps, prm, pl, st);
     }
     const int grid = prm.n_tiles < sms ? prm.n_tiles : sms;
     if (x3) {

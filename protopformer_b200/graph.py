@@ -25,7 +25,7 @@ from .dist import FlatGradReducer
 class GraphedHeadStep:
     def __init__(self, params: dict, cfg: ops.HeadConfig, B: int, N: int, C: int, m: int, n_slots: int = 1,
                  heads: int = 0, ppc_cov_coe: float = 0.1, ppc_mean_coe: float = 0.5, train: bool = True,
-                 process_group=None, device=None, fused: bool = True):
+                 process_group=None, device=None, fused: bool = True, allreduce_in_graph: bool = False):
         """params: dict with Wa (D,Din), ba (D), P (P,D), Pg (Pg,D) [leaf tensors, requires_grad in training] and
         the frozen Wl (C,P), Wg (C,Pg).  ppc_*_coe follow scripts/train_cub.sh:43-44."""
         self.p, self.cfg, self.B, self.N, self.C, self.m = params, cfg, B, N, C, m
@@ -47,6 +47,7 @@ class GraphedHeadStep:
             named = [(k, params[k]) for k in ("P", "Pg", "Wa", "ba")]
             self.reducer = FlatGradReducer(named, process_group)
         self.kernel_launches_per_step = 0
+        self.allreduce_in_graph = allreduce_in_graph      # record the NCCL gradient all-reduce inside the CUDA graph
         self.fused = None
         if fused:
             # one set of intermediate buffers shared by all slots (replays are serial on one stream)
@@ -62,6 +63,8 @@ class GraphedHeadStep:
         with torch.no_grad():
             f.step(self.tokens[slot], self.scores[slot], self.labels[slot], p["Wa"], p["ba"], p["P"], p["Pg"],
                    p["Wl"], p["Wg"], self.grads if self.train else None)
+        if self.train and self.allreduce_in_graph:
+            self.reducer.allreduce()
         self.loss[slot] = f.losses[0]
         self.logits[slot] = f.logits
         self.ppc[slot] = (f.losses[2], f.losses[3])
@@ -102,7 +105,7 @@ class GraphedHeadStep:
             for slot in range(len(self.tokens)):
                 g = torch.cuda.CUDAGraph()
                 n0 = _lib.launch_count()
-                with torch.cuda.graph(g, pool=pool):
+                with torch.cuda.graph(g, pool=pool, capture_error_mode="thread_local"):
                     self._step(slot)
                 self.kernel_launches_per_step = _lib.launch_count() - n0
                 pool = g.pool()
@@ -122,5 +125,6 @@ class GraphedHeadStep:
         return self.loss[slot]
 
     def allreduce_grads(self):
-        if self.reducer is not None:
+        """Gradient all-reduce of the step just run (no-op when it is already part of the captured graph)."""
+        if self.reducer is not None and not self.allreduce_in_graph:
             self.reducer.allreduce()
