@@ -141,22 +141,30 @@ int pph_logits_bwd(const float* dlogits, const float* dlogits_g, const float* dl
  *   dZs[b,k,:] = 2 * sum_{p: argmin[b,p]=k} g_l[b,p] * (Zs[b,k,:] - Pl[p,:])   dZc[b,:] = 2 * sum_p g_g[b,p] * (Zc[b,:] - Pg[p,:])
  * All four outputs are OVERWRITTEN; every row is summed in a fixed order (bit-reproducible).
  * `workspace`: caller-owned device scratch of pph_similarity_bwd_ws_bytes() bytes, ZERO-FILLED once before its
- * first use (it holds the token bins and self-resetting counters). */
+ * first use (it holds the token bins and self-resetting counters).
+ * `parts`: PPH_BWD_BIN (bin the prototypes by argmin token; needs only argmin_l + workspace, so it can run on another
+ * stream as soon as the forward similarity is done) | PPH_BWD_GRADS (the four gradients; requires the bins). */
+#define PPH_BWD_BIN   1
+#define PPH_BWD_GRADS 2
 int pph_similarity_bwd_ws_bytes(int B, int K, int D, int P, int Pg, long long* bytes /* host */);
 int pph_similarity_bwd(const float* g_l, const float* g_g, const int32_t* argmin_l,
                        const float* Zs, const float* Zc, const float* Pl, const float* Pgl,
-                       int B, int K, int D, int P, int Pg, void* workspace,
+                       int B, int K, int D, int P, int Pg, void* workspace, int parts,
                        float* dZs, float* dZc, float* dPl, float* dPg, pph_stream_t stream);
 
 /* (a8, part 3) backward of pph_addon_fwd: dpre = dZ * Z * (1-Z);  dWa = dpre^T X_sel;  dba = sum dpre;
  * dtokens[b, 1+idx] = dpre Wa (CLS row 0 likewise), every other row zero.
  * dWa [D,Din], dba [D], dtokens [B,1+N,Din] are OVERWRITTEN (dtokens may be NULL: no gradient to the backbone).
  * `workspace`: caller-owned device scratch of pph_addon_bwd_ws_bytes() bytes (split-K partials of the weight
- * gradient, summed in a fixed order). */
+ * gradient, summed in a fixed order).
+ * `parts`: PPH_ADDON_WGRAD (dWa, dba) | PPH_ADDON_DGRAD (dtokens); the two are independent and may be issued on
+ * different streams. */
+#define PPH_ADDON_WGRAD 1
+#define PPH_ADDON_DGRAD 2
 int pph_addon_bwd_ws_bytes(int B, int N, int Din, int D, int K, long long* bytes /* host */);
 int pph_addon_bwd(const float* tokens, const int32_t* idx32, const float* Wa,
                   const float* Zs, const float* Zc, const float* dZs, const float* dZc,
-                  int B, int N, int Din, int D, int K, void* workspace,
+                  int B, int N, int Din, int D, int K, void* workspace, int parts,
                   float* dWa, float* dba, float* dtokens, pph_stream_t stream);
 
 /* loss tail adjacent to the head (engine_proto.py:51, 61-64): ce = CrossEntropy(logits, labels) (mean over B),

@@ -34,10 +34,10 @@ SIGNATURES = {
     "pph_ppc_bwd": [_p, _p, _p, _p, _p, _p, _p, _f, _f, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _i, _p, _p, _p],
     "pph_logits_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _f, _p, _p, _p],
     "pph_similarity_bwd_ws_bytes": [_i, _i, _i, _i, _i, C.POINTER(C.c_longlong)],
-    "pph_similarity_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p],
+    "pph_similarity_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p],
     "pph_loss_tail": [_p, _p, _p, _f, _f, _f, _i, _i, _p, _p, _p, _p, _p],
     "pph_addon_bwd_ws_bytes": [_i, _i, _i, _i, _i, C.POINTER(C.c_longlong)],
-    "pph_addon_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p],
+    "pph_addon_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p],
 }
 _RESTYPES = {"pph_last_error_string": C.c_char_p}
 
@@ -93,6 +93,10 @@ def call(name: str, *args):
     global _launches
     if name == "pph_similarity_fwd":
         _launches += 2 if conv[0] == MODE_FP32_FMA else 1      # local + global kernels vs one fused tcgen05 kernel
+    elif name == "pph_similarity_bwd":
+        _launches += (1 if conv[13] & 1 else 0) + (1 if conv[13] & 2 else 0)
+    elif name == "pph_addon_bwd":
+        _launches += (2 if conv[13] & 1 else 0) + (1 if conv[13] & 2 else 0)
     else:
         _launches += KERNELS_PER_CALL.get(name, 0)
     if rc != 0:

@@ -506,17 +506,20 @@ extern "C" int pph_addon_bwd_ws_bytes(int B, int N, int Din, int D, int K, long 
 
 extern "C" int pph_addon_bwd(const float* tokens, const int32_t* idx32, const float* Wa,
                              const float* Zs, const float* Zc, const float* dZs, const float* dZc,
-                             int B, int N, int Din, int D, int K, void* workspace,
+                             int B, int N, int Din, int D, int K, void* workspace, int parts,
                              float* dWa, float* dba, float* dtokens, pph_stream_t stream) {
     using namespace pph;
-    PPH_REQUIRE(tokens && idx32 && Wa && Zs && Zc && dZs && dZc && dWa && dba, PPH_EINVAL,
+    PPH_REQUIRE((parts & 3) != 0, PPH_EINVAL, "pph_addon_bwd: parts must include PPH_ADDON_WGRAD and/or PPH_ADDON_DGRAD");
+    if (!(parts & PPH_ADDON_DGRAD)) dtokens = nullptr;
+    const bool want_w = (parts & PPH_ADDON_WGRAD) != 0;
+    PPH_REQUIRE(tokens && idx32 && Wa && Zs && Zc && dZs && dZc && (!want_w || (dWa && dba)), PPH_EINVAL,
                 "pph_addon_bwd: null pointer");
     PPH_REQUIRE(B >= 0 && N >= 1 && Din >= 1 && D >= 1 && K >= 1 && K <= N, PPH_EINVAL,
                 "pph_addon_bwd: bad dims B=%d N=%d Din=%d D=%d K=%d", B, N, Din, D, K);
     cudaStream_t st = as_stream(stream);
     const bool tc = addon_tc_ok(Din, D) && B > 0;
     cudaError_t e = cudaSuccess;
-    if (!tc) {
+    if (!tc && want_w) {
         e = cudaMemsetAsync(dWa, 0, sizeof(float) * (size_t)D * Din, st);
         if (e == cudaSuccess) e = cudaMemsetAsync(dba, 0, sizeof(float) * (size_t)D, st);
     }
@@ -529,9 +532,9 @@ extern "C" int pph_addon_bwd(const float* tokens, const int32_t* idx32, const fl
     if (B == 0) return 0;
     const int R = B * (K + 1);
     if (tc) {
-        PPH_REQUIRE(workspace, PPH_EINVAL, "pph_addon_bwd: null workspace (size it with pph_addon_bwd_ws_bytes)");
+        PPH_REQUIRE(workspace || !want_w, PPH_EINVAL, "pph_addon_bwd: null workspace (size it with pph_addon_bwd_ws_bytes)");
         RowSrc src{idx32, B, N, Din, K, R};
-        {   // dWa / dba: [D x (Din+1)] = dpre^T [D x R] * [Xsel | 1]^T, split over r, partials + ordered reduction
+        if (want_w) {   // dWa / dba: [D x (Din+1)] = dpre^T [D x R] * [Xsel | 1]^T, split over r, partials + ordered reduction
             const int ldn = ceil_div(Din + 1, 4) * 4;
             int splits = wgrad_splits(R);
             const int k_per_split = ceil_div(ceil_div(R, splits), kTgBK) * kTgBK;
@@ -556,7 +559,7 @@ extern "C" int pph_addon_bwd(const float* tokens, const int32_t* idx32, const fl
         return 0;
     }
     RowMap map{B, K, D};
-    {   // dWa[d, din] = sum_r dpre[r,d] * X[r,din];  dba[d] = sum_r dpre[r,d]   (split over r)
+    if (want_w) {   // dWa[d, din] = sum_r dpre[r,d] * X[r,din];  dba[d] = sum_r dpre[r,d]   (split over r)
         DpreOp<true> a{Zs, Zc, dZs, dZc, map, R};
         XselOp b{tokens, idx32, B, N, Din, K, R};
         WgradEpi epi{dWa, dba, Din};

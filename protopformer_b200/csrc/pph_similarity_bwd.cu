@@ -405,9 +405,18 @@ extern "C" int pph_similarity_bwd_ws_bytes(int B, int K, int D, int P, int Pg, l
 
 extern "C" int pph_similarity_bwd(const float* g_l, const float* g_g, const int32_t* argmin_l,
                                   const float* Zs, const float* Zc, const float* Pl, const float* Pgl,
-                                  int B, int K, int D, int P, int Pg, void* workspace,
+                                  int B, int K, int D, int P, int Pg, void* workspace, int parts,
                                   float* dZs, float* dZc, float* dPl, float* dPg, pph_stream_t stream) {
     using namespace pph;
+    PPH_REQUIRE((parts & 3) != 0, PPH_EINVAL, "pph_similarity_bwd: parts must include PPH_BWD_BIN and/or PPH_BWD_GRADS");
+    if (!(parts & PPH_BWD_GRADS)) {      // binning only: needs argmin and the workspace
+        PPH_REQUIRE(argmin_l && workspace && B >= 1 && K >= 1 && P >= 1, PPH_EINVAL, "pph_similarity_bwd(bin): bad args");
+        const size_t bs = sizeof(int) * ((size_t)8 * K + 2 * (size_t)(K + 1));
+        PPH_REQUIRE(bs <= 48 * 1024, PPH_EUNSUP, "pph_similarity_bwd: K too large");
+        const BwdWorkspace wb = carve_ws(workspace, B, K, D, P, Pg);
+        bin_tokens_kernel<<<B, 256, bs, as_stream(stream)>>>(argmin_l, K, P, wb.bin_start, wb.item_start, wb.bin_list);
+        return launch_status("pph_similarity_bwd(bin)");
+    }
     PPH_REQUIRE(g_l && argmin_l && Zs && Pl && dZs && dPl, PPH_EINVAL, "pph_similarity_bwd: null local pointer");
     PPH_REQUIRE(Pg == 0 || (g_g && Zc && Pgl && dZc && dPg), PPH_EINVAL, "pph_similarity_bwd: null global pointer");
     PPH_REQUIRE(B >= 0 && K >= 1 && D >= 1 && D <= 512 && P >= 1 && Pg >= 0, PPH_EINVAL,
@@ -422,9 +431,12 @@ extern "C" int pph_similarity_bwd(const float* g_l, const float* g_g, const int3
     const size_t bin_smem = sizeof(int) * ((size_t)8 * K + 2 * (size_t)(K + 1));
     PPH_REQUIRE(bin_smem <= 48 * 1024, PPH_EUNSUP, "pph_similarity_bwd: K too large");
     const BwdWorkspace w = carve_ws(workspace, B, K, D, P, Pg);
-    bin_tokens_kernel<<<B, 256, bin_smem, st>>>(argmin_l, K, P, w.bin_start, w.item_start, w.bin_list);
-    int rc = launch_status("pph_similarity_bwd(bin)");
-    if (rc) return rc;
+    int rc = 0;
+    if (parts & PPH_BWD_BIN) {
+        bin_tokens_kernel<<<B, 256, bin_smem, st>>>(argmin_l, K, P, w.bin_start, w.item_start, w.bin_list);
+        rc = launch_status("pph_similarity_bwd(bin)");
+        if (rc) return rc;
+    }
     const int dv = ceil_div(D, 32);
     const bool full = (D % 32 == 0);
 #define PPH_BWD(DV, FULL) launch_bwd<DV, FULL>(g_l, g_g, argmin_l, w, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, dZs, dZc, dPl, dPg, st)

@@ -105,7 +105,8 @@ class _Addon(torch.autograd.Function):
         dWa, dba = torch.empty_like(Wa), _empty((D,), torch.float32, Wa)
         dtok = torch.empty_like(tokens) if ctx.needs_input_grad[0] else None
         ws = addon_bwd_workspace(B, N, Din, D, K, tokens.device)
-        _lib.call("pph_addon_bwd", tokens, idx32, Wa, Zs, Zc, dZs, dZc, B, N, Din, D, K, ws, dWa, dba, dtok)
+        _lib.call("pph_addon_bwd", tokens, idx32, Wa, Zs, Zc, dZs, dZc, B, N, Din, D, K, ws,
+                  1 | (2 if dtok is not None else 0), dWa, dba, dtok)
         return dtok, None, dWa, dba, None, None
 
 
@@ -237,7 +238,7 @@ class _SimilarityLogits(torch.autograd.Function):
         dZs, dZc = torch.empty_like(Zs), torch.empty_like(Zc)
         dPl, dPg = torch.empty_like(Pl), torch.empty_like(Pgl)
         ws = bwd_workspace(B, K, D, P, Pg, Zs.device)
-        _lib.call("pph_similarity_bwd", g_l, g_g, argmin, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, ws, dZs, dZc, dPl, dPg)
+        _lib.call("pph_similarity_bwd", g_l, g_g, argmin, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, ws, 3, dZs, dZc, dPl, dPg)
         return dZs, dZc, dPl, dPg, None, None, None, None
 
 
@@ -409,7 +410,7 @@ class FusedHeadStep:
             self.ws_addon = addon_bwd_workspace(B, N, Din, D, K, device)
         # independent kernels run on a forked stream (under CUDA-graph capture this becomes a parallel branch)
         self.side = torch.cuda.Stream(device=device)
-        self.ev = [torch.cuda.Event() for _ in range(4)]
+        self.ev = [torch.cuda.Event() for _ in range(7)]
 
     def step(self, tokens, scores, labels, Wa, ba, P, Pg, Wl, Wg, grads=None, upstream: float = 1.0):
         B, N, Din, D, Pn, Pgn, C, m, H = self.dims
@@ -445,6 +446,10 @@ class FusedHeadStep:
                   float(cfg.eps), float(cfg.ppc_cov_thresh), float(cfg.ppc_mean_thresh), self.dslice, self.stats,
                   self.ppc_partial, self.ppc_counter, self.ppc_losses)
                 ev[3].record(side)
+                if self.train:   # the token bins of the backward only need argmin: off the critical path
+                    c("pph_similarity_bwd", None, None, self.argmin, None, None, None, None, B, K, D, Pn, Pgn, self.ws,
+                      1, None, None, None, None)
+                    ev[4].record(side)
         c("pph_logits_fwd", self.act_l, self.act_g, Wl, Wg, B, Pn, Pgn, C, float(cfg.global_coe), self.logits,
           self.logits_g, self.logits_l)
         if ppc:
@@ -455,12 +460,23 @@ class FusedHeadStep:
             return self.losses
         c("pph_logits_bwd", self.dlogits, None, None, Wl, Wg, self.dmin_l, self.dmin_g, B, Pn, Pgn, C,
           float(cfg.global_coe), cfg.act_id, float(cfg.eps), self.g_l, self.g_g)
+        binned = ppc                                   # bins were produced on the side stream next to the PPC loss
+        if binned:
+            main.wait_event(ev[4])
         c("pph_similarity_bwd", self.g_l, self.g_g, self.argmin, self.Zs, self.Zc, P, Pg, B, K, D, Pn, Pgn, self.ws,
-          self.dZs, self.dZc, grads["P"], grads["Pg"])
+          2 if binned else 3, self.dZs, self.dZc, grads["P"], grads["Pg"])
         if ppc:
             c("pph_ppc_bwd", self.Zs, P, self.idx32, labels, self.dslice, self.stats, None,
               self.cov_coe * float(upstream), self.mean_coe * float(upstream), B, K, D, Pn, m, N, cfg.act_id,
               float(cfg.eps), float(cfg.ppc_cov_thresh), float(cfg.ppc_mean_thresh), 1, self.dZs, grads["P"])
+        # weight gradient || token gradient (independent GEMMs, 82 + 41 CTAs: they share the machine)
+        ev[5].record(main)
+        side.wait_event(ev[5])
+        with torch.cuda.stream(side):
+            c("pph_addon_bwd", tokens, self.idx32, Wa, self.Zs, self.Zc, self.dZs, self.dZc, B, N, Din, D, K,
+              self.ws_addon, 2, None, None, self.dtokens)
+            ev[6].record(side)
         c("pph_addon_bwd", tokens, self.idx32, Wa, self.Zs, self.Zc, self.dZs, self.dZc, B, N, Din, D, K,
-          self.ws_addon, grads["Wa"], grads["ba"], self.dtokens)
+          self.ws_addon, 1, grads["Wa"], grads["ba"], None)
+        main.wait_event(ev[6])
         return self.losses

@@ -24,5 +24,5 @@ with torch.no_grad():
     dWa = torch.empty_like(case["Wa"]); dba = torch.empty(D, device=dev); dtok = torch.empty_like(case["tokens"])
     ws = ops.addon_bwd_workspace(B, N, Din, D, K, dev)
     for it in range(2):
-        _lib.call("pph_addon_bwd", case["tokens"], idx, case["Wa"], tf.Zs, tf.Zc, dZs, dZc, B, N, Din, D, K, ws, dWa, dba, dtok)
+        _lib.call("pph_addon_bwd", case["tokens"], idx, case["Wa"], tf.Zs, tf.Zc, dZs, dZc, B, N, Din, D, K, ws, 3, dWa, dba, dtok)
         dump(f"addon_bwd (last = dX gemm)[{it}]:")
