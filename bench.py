@@ -297,6 +297,7 @@ def main():
     # ---- roofline of the dominant kernel (tcgen05 similarity), timed alone on its stream ---------------------------
     peaks = _peaks()
     roof = None
+    dominant = None
     if rank == 0:
         with torch.no_grad():
             tfs = []
@@ -334,11 +335,50 @@ def main():
             us = min(us_eager, us_graph)
         flops = shape.B * (2.0 * shape.K * shape.D * shape.P + 2.0 * shape.D * shape.Pg)   # F_sim, SURVEY.md 8(d)
         achieved = flops / (us * 1e-6) / 1e12
-        roof = {"kernel": "similarity_tc_kernel (tcgen05, mode %s)" % args.mode, "bound": "tensor",
-                "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": achieved / peaks["tf_burst"],
-                "traffic": None, "us_per_launch": us, "algorithmic_flops_per_launch": flops,
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed ncu --set full
+        # capture (profiles/r1_ncu_full_step_kernels.txt, cold caches); its operands total 7.1 MB, i.e. no re-reads
+        traffic = 7.22e6 if (WORKLOAD == "cub_b64") else None
+        roof = {"kernel": "similarity_tc2_kernel (tcgen05 + TMA, resident prototype tile, mode %s)" % args.mode,
+                "bound": "tensor", "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["tf_burst"], "traffic": traffic, "us_per_launch": us,
+                "algorithmic_flops_per_launch": flops,
                 "peak_source": peaks["src"] + " bf16 burst (kernel timed alone)",
-                "note": "fp32 mode issues 3 bf16 MMA passes per algorithmic flop" if args.mode == "fp32" else ""}
+                "note": ("fp32 mode issues 3 bf16 MMA passes per algorithmic flop: tensor-pipe work is 3x the algorithmic "
+                         "figure" if args.mode == "fp32" else "")}
+        # the kernel with the largest share of the step (profiles/r1_launches_final_warm.txt): the argmin-routed sparse
+        # backward, a byte/latency-bound gather.  Timed alone the same way; roofline = HBM with its compulsory bytes.
+        try:
+            with torch.no_grad():
+                f = step.fused
+                B_, K_, D_, P_, Pg_ = shape.B, shape.K, shape.D, shape.P, shape.Pg
+                args_b = (f.g_l, f.g_g, f.argmin, f.Zs, f.Zc, params["P"].detach(), params["Pg"].detach(), B_, K_, D_, P_,
+                          Pg_, f.ws, 2, f.dZs, f.dZc, torch.empty_like(params["P"]), torch.empty_like(params["Pg"]))
+                for _ in range(3):
+                    _lib.call("pph_similarity_bwd", *args_b)
+                torch.cuda.synchronize()
+                gb = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gb):
+                    for _ in range(20):
+                        _lib.call("pph_similarity_bwd", *args_b)
+                gb.replay()
+                torch.cuda.synchronize()
+                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                b0.record()
+                for _ in range(10):
+                    gb.replay()
+                b1.record()
+                torch.cuda.synchronize()
+                us_b = 1e3 * b0.elapsed_time(b1) / 200
+            # compulsory bytes: Zs, Zc, P, Pg, g_l, g_g, argmin, bins read once; dZs, dZc, dP, dPg written once
+            byts = 4.0 * (2 * B_ * K_ * D_ + 2 * B_ * D_ + 2 * (P_ + Pg_) * D_ + B_ * (P_ + Pg_) + 2 * B_ * P_)
+            ach = byts / (us_b * 1e-6) / 1e9
+            dominant = {"kernel": "sim_grads_kernel (argmin-routed sparse backward: dP, dPg, dZs, dZc)", "bound": "hbm",
+                        "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
+                        "us_per_launch": us_b, "algorithmic_bytes_per_launch": byts,
+                        "note": "gathers 2*B*P rows of D floats from L2-resident operands (197 MB of L2 traffic): "
+                                "latency/L2-bound, far from the HBM roofline by construction"}
+        except Exception as exc:      # the headline numbers must not depend on this auxiliary measurement
+            dominant = {"error": str(exc)}
 
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------------------
     cpu = None
@@ -367,6 +407,7 @@ def main():
             "gpu_launches_per_step": step.kernel_launches_per_step,
             "clocks": sampler.summary(),
             "roofline": roof,
+            "largest_share_kernel": dominant if rank == 0 else None,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
