@@ -272,6 +272,7 @@ struct FwdBOp {     // (row = n, k = din): Wa[n, din]
     }
 };
 struct FwdEpi {
+    static constexpr bool kDirect = false;
     const float* ba;
     float *Zs, *Zc, *z2s, *z2c, *z2s_ctr, *z2c_ctr, *z2s_hi, *z2c_hi;
     uint16_t *Zs_hi, *Zs_lo, *Zc_hi, *Zc_lo;
@@ -414,6 +415,7 @@ struct XselColOp {  // (row = din, k = r): gathered token rows transposed; row D
     }
 };
 struct DxTcEpi {    // scatter rows of dX into the (zero-filled) token gradient
+    static constexpr bool kDirect = false;
     float* dtokens;
     RowSrc src;
     struct State { int dummy; };
@@ -426,6 +428,7 @@ struct DxTcEpi {    // scatter rows of dX into the (zero-filled) token gradient
     __device__ __forceinline__ void finish(State&, int, int, int, float*, bool) const {}
 };
 struct WgradPartEpi {   // per-split partial tile [split][D][ldn]
+    static constexpr bool kDirect = false;
     float* part;
     int D, ldn;
     struct State { int dummy; };

@@ -6,8 +6,9 @@
 // laid out for L2 traffic and determinism instead:
 //   forward : CTA = 8 images x 8 classes, the 256 threads split the prototype axis (coalesced row reads), 64
 //             register accumulators per thread, one block reduction -> every logit has ONE writer (deterministic).
-//   backward: CTA = 64 images x 32 prototypes, contraction over the C classes from shared memory, 2x4 register tile.
+//   backward: transposed product G^T = W^T * upstream^T on tcgen05 through the manual-fill GEMM (pph_tcgemm.cuh).
 #include "pph_common.cuh"
+#include "pph_tcgemm.cuh"
 
 namespace pph {
 
@@ -70,93 +71,70 @@ logits_fwd_kernel(const float* __restrict__ act_l, const float* __restrict__ act
     }
 }
 
-// g[b,p] = (coef * sum_c dlogits[b,c] W[c,p] + sum_c extra[b,c] W[c,p]) * act'(dmin[b,p]) * [dmin > 0]
-constexpr int kLbTB = 64, kLbTP = 32, kLbCC = 64;   // images, prototypes per CTA; class chunk staged in smem
-
-__global__ void __launch_bounds__(kLogThreads)
-logits_bwd_kernel(const float* __restrict__ dlogits, const float* __restrict__ dlogits_g,
-                  const float* __restrict__ dlogits_l, const float* __restrict__ Wl, const float* __restrict__ Wg,
-                  const float* __restrict__ dmin_l, const float* __restrict__ dmin_g,
-                  int B, int P, int Pg, int C, int tiles_l, float gc, int act_fn, float eps,
-                  float* __restrict__ g_l, float* __restrict__ g_g) {
-    __shared__ __align__(16) float up[kLbCC][kLbTB + 2];     // upstream gradient chunk, transposed [c][b]
-    __shared__ __align__(16) float wt[kLbCC][kLbTP];         // last-layer chunk [c][p]
-    const int tid = threadIdx.x;
-    const bool global = (int)blockIdx.x >= tiles_l;
-    const int p0 = (global ? blockIdx.x - tiles_l : blockIdx.x) * kLbTP;
-    const int b0 = blockIdx.y * kLbTB;
-    const int np = global ? Pg : P;
-    const float* W = global ? Wg : Wl;
-    const float* extra = global ? dlogits_g : dlogits_l;
-    const float coef = global ? gc : 1.0f - gc;
-    const int tb = tid & 31, tp = tid >> 5;      // images 2*tb, 2*tb+1; prototypes 4*tp .. 4*tp+3
-    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    // the next class chunk is fetched into registers while the current one is contracted from shared memory
-    constexpr int NU = kLbCC * kLbTB / kLogThreads, NW = kLbCC * kLbTP / kLogThreads;     // 16, 8
-    float ru[NU], rw[NW];
-    auto fetch = [&](int cc) {
+// ---- backward on tcgen05 (pph_tcgemm.cuh): G^T[p, b] = sum_c W[c,p] * up[b,c], rows = local prototypes (padded to a
+// 128 multiple) followed by the global ones, columns = images, contraction over the C classes (zero padded to 64).
+// 32 CTAs at the CUB shape instead of a latency-bound CUDA-core tile loop; the epilogue applies the similarity
+// derivative and writes g[b,p] directly (thread = prototype: loads and stores are coalesced without a transpose).
+struct LbAOp {      // (row = m -> (branch, p), k = c) -> W[c, p]; consecutive lanes = consecutive prototypes
+    static constexpr bool kContigK = false;
+    const float *Wl, *Wg;
+    int P, Plpad, Pg, C;
+    __device__ __forceinline__ void load8(int m, int c0, float (&v)[8]) const {
+        const bool global = m >= Plpad;
+        const int p = global ? m - Plpad : m, np = global ? Pg : P;
+        const float* W = global ? Wg : Wl;
 #pragma unroll
-        for (int q = 0; q < NU; ++q) {
-            const int i = tid + q * kLogThreads;
-            const int b = i / kLbCC, c = i - b * kLbCC;       // consecutive threads: consecutive classes (coalesced)
-            float v = 0.f;
-            if (b0 + b < B && cc + c < C) {
-                const size_t o = (size_t)(b0 + b) * C + cc + c;
-                v = coef * __ldg(dlogits + o);
-                if (extra) v += __ldg(extra + o);
-            }
-            ru[q] = v;
-        }
-#pragma unroll
-        for (int q = 0; q < NW; ++q) {
-            const int i = tid + q * kLogThreads;
-            const int c = i / kLbTP, p = i - c * kLbTP;
-            rw[q] = (cc + c < C && p0 + p < np) ? __ldg(W + (size_t)(cc + c) * np + p0 + p) : 0.f;
-        }
-    };
-    fetch(0);
-    for (int cc = 0; cc < C; cc += kLbCC) {
-#pragma unroll
-        for (int q = 0; q < NU; ++q) {
-            const int i = tid + q * kLogThreads;
-            const int b = i / kLbCC, c = i - b * kLbCC;
-            up[c][b] = ru[q];
-        }
-#pragma unroll
-        for (int q = 0; q < NW; ++q) {
-            const int i = tid + q * kLogThreads;
-            const int c = i / kLbTP, p = i - c * kLbTP;
-            wt[c][p] = rw[q];
-        }
-        __syncthreads();
-        if (cc + kLbCC < C) fetch(cc + kLbCC);
-#pragma unroll 8
-        for (int c = 0; c < kLbCC; ++c) {
-            const float2 u = *reinterpret_cast<const float2*>(&up[c][2 * tb]);
-            const float4 w = *reinterpret_cast<const float4*>(&wt[c][4 * tp]);
-            acc[0][0] = fmaf(u.x, w.x, acc[0][0]); acc[0][1] = fmaf(u.x, w.y, acc[0][1]);
-            acc[0][2] = fmaf(u.x, w.z, acc[0][2]); acc[0][3] = fmaf(u.x, w.w, acc[0][3]);
-            acc[1][0] = fmaf(u.y, w.x, acc[1][0]); acc[1][1] = fmaf(u.y, w.y, acc[1][1]);
-            acc[1][2] = fmaf(u.y, w.z, acc[1][2]); acc[1][3] = fmaf(u.y, w.w, acc[1][3]);
-        }
-        __syncthreads();
+        for (int i = 0; i < 8; ++i) v[i] = (p < np && c0 + i < C) ? __ldg(W + (size_t)(c0 + i) * np + p) : 0.f;
     }
-    const float* dmin = global ? dmin_g : dmin_l;
-    float* g = global ? g_g : g_l;
+};
+struct LbBOp {      // (row = b, k = c) -> upstream gradient of the branch this CTA's rows belong to
+    static constexpr bool kContigK = true;
+    const float *dlogits, *dlogits_g, *dlogits_l;
+    int B, C, Plpad;
+    float gc;
+    __device__ __forceinline__ void load8(int b, int c0, float (&v)[8]) const {
+        const bool global = (int)blockIdx.x * kTgBM >= Plpad;
+        const float coef = global ? gc : 1.0f - gc;
+        const float* extra = global ? dlogits_g : dlogits_l;
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-        const int b = b0 + 2 * tb + i;
-        if (b >= B) continue;
+        for (int i = 0; i < 8; ++i) {
+            float x = 0.f;
+            if (b < B && c0 + i < C) {
+                const size_t o = (size_t)b * C + c0 + i;
+                x = coef * __ldg(dlogits + o);
+                if (extra) x += __ldg(extra + o);
+            }
+            v[i] = x;
+        }
+    }
+};
+struct LbEpi {
+    static constexpr bool kDirect = true;
+    const float *dmin_l, *dmin_g;
+    float *g_l, *g_g;
+    int B, P, Plpad, Pg, act_fn;
+    float eps;
+    struct State { int dummy; };
+    __device__ __forceinline__ void init(State& s) const { s.dummy = 0; }
+    __device__ __forceinline__ void row_ptrs(int, void* (&)[3]) const {}
+    __device__ __forceinline__ void transform(State&, int m, int n0, uint32_t (&acc)[32]) const {
+        const bool global = m >= Plpad;
+        const int p = global ? m - Plpad : m, np = global ? Pg : P;
+        if (p >= np) return;
+        const float* dmin = global ? dmin_g : dmin_l;
+        float* g = global ? g_g : g_l;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int p = p0 + 4 * tp + j;
-            if (p < np) {
+        for (int j = 0; j < 32; ++j) {
+            const int b = n0 + j;
+            if (b < B) {
                 const size_t o = (size_t)b * np + p;
-                g[o] = acc[i][j] * dact_of_dist(__ldg(dmin + o), act_fn, eps);
+                g[o] = __uint_as_float(acc[j]) * dact_of_dist(__ldg(dmin + o), act_fn, eps);
             }
         }
     }
-}
+    __device__ __forceinline__ void store2(void* const*, int, float, float) const {}
+    __device__ __forceinline__ void finish(State&, int, int, int, float*, bool) const {}
+};
 
 }  // namespace pph
 
@@ -183,10 +161,10 @@ extern "C" int pph_logits_bwd(const float* dlogits, const float* dlogits_g, cons
                 "pph_logits_bwd: null pointer");
     PPH_REQUIRE(B >= 0 && P >= 1 && Pg >= 0 && C >= 1, PPH_EINVAL, "pph_logits_bwd: bad dims");
     if (B == 0) return 0;
-    const int tiles_l = ceil_div(P, kLbTP), tiles_g = Pg > 0 ? ceil_div(Pg, kLbTP) : 0;
-    dim3 grid(tiles_l + tiles_g, ceil_div(B, kLbTB));
-    logits_bwd_kernel<<<grid, kLogThreads, 0, as_stream(stream)>>>(dlogits, dlogits_g, dlogits_l, Wl, Wg, dmin_l,
-                                                                  dmin_g, B, P, Pg, C, tiles_l, global_coe, act_fn,
-                                                                  eps, g_l, g_g);
-    return launch_status("pph_logits_bwd");
+    const int Plpad = ceil_div(P, kTgBM) * kTgBM;
+    LbAOp a{Wl, Wg, P, Plpad, Pg, C};
+    LbBOp b{dlogits, dlogits_g, dlogits_l, B, C, Plpad, global_coe};
+    LbEpi e{dmin_l, dmin_g, g_l, g_g, B, P, Plpad, Pg, act_fn, eps};
+    const int N = ceil_div(B, 2) * 2;           // the kernel walks columns in pairs
+    return launch_tcgemm(Plpad + Pg, N, C, tcgemm_pick_bn(N), 1, a, b, e, as_stream(stream), "pph_logits_bwd(tcgen05)");
 }

@@ -68,6 +68,7 @@ __device__ __forceinline__ void tg_store_split8(uint8_t* hi_tile, uint8_t* lo_ti
 //   __device__ void transform(State&, int m, int n0, uint32_t (&acc)[32]) const;  // thread = row m, in place
 //   __device__ void store2(void* const* p, int n, float v0, float v1) const;   // columns n, n+1 (n even), coalesced
 //   __device__ void finish(State&, int m, int row_local, int cgroup, float* scratch, bool valid) const;
+//   static constexpr bool kDirect;   // true: transform() stores its own results (thread = row), no transposed store phase
 template <class AOp, class BOp, class Epi>
 __global__ void __launch_bounds__(kTgThreads, 1)
 tcgemm_kernel(int M, int N, int Kd, int BN, int k_per_split, AOp a_op, BOp b_op, Epi epi) {
@@ -217,6 +218,7 @@ tcgemm_kernel(int M, int N, int Kd, int BN, int k_per_split, AOp a_op, BOp b_op,
             ptx::tmem_ld_wait(v);
             if (c0 == 0) dbg_stamp(21);
             if (m_row < M) epi.transform(st, m_row, n0 + c0, v);
+            if (Epi::kDirect) continue;
             __syncwarp();
             if (c0 == 0) dbg_stamp(22);
 #pragma unroll
