@@ -337,7 +337,7 @@ def main():
         achieved = flops / (us * 1e-6) / 1e12
         # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed ncu --set full
         # capture (profiles/r1_ncu_full_step_kernels.txt, cold caches); its operands total 7.1 MB, i.e. no re-reads
-        traffic = 7.22e6 if (WORKLOAD == "cub_b64") else None
+        traffic = 7.22e6 if (WORKLOAD == "cub_b64" and args.mode == "fp32") else None
         roof = {"kernel": "similarity_tc2_kernel (tcgen05 + TMA, resident prototype tile, mode %s)" % args.mode,
                 "bound": "tensor", "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["tf_burst"], "traffic": traffic, "us_per_launch": us,
@@ -352,7 +352,8 @@ def main():
                 f = step.fused
                 B_, K_, D_, P_, Pg_ = shape.B, shape.K, shape.D, shape.P, shape.Pg
                 args_b = (f.g_l, f.g_g, f.argmin, f.Zs, f.Zc, params["P"].detach(), params["Pg"].detach(), B_, K_, D_, P_,
-                          Pg_, f.ws, 2, f.dZs, f.dZc, torch.empty_like(params["P"]), torch.empty_like(params["Pg"]))
+                          Pg_, f.ws, 2, None, None, f.dZs, f.dZc, torch.empty_like(params["P"]),
+                          torch.empty_like(params["Pg"]))
                 for _ in range(3):
                     _lib.call("pph_similarity_bwd", *args_b)
                 torch.cuda.synchronize()

@@ -143,13 +143,16 @@ int pph_logits_bwd(const float* dlogits, const float* dlogits_g, const float* dl
  * `workspace`: caller-owned device scratch of pph_similarity_bwd_ws_bytes() bytes, ZERO-FILLED once before its
  * first use (it holds the token bins and self-resetting counters).
  * `parts`: PPH_BWD_BIN (bin the prototypes by argmin token; needs only argmin_l + workspace, so it can run on another
- * stream as soon as the forward similarity is done) | PPH_BWD_GRADS (the four gradients; requires the bins). */
+ * stream as soon as the forward similarity is done) | PPH_BWD_GRADS (the four gradients; requires the bins).
+ * add_dZs [B,K,D] / add_dPl [P,D] (either may be NULL): gradients from elsewhere (the PPC loss) that are added while
+ * dZs / dPl are written, so that they can be produced concurrently and cost no extra pass. */
 #define PPH_BWD_BIN   1
 #define PPH_BWD_GRADS 2
 int pph_similarity_bwd_ws_bytes(int B, int K, int D, int P, int Pg, long long* bytes /* host */);
 int pph_similarity_bwd(const float* g_l, const float* g_g, const int32_t* argmin_l,
                        const float* Zs, const float* Zc, const float* Pl, const float* Pgl,
                        int B, int K, int D, int P, int Pg, void* workspace, int parts,
+                       const float* add_dZs, const float* add_dPl,
                        float* dZs, float* dZc, float* dPl, float* dPg, pph_stream_t stream);
 
 /* (a8, part 3) backward of pph_addon_fwd: dpre = dZ * Z * (1-Z);  dWa = dpre^T X_sel;  dba = sum dpre;

@@ -34,7 +34,7 @@ SIGNATURES = {
     "pph_ppc_bwd": [_p, _p, _p, _p, _p, _p, _p, _f, _f, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _i, _p, _p, _p],
     "pph_logits_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _f, _i, _f, _p, _p, _p],
     "pph_similarity_bwd_ws_bytes": [_i, _i, _i, _i, _i, C.POINTER(C.c_longlong)],
-    "pph_similarity_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p],
+    "pph_similarity_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p, _p, _p, _p],
     "pph_loss_tail": [_p, _p, _p, _f, _f, _f, _i, _i, _p, _p, _p, _p, _p],
     "pph_addon_bwd_ws_bytes": [_i, _i, _i, _i, _i, C.POINTER(C.c_longlong)],
     "pph_addon_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p],

@@ -102,7 +102,7 @@ template <int DV, bool FULL>
 __device__ __forceinline__ void
 proto_grad_body(int vb, const float* __restrict__ g_l, const float* __restrict__ g_g, const int32_t* __restrict__ argmin_l,
                 const float* __restrict__ Zs, const float* __restrict__ Zc, const float* __restrict__ Pl,
-                const float* __restrict__ Pgl, int B, int K, int D, int P, int Pg,
+                const float* __restrict__ Pgl, int B, int K, int D, int P, int Pg, const float* __restrict__ add_dPl,
                 float* __restrict__ dPl, float* __restrict__ dPg) {
     const int row = vb * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= P + Pg) return;
@@ -146,9 +146,11 @@ proto_grad_body(int vb, const float* __restrict__ g_l, const float* __restrict__
     }
     const float* pr = (global ? Pgl : Pl) + (size_t)p * D;
     float* out = (global ? dPg : dPl) + (size_t)p * D;
+    const float* add = (!global && add_dPl) ? add_dPl + (size_t)p * D : nullptr;      // e.g. the PPC-loss contribution
 #pragma unroll
     for (int i = 0; i < DV; ++i)
-        if (FULL || i * 32 + lane < D) out[i * 32 + lane] = 2.0f * (__ldg(pr + i * 32 + lane) * gsum - acc[i]);
+        if (FULL || i * 32 + lane < D)
+            out[i * 32 + lane] = 2.0f * (__ldg(pr + i * 32 + lane) * gsum - acc[i]) + (add ? __ldg(add + i * 32 + lane) : 0.f);
 }
 
 // One warp per work item = (image, token, chunk of <= kBinChunk bin entries).  Single-chunk bins write their row
@@ -160,7 +162,7 @@ token_grad_body(int vb, const float* __restrict__ g_l, const int32_t* __restrict
                 const int32_t* __restrict__ item_start, const int32_t* __restrict__ bin_list,
                 const float* __restrict__ Zs, const float* __restrict__ Pl, int B, int K, int D, int P,
                 int items_per_image, float* part, float* part_gsum, unsigned int* counters,
-                float* __restrict__ dZs) {
+                const float* __restrict__ add_dZs, float* __restrict__ dZs) {
     const int gw = vb * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int b = gw / items_per_image, item = gw - b * items_per_image;
     if (b >= B) return;
@@ -217,10 +219,12 @@ token_grad_body(int vb, const float* __restrict__ g_l, const int32_t* __restrict
     const size_t row = (size_t)b * K + k;
     const float* zr = Zs + row * D;
     float* out = dZs + row * D;
+    const float* add = add_dZs ? add_dZs + row * D : nullptr;                          // e.g. the PPC-loss contribution
     if (nchunks == 1) {
 #pragma unroll
         for (int i = 0; i < DV; ++i)
-            if (FULL || i * 32 + lane < D) out[i * 32 + lane] = 2.0f * (__ldg(zr + i * 32 + lane) * gsum - acc[i]);
+            if (FULL || i * 32 + lane < D)
+                out[i * 32 + lane] = 2.0f * (__ldg(zr + i * 32 + lane) * gsum - acc[i]) + (add ? __ldg(add + i * 32 + lane) : 0.f);
         return;
     }
     const size_t slot = (size_t)b * items_per_image + item;                 // partial slot of this chunk
@@ -248,7 +252,8 @@ token_grad_body(int vb, const float* __restrict__ g_l, const int32_t* __restrict
     }
 #pragma unroll
     for (int i = 0; i < DV; ++i)
-        if (FULL || i * 32 + lane < D) out[i * 32 + lane] = 2.0f * (__ldg(zr + i * 32 + lane) * gt - tot[i]);
+        if (FULL || i * 32 + lane < D)
+            out[i * 32 + lane] = 2.0f * (__ldg(zr + i * 32 + lane) * gt - tot[i]) + (add ? __ldg(add + i * 32 + lane) : 0.f);
     if (lane == 0) counters[row] = 0u;                                       // self-resetting (graph replay)
 }
 
@@ -359,8 +364,8 @@ sim_grads_kernel(const float* __restrict__ g_l, const float* __restrict__ g_g, c
                  const float* __restrict__ Pl, const float* __restrict__ Pgl, int B, int K, int D, int P, int Pg,
                  int items_per_image, int n_cls, int n_slices, int p_per_slice, int n_proto,
                  float* tok_part, float* tok_gsum, unsigned int* tok_counters, float* cls_part,
-                 unsigned int* cls_counters, float* __restrict__ dZs, float* __restrict__ dZc,
-                 float* __restrict__ dPl, float* __restrict__ dPg) {
+                 unsigned int* cls_counters, const float* __restrict__ add_dZs, const float* __restrict__ add_dPl,
+                 float* __restrict__ dZs, float* __restrict__ dZc, float* __restrict__ dPl, float* __restrict__ dPg) {
     int vb = blockIdx.x;
     if (vb < n_cls) {
         cls_grad_body(vb % n_slices, vb / n_slices, n_slices, g_g, Zc, Pgl, B, D, Pg, p_per_slice, cls_part, cls_counters, dZc);
@@ -368,19 +373,19 @@ sim_grads_kernel(const float* __restrict__ g_l, const float* __restrict__ g_g, c
     }
     vb -= n_cls;
     if (vb < n_proto) {
-        proto_grad_body<DV, FULL>(vb, g_l, g_g, argmin_l, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, dPl, dPg);
+        proto_grad_body<DV, FULL>(vb, g_l, g_g, argmin_l, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, add_dPl, dPl, dPg);
         return;
     }
     vb -= n_proto;
     token_grad_body<DV, FULL>(vb, g_l, bin_start, item_start, bin_list, Zs, Pl, B, K, D, P, items_per_image, tok_part,
-                              tok_gsum, tok_counters, dZs);
+                              tok_gsum, tok_counters, add_dZs, dZs);
 }
 
 template <int DV, bool FULL>
 static int launch_bwd(const float* g_l, const float* g_g, const int32_t* argmin_l, const BwdWorkspace& w,
                       const float* Zs, const float* Zc, const float* Pl, const float* Pgl,
-                      int B, int K, int D, int P, int Pg, float* dZs, float* dZc, float* dPl, float* dPg,
-                      cudaStream_t st) {
+                      int B, int K, int D, int P, int Pg, const float* add_dZs, const float* add_dPl,
+                      float* dZs, float* dZc, float* dPl, float* dPg, cudaStream_t st) {
     const int slices = 16;
     const int p_per_slice = Pg > 0 ? ceil_div(ceil_div(Pg, slices), 64) * 64 : 64;
     const int nsl = Pg > 0 ? ceil_div(Pg, p_per_slice) : 0;
@@ -389,8 +394,8 @@ static int launch_bwd(const float* g_l, const float* g_g, const int32_t* argmin_
     const int n_tok = ceil_div(B * w.items_per_image, 8);
     sim_grads_kernel<DV, FULL><<<n_cls + n_proto + n_tok, 256, 0, st>>>(
         g_l, g_g, argmin_l, w.bin_start, w.item_start, w.bin_list, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, w.items_per_image,
-        n_cls, nsl, p_per_slice, n_proto, w.tok_part, w.tok_gsum, w.tok_counters, w.cls_part, w.cls_counters, dZs, dZc,
-        dPl, dPg);
+        n_cls, nsl, p_per_slice, n_proto, w.tok_part, w.tok_gsum, w.tok_counters, w.cls_part, w.cls_counters, add_dZs,
+        add_dPl, dZs, dZc, dPl, dPg);
     return launch_status("pph_similarity_bwd(grads)");
 }
 
@@ -406,6 +411,7 @@ extern "C" int pph_similarity_bwd_ws_bytes(int B, int K, int D, int P, int Pg, l
 extern "C" int pph_similarity_bwd(const float* g_l, const float* g_g, const int32_t* argmin_l,
                                   const float* Zs, const float* Zc, const float* Pl, const float* Pgl,
                                   int B, int K, int D, int P, int Pg, void* workspace, int parts,
+                                  const float* add_dZs, const float* add_dPl,
                                   float* dZs, float* dZc, float* dPl, float* dPg, pph_stream_t stream) {
     using namespace pph;
     PPH_REQUIRE((parts & 3) != 0, PPH_EINVAL, "pph_similarity_bwd: parts must include PPH_BWD_BIN and/or PPH_BWD_GRADS");
@@ -439,7 +445,7 @@ extern "C" int pph_similarity_bwd(const float* g_l, const float* g_g, const int3
     }
     const int dv = ceil_div(D, 32);
     const bool full = (D % 32 == 0);
-#define PPH_BWD(DV, FULL) launch_bwd<DV, FULL>(g_l, g_g, argmin_l, w, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, dZs, dZc, dPl, dPg, st)
+#define PPH_BWD(DV, FULL) launch_bwd<DV, FULL>(g_l, g_g, argmin_l, w, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, add_dZs, add_dPl, dZs, dZc, dPl, dPg, st)
     if (full && dv == 2) rc = PPH_BWD(2, true);
     else if (full && dv == 6) rc = PPH_BWD(6, true);
     else if (full && dv == 12) rc = PPH_BWD(12, true);

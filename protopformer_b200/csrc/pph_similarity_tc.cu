@@ -643,7 +643,6 @@ int similarity_fwd_tc(int mode, int act_fn, float eps, int B, int K, int D, int 
 
     TcParams prm;
     prm.B = B; prm.K = K; prm.D = D; prm.P = P; prm.Pg = Pg;
-    const bool static81 = (K == 81), static121 = (K == 121);
     prm.G = kTcMaxN / K;
     prm.MT_l = ceil_div(P, kTcBlockM);
     prm.NG_l = ceil_div(B, prm.G);
@@ -681,25 +680,26 @@ int similarity_fwd_tc(int mode, int act_fn, float eps, int B, int K, int D, int 
         if (sms <= 0) sms = 148;
     }
     const Tc2Plan pl = plan_tc2(prm, x3 ? 3 : 1, sms);
-    if (pl.ok) {
-        if (x3) {
-            if (static81) return launch_tc2<3, 81>(maps, prm, pl, st);
-            if (static121) return launch_tc2<3, 121>(maps, prm, pl, st);
-            return launch_tc2<3, 0>(maps, prm, pl, st);
-        }
-        if (static81) return launch_tc2<1, 81>(maps, prm, pl, st);
-        if (static121) return launch_tc2<1, 121>(maps, prm, pl, st);
-        return launch_tc2<1, 0>(maps, prm, pl, st);
-    }
     const int grid = prm.n_tiles < sms ? prm.n_tiles : sms;
-    if (x3) {
-        if (static81) return launch_tc<3, 81>(maps, prm, grid, st);
-        if (static121) return launch_tc<3, 121>(maps, prm, grid, st);
-        return launch_tc<3, 0>(maps, prm, grid, st);
+    // compile-time token counts: every K of the BASELINE sweep (49..196 squares) gets an epilogue whose image
+    // boundaries are static; any other K takes the generic epilogue (KT = 0)
+#define PPH_TC_DISPATCH(KT)                                                                          \
+    do {                                                                                             \
+        if (pl.ok) return x3 ? launch_tc2<3, KT>(maps, prm, pl, st) : launch_tc2<1, KT>(maps, prm, pl, st); \
+        return x3 ? launch_tc<3, KT>(maps, prm, grid, st) : launch_tc<1, KT>(maps, prm, grid, st);   \
+    } while (0)
+    switch (K) {
+        case 49: PPH_TC_DISPATCH(49);
+        case 64: PPH_TC_DISPATCH(64);
+        case 81: PPH_TC_DISPATCH(81);
+        case 100: PPH_TC_DISPATCH(100);
+        case 121: PPH_TC_DISPATCH(121);
+        case 144: PPH_TC_DISPATCH(144);
+        case 169: PPH_TC_DISPATCH(169);
+        case 196: PPH_TC_DISPATCH(196);
+        default: PPH_TC_DISPATCH(0);
     }
-    if (static81) return launch_tc<1, 81>(maps, prm, grid, st);
-    if (static121) return launch_tc<1, 121>(maps, prm, grid, st);
-    return launch_tc<1, 0>(maps, prm, grid, st);
+#undef PPH_TC_DISPATCH
 }
 
 }  // namespace pph

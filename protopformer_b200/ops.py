@@ -238,7 +238,8 @@ class _SimilarityLogits(torch.autograd.Function):
         dZs, dZc = torch.empty_like(Zs), torch.empty_like(Zc)
         dPl, dPg = torch.empty_like(Pl), torch.empty_like(Pgl)
         ws = bwd_workspace(B, K, D, P, Pg, Zs.device)
-        _lib.call("pph_similarity_bwd", g_l, g_g, argmin, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, ws, 3, dZs, dZc, dPl, dPg)
+        _lib.call("pph_similarity_bwd", g_l, g_g, argmin, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, ws, 3, None, None,
+                  dZs, dZc, dPl, dPg)
         return dZs, dZc, dPl, dPg, None, None, None, None
 
 
@@ -405,6 +406,7 @@ class FusedHeadStep:
         if train:
             self.dlogits, self.g_l, self.g_g = e(B, C), e(B, P), e(B, Pg)
             self.dZs, self.dZc = e(B, K, D), e(B, D)
+            self.dZs_ppc, self.dP_ppc = e(B, K, D), z(P, D)
             self.dtokens = e(B, 1 + N, Din)
             self.ws = bwd_workspace(B, K, D, P, Pg, device)
             self.ws_addon = addon_bwd_workspace(B, N, Din, D, K, device)
@@ -448,7 +450,14 @@ class FusedHeadStep:
                 ev[3].record(side)
                 if self.train:   # the token bins of the backward only need argmin: off the critical path
                     c("pph_similarity_bwd", None, None, self.argmin, None, None, None, None, B, K, D, Pn, Pgn, self.ws,
-                      1, None, None, None, None)
+                      1, None, None, None, None, None, None)
+                    # ... and the PPC backward only needs the PPC forward: its contributions go to side buffers that
+                    # the gradient kernel adds while it writes dZs / dP
+                    self.dP_ppc.zero_()
+                    c("pph_ppc_bwd", self.Zs, P, self.idx32, labels, self.dslice, self.stats, None,
+                      self.cov_coe * float(upstream), self.mean_coe * float(upstream), B, K, D, Pn, m, N, cfg.act_id,
+                      float(cfg.eps), float(cfg.ppc_cov_thresh), float(cfg.ppc_mean_thresh), 0, self.dZs_ppc,
+                      self.dP_ppc)
                     ev[4].record(side)
         c("pph_logits_fwd", self.act_l, self.act_g, Wl, Wg, B, Pn, Pgn, C, float(cfg.global_coe), self.logits,
           self.logits_g, self.logits_l)
@@ -464,11 +473,8 @@ class FusedHeadStep:
         if binned:
             main.wait_event(ev[4])
         c("pph_similarity_bwd", self.g_l, self.g_g, self.argmin, self.Zs, self.Zc, P, Pg, B, K, D, Pn, Pgn, self.ws,
-          2 if binned else 3, self.dZs, self.dZc, grads["P"], grads["Pg"])
-        if ppc:
-            c("pph_ppc_bwd", self.Zs, P, self.idx32, labels, self.dslice, self.stats, None,
-              self.cov_coe * float(upstream), self.mean_coe * float(upstream), B, K, D, Pn, m, N, cfg.act_id,
-              float(cfg.eps), float(cfg.ppc_cov_thresh), float(cfg.ppc_mean_thresh), 1, self.dZs, grads["P"])
+          2 if binned else 3, self.dZs_ppc if ppc else None, self.dP_ppc if ppc else None,
+          self.dZs, self.dZc, grads["P"], grads["Pg"])
         # weight gradient || token gradient (independent GEMMs, 82 + 41 CTAs: they share the machine)
         ev[5].record(main)
         side.wait_event(ev[5])

@@ -61,7 +61,7 @@ with torch.no_grad():
     res["logits_bwd"] = timeit("logits_bwd", lambda: _lib.call("pph_logits_bwd", dlog, None, None, case["Wl"], case["Wg"], dmin_l, dmin_g, B, P, Pg, C, 0.5, 0, 1e-4, g_l, g_g))
     dZs = torch.empty_like(tf.Zs); dZc = torch.empty_like(tf.Zc); dPl = torch.empty_like(pl.P); dPg = torch.empty_like(pg.P)
     ws = ops.bwd_workspace(B, K, D, P, Pg, dev)
-    res["similarity_bwd"] = timeit("similarity_bwd", lambda: _lib.call("pph_similarity_bwd", g_l, g_g, argmin, tf.Zs, tf.Zc, pl.P, pg.P, B, K, D, P, Pg, ws, 3, dZs, dZc, dPl, dPg))
+    res["similarity_bwd"] = timeit("similarity_bwd", lambda: _lib.call("pph_similarity_bwd", g_l, g_g, argmin, tf.Zs, tf.Zc, pl.P, pg.P, B, K, D, P, Pg, ws, 3, None, None, dZs, dZc, dPl, dPg))
     lt_part = torch.empty(B, device=dev); lt_cnt = torch.zeros(1, dtype=torch.int32, device=dev); lt_out = torch.empty(4, device=dev)
     res["loss_tail"] = timeit("loss_tail", lambda: _lib.call("pph_loss_tail", logits, labels, losses, 0.1, 0.5, 1.0, B, C, lt_part, lt_cnt, lt_out, dlog))
     dWa = torch.empty_like(case["Wa"]); dba = torch.empty(D, device=dev); dtok = torch.empty_like(tok)
