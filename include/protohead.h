@@ -178,6 +178,31 @@ int pph_loss_tail(const float* logits, const int64_t* labels, const float* ppc_l
                   float cov_coe, float mean_coe, float upstream, int B, int C,
                   float* partial, uint32_t* counter, float* out_losses, float* dlogits, pph_stream_t stream);
 
+/* out_losses[4] = (ce + cov_coe*ppc[0] + mean_coe*ppc[1], ce, ppc[0], ppc[1]) from ce_losses[4] = the out_losses of a
+ * pph_loss_tail call made with ppc_losses = NULL (engine_proto.py:61-64).  Splitting the sum off lets the cross-entropy
+ * gradient start before the PPC loss (computed on another stream) is available.  ppc_losses may be NULL (= 0). */
+int pph_loss_combine(const float* ce_losses, const float* ppc_losses, float cov_coe, float mean_coe,
+                     float* out_losses, pph_stream_t stream);
+
+/* (next #1, producer of the selection score) tools/deit_models_attn.py:99-124 attn_rollout + :226
+ * `cls_token_attn = attn_rollout(all_attn)[:, 0, 1:]`, computed without forming the (T,T) products:
+ *   per layer l and image b: fused = head_fusion over H of attn_l[b] (T x T); the k_discard smallest entries of the
+ *   flattened map are zeroed (k_discard = int(T*T*discard_ratio), computed by the caller exactly as the reference does;
+ *   ties at the threshold: lowest flat index first); a_l = rownorm((fused + identity_w * I) / (1 + identity_w));
+ *   v = v0[b] (or e_0 when v0 is NULL); for l = L-1 .. 0: v <- v a_l;   scores[b] = v[drop_first:].
+ * attn_layers: HOST array of L DEVICE pointers, each a contiguous fp32 [B,H,T,T] tensor (they are copied into the kernel
+ * arguments: nothing is retained).  head_fusion: 0 mean, 1 max, 2 min.  identity_w = 0.2 in the reference.
+ * v0 [B,T] optional start row (CaiT, cait_models_attn.py:255-259); drop_first = 1 drops the CLS column (DeiT).
+ * scores [B, T - drop_first].  workspace: pph_rollout_ws_bytes() bytes of device scratch (sparse per-layer matrices).
+ * L <= 32, 2 <= T <= 224. */
+#define PPH_FUSE_MEAN 0
+#define PPH_FUSE_MAX  1
+#define PPH_FUSE_MIN  2
+int pph_rollout_ws_bytes(int L, int B, int T, int k_discard, long long* bytes /* host */);
+int pph_rollout_scores(const float* const* attn_layers /* host array of device pointers */, int L, int B, int H, int T,
+                       int k_discard, int head_fusion, float identity_w, const float* v0, int drop_first,
+                       void* workspace, float* scores, pph_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

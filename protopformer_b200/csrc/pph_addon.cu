@@ -24,6 +24,7 @@ addon_fwd_kernel(const float* __restrict__ tokens, const int32_t* __restrict__ i
                  float* __restrict__ z2s_hi, float* __restrict__ z2c_hi,
                  uint16_t* __restrict__ Zs_hi, uint16_t* __restrict__ Zs_lo,
                  uint16_t* __restrict__ Zc_hi, uint16_t* __restrict__ Zc_lo) {
+    pdl_sync();
     __shared__ __align__(16) float As[kAddBK][kAddBM + 4];
     __shared__ __align__(16) float Ws[kAddBK][kAddBN + 4];
     __shared__ long src_off[kAddBM];    // element offset of the source token row, -1 = row out of range
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(256)
 split_rows_kernel(const float* __restrict__ V, int R, int D, float center, uint16_t* __restrict__ hi,
                   uint16_t* __restrict__ lo, float* __restrict__ v2, float* __restrict__ v2_ctr,
                   float* __restrict__ v2_hi) {
+    pdl_sync();
     const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= R) return;
     const float* v = V + (size_t)row * D;
@@ -444,6 +446,7 @@ struct WgradPartEpi {   // per-split partial tile [split][D][ldn]
 __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ part, int splits, int D, int Din, int ldn, float* __restrict__ dWa,
                     float* __restrict__ dba) {
+    pdl_sync();
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= D * (Din + 1)) return;
     const int d = i / (Din + 1), n = i - d * (Din + 1);
@@ -476,9 +479,7 @@ extern "C" int pph_addon_fwd(const float* tokens, const int32_t* idx32, const fl
         FwdEpi e{ba, Zs, Zc, z2s, z2c, z2s_ctr, z2c_ctr, z2s_hi, z2c_hi, Zs_hi, Zs_lo, Zc_hi, Zc_lo, center, K, D};
         return launch_tcgemm(R, D, Din, tcgemm_pick_bn(D), 1, a, b, e, as_stream(stream), "pph_addon_fwd(tcgen05)");
     }
-    pph::addon_fwd_kernel<<<pph::ceil_div(R, pph::kAddBM), pph::kAddThreads, 0, pph::as_stream(stream)>>>(
-        tokens, idx32, Wa, ba, B, N, Din, D, K, Zs, Zc, z2s, z2c, center, z2s_ctr, z2c_ctr, z2s_hi, z2c_hi, Zs_hi,
-        Zs_lo, Zc_hi, Zc_lo);
+    pph::launch_k(pph::addon_fwd_kernel, dim3(pph::ceil_div(R, pph::kAddBM)), dim3(pph::kAddThreads), (size_t)(0), pph::as_stream(stream), tokens, idx32, Wa, ba, B, N, Din, D, K, Zs, Zc, z2s, z2c, center, z2s_ctr, z2c_ctr, z2s_hi, z2c_hi, Zs_hi, Zs_lo, Zc_hi, Zc_lo);
     return pph::launch_status("pph_addon_fwd");
 }
 
@@ -487,8 +488,7 @@ extern "C" int pph_split_rows(const float* V, int R, int D, float center, uint16
     PPH_REQUIRE(V, PPH_EINVAL, "pph_split_rows: null pointer");
     PPH_REQUIRE(R >= 0 && D >= 1, PPH_EINVAL, "pph_split_rows: bad dims R=%d D=%d", R, D);
     if (R == 0) return 0;
-    pph::split_rows_kernel<<<pph::ceil_div(R, 8), 256, 0, pph::as_stream(stream)>>>(V, R, D, center, hi, lo, v2, v2_ctr,
-                                                                                            v2_hi);
+    pph::launch_k(pph::split_rows_kernel, dim3(pph::ceil_div(R, 8)), dim3(256), (size_t)(0), pph::as_stream(stream), V, R, D, center, hi, lo, v2, v2_ctr, v2_hi);
     return pph::launch_status("pph_split_rows");
 }
 
@@ -548,7 +548,7 @@ extern "C" int pph_addon_bwd(const float* tokens, const int32_t* idx32, const fl
             WgradPartEpi epi{part, D, ldn};
             int rc = launch_tcgemm(D, ldn, R, tcgemm_pick_bn(ldn), splits, a, b, epi, st, "pph_addon_bwd(wgrad tcgen05)");
             if (rc) return rc;
-            wgrad_reduce_kernel<<<ceil_div(D * (Din + 1), 256), 256, 0, st>>>(part, splits, D, Din, ldn, dWa, dba);
+            launch_k(wgrad_reduce_kernel, dim3(ceil_div(D * (Din + 1), 256)), dim3(256), (size_t)(0), st, part, splits, D, Din, ldn, dWa, dba);
             rc = launch_status("pph_addon_bwd(wgrad reduce)");
             if (rc) return rc;
         }

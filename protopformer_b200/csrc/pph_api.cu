@@ -1,5 +1,6 @@
 // Library-level entry points: version, last-error string, device query.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "pph_common.cuh"
@@ -13,6 +14,14 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("PPH_PDL");
+        return e != nullptr && e[0] == '1';
+    }();
+    return on;
 }
 
 }  // namespace pph

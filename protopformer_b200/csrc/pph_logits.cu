@@ -19,6 +19,7 @@ __global__ void __launch_bounds__(kLogThreads)
 logits_fwd_kernel(const float* __restrict__ act_l, const float* __restrict__ act_g, const float* __restrict__ Wl,
                   const float* __restrict__ Wg, int B, int P, int Pg, int C, float gc,
                   float* __restrict__ logits, float* __restrict__ logits_g, float* __restrict__ logits_l) {
+    pdl_sync();
     __shared__ float red[kLogThreads / 32][kLogTB * kLogTC];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b0 = blockIdx.y * kLogTB, c0 = blockIdx.x * kLogTC;
@@ -147,8 +148,7 @@ extern "C" int pph_logits_fwd(const float* act_l, const float* act_g, const floa
     PPH_REQUIRE(B >= 0 && P >= 1 && Pg >= 0 && C >= 1, PPH_EINVAL, "pph_logits_fwd: bad dims");
     if (B == 0) return 0;
     dim3 grid(ceil_div(C, kLogTC), ceil_div(B, kLogTB));
-    logits_fwd_kernel<<<grid, kLogThreads, 0, as_stream(stream)>>>(act_l, act_g, Wl, Wg, B, P, Pg, C, global_coe,
-                                                                  logits, logits_g, logits_l);
+    launch_k(logits_fwd_kernel, dim3(grid), dim3(kLogThreads), (size_t)(0), as_stream(stream), act_l, act_g, Wl, Wg, B, P, Pg, C, global_coe, logits, logits_g, logits_l);
     return launch_status("pph_logits_fwd");
 }
 

@@ -15,6 +15,7 @@ __global__ void __launch_bounds__(256)
 loss_tail_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, const float* __restrict__ ppc,
                  float cov_coe, float mean_coe, float upstream, int B, int C, float* partial, unsigned int* counter,
                  float* __restrict__ out, float* __restrict__ dlogits) {
+    pdl_sync();
     const int b = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     __shared__ unsigned int s_ticket;
     if (b < B) {
@@ -57,7 +58,30 @@ loss_tail_kernel(const float* __restrict__ logits, const int64_t* __restrict__ l
     }
 }
 
+// total = ce + cov_coe * ppc[0] + mean_coe * ppc[1] from a cross-entropy computed WITHOUT the PPC terms: lets the loss
+// tail (and with it the whole last-layer backward) start before the PPC loss has finished on its own stream.
+__global__ void loss_combine_kernel(const float* __restrict__ ce_losses, const float* __restrict__ ppc, float cov_coe,
+                                    float mean_coe, float* __restrict__ out) {
+    pdl_sync();
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        const float ce = ce_losses[1], cov = ppc ? ppc[0] : 0.f, mean = ppc ? ppc[1] : 0.f;
+        out[0] = ce + cov_coe * cov + mean_coe * mean;
+        out[1] = ce;
+        out[2] = cov;
+        out[3] = mean;
+    }
+}
+
 }  // namespace pph
+
+extern "C" int pph_loss_combine(const float* ce_losses, const float* ppc_losses, float cov_coe, float mean_coe,
+                                float* out_losses, pph_stream_t stream) {
+    using namespace pph;
+    PPH_REQUIRE(ce_losses && out_losses, PPH_EINVAL, "pph_loss_combine: null pointer");
+    launch_k(loss_combine_kernel, dim3(1), dim3(32), (size_t)0, as_stream(stream), ce_losses, ppc_losses, cov_coe, mean_coe,
+             out_losses);
+    return launch_status("pph_loss_combine");
+}
 
 extern "C" int pph_loss_tail(const float* logits, const int64_t* labels, const float* ppc_losses,
                              float cov_coe, float mean_coe, float upstream, int B, int C,
@@ -66,8 +90,6 @@ extern "C" int pph_loss_tail(const float* logits, const int64_t* labels, const f
     using namespace pph;
     PPH_REQUIRE(logits && labels && partial && counter && out_losses, PPH_EINVAL, "pph_loss_tail: null pointer");
     PPH_REQUIRE(B >= 1 && C >= 1, PPH_EINVAL, "pph_loss_tail: bad dims B=%d C=%d", B, C);
-    loss_tail_kernel<<<ceil_div(B, 8), 256, 0, as_stream(stream)>>>(logits, labels, ppc_losses, cov_coe, mean_coe,
-                                                                   upstream, B, C, partial, counter, out_losses,
-                                                                   dlogits);
+    launch_k(loss_tail_kernel, dim3(ceil_div(B, 8)), dim3(256), (size_t)(0), as_stream(stream), logits, labels, ppc_losses, cov_coe, mean_coe, upstream, B, C, partial, counter, out_losses, dlogits);
     return launch_status("pph_loss_tail");
 }

@@ -84,6 +84,7 @@ ppc_fwd_kernel(const float* __restrict__ Zs, const float* __restrict__ z2s, cons
                float cov_thresh, float mean_thresh,
                float* __restrict__ dslice, float* __restrict__ stats, float* partial, unsigned int* counter,
                float* __restrict__ losses) {
+    pdl_sync();
     extern __shared__ __align__(16) float sm[];
     const PpcSmem s = ppc_carve(sm, m, D, K, kc);
     __shared__ float red[kPpcThreads / 32];
@@ -204,6 +205,7 @@ ppc_bwd_kernel(const float* __restrict__ Zs, const float* __restrict__ Pl, const
                int B, int K, int D, int P, int m, int N, int side,
                int act_fn, float eps, float mean_thresh, int accumulate, float* __restrict__ dZs,
                float* __restrict__ dP) {
+    pdl_sync();
     extern __shared__ __align__(16) float sm[];
     float* Prow = sm;                         // [m][D]
     float* Zt = Prow + m * D;                 // [kPpcBwdTok][D]
@@ -302,9 +304,7 @@ static int launch_ppc_bwd(dim3 grid, size_t smem, cudaStream_t st, const float* 
         cudaError_t e = cudaFuncSetAttribute(ppc_bwd_kernel<DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("pph_ppc_bwd: %s", cudaGetErrorString(e)); return (int)e; }
     }
-    ppc_bwd_kernel<DV><<<grid, kPpcBwdThreads, smem, st>>>(Zs, Pl, idx32, labels, dslice, stats, g_losses, gs_cov,
-                                                          gs_mean, B, K, D, P, m, N, side, act_fn, eps, mean_thresh,
-                                                          accumulate, dZs, dP);
+    launch_k(ppc_bwd_kernel<DV>, dim3(grid), dim3(kPpcBwdThreads), (size_t)(smem), st, Zs, Pl, idx32, labels, dslice, stats, g_losses, gs_cov, gs_mean, B, K, D, P, m, N, side, act_fn, eps, mean_thresh, accumulate, dZs, dP);
     return launch_status("pph_ppc_bwd");
 }
 
@@ -344,9 +344,7 @@ extern "C" int pph_ppc_fwd(const float* Zs, const float* z2s, const float* Pl, c
         cudaError_t e = cudaFuncSetAttribute(ppc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) { set_error("pph_ppc_fwd: %s", cudaGetErrorString(e)); return (int)e; }
     }
-    ppc_fwd_kernel<<<B, kPpcThreads, smem, as_stream(stream)>>>(Zs, z2s, Pl, p2l, idx32, labels, B, K, D, P, m, N,
-                                                               side, kc, act_fn, eps, cov_thresh, mean_thresh, dslice,
-                                                               stats, partial, counter, losses);
+    launch_k(ppc_fwd_kernel, dim3(B), dim3(kPpcThreads), (size_t)(smem), as_stream(stream), Zs, z2s, Pl, p2l, idx32, labels, B, K, D, P, m, N, side, kc, act_fn, eps, cov_thresh, mean_thresh, dslice, stats, partial, counter, losses);
     return launch_status("pph_ppc_fwd");
 }
 

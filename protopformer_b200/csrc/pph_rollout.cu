@@ -1,0 +1,352 @@
+// Attention rollout -> CLS-row token score: the producer of `cls_token_attn`, the score the
+// prototype head's foreground selection consumes.  Replaces, per reserve layer,
+//   tools/deit_models_attn.py:99-124  attn_rollout   (head mean, discard of the int(T*T*0.9) smallest entries by
+//                                     topk + scatter_, (A + 0.2 I) / 1.2, row normalisation, L batched T^3 matmuls)
+//   tools/deit_models_attn.py:226     cls_token_attn = attn_rollout[:, 0, 1:]
+// Only row 0 of the product is consumed, so the matmul chain collapses to L vector-matrix products walked from the
+// last layer to the first, and after the discard only ~10 % of every matrix is non-zero.  Two kernels:
+//
+//  rollout_prepare_kernel  (HBM bound: reads every attention tensor exactly once, H*T*T*4 B per (layer, image))
+//    persistent CTAs, one (layer, image) tile at a time: stream the H head maps, fuse them into a T x T fp32 tile in
+//    shared memory (155 KB at T = 197), find the EXACT k-th smallest entry with a 4-pass 8-bit radix select on the
+//    order-preserving integer image of the floats (warp-aggregated shared-memory histograms), zero the k smallest
+//    (ties at the threshold: lowest flat index first), add the identity, normalise the rows, and write the surviving
+//    entries as a column-compressed sparse matrix (<= T*T - k + T entries: ~25 KB instead of 155 KB).
+//  rollout_chain_kernel    (latency bound, tiny: the sparse matrices are L2 resident)
+//    one CTA per image: v = e_0 (or a caller-supplied start row, the CaiT variant cait_models_attn.py:255-259);
+//    for l = L-1 .. 0: v <- v @ a_l as a gather over the columns' entry lists (one warp per column, fixed summation
+//    order -> bit-reproducible); scores[b, :] = v[1:] (or all of v).
+#include <math.h>
+
+#include "pph_common.cuh"
+
+namespace pph {
+
+constexpr int kRoThreads = 1024;
+constexpr int kRoMaxLayers = 32;
+constexpr int kRoMaxT = 224;              // T*T*4 B must fit in shared memory beside the scratch
+constexpr int kRoChainThreads = 512;
+
+struct RoLayers {
+    const float* p[kRoMaxLayers];
+};
+
+struct RoWorkspace {
+    int32_t* col_ptr;      // [L*B][T+1]
+    float* ent_val;        // [L*B][cap]
+    uint16_t* ent_row;     // [L*B][cap]
+    int cap;
+};
+
+static inline int rollout_cap(int T, int k_discard) { return ((T * T - k_discard + T) + 7) & ~7; }
+
+static RoWorkspace rollout_carve(void* ws, int L, int B, int T, int k_discard) {
+    RoWorkspace w;
+    w.cap = rollout_cap(T, k_discard);
+    uint8_t* p = reinterpret_cast<uint8_t*>(ws);
+    const size_t tiles = (size_t)L * B;
+    w.col_ptr = reinterpret_cast<int32_t*>(p);
+    p += ((tiles * (T + 1) * 4 + 255) / 256) * 256;
+    w.ent_val = reinterpret_cast<float*>(p);
+    p += ((tiles * w.cap * 4 + 255) / 256) * 256;
+    w.ent_row = reinterpret_cast<uint16_t*>(p);
+    return w;
+}
+
+static long long rollout_ws_bytes(int L, int B, int T, int k_discard) {
+    const size_t tiles = (size_t)L * B;
+    const int cap = rollout_cap(T, k_discard);
+    return (long long)(((tiles * (T + 1) * 4 + 255) / 256) * 256 + ((tiles * cap * 4 + 255) / 256) * 256 +
+                       ((tiles * cap * 2 + 255) / 256) * 256);
+}
+
+// order-preserving map float -> uint32 (a < b  <=>  key(a) < key(b); -0 is folded onto +0 first)
+__device__ __forceinline__ uint32_t ro_key(float x) {
+    const uint32_t b = __float_as_uint(x + 0.0f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// exclusive scan of one value per thread over the whole CTA (kRoThreads threads); `wsum` = 32 ints of scratch
+__device__ __forceinline__ int block_excl_scan(int v, int* wsum, int& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int w = wsum[lane];
+        int wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += t;
+        }
+        wsum[lane] = wi - w;                     // exclusive warp offsets
+        if (lane == 31) wsum[32] = wi;           // grand total
+    }
+    __syncthreads();
+    total = wsum[32];
+    const int r = wsum[warp] + incl - v;
+    __syncthreads();                             // wsum may be reused by the caller
+    return r;
+}
+
+template <int HT>      // HT > 0: compile-time head count (the head loop unrolls, 8*HT loads in flight); 0: runtime H
+__global__ void __launch_bounds__(kRoThreads, 1)
+rollout_prepare_kernel(const RoLayers layers, int L, int B, int H, int T, int k_discard, int head_fusion,
+                       float identity_w, int cap, int32_t* __restrict__ col_ptr, float* __restrict__ ent_val,
+                       uint16_t* __restrict__ ent_row) {
+    pdl_sync();
+    extern __shared__ __align__(16) uint8_t ro_smem[];
+    const int n = T * T;
+    float* M = reinterpret_cast<float*>(ro_smem);                            // [T*T]
+    uint32_t* hist = reinterpret_cast<uint32_t*>(M + ((n + 3) & ~3));        // [256]
+    int* cnt = reinterpret_cast<int*>(hist + 256);                           // [1024] per-(column, segment) counts
+    int* wsum = cnt + kRoThreads;                                            // [33]
+    __shared__ uint32_t s_prefix, s_cnt;
+    __shared__ int s_krem;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n_pad = (n + 31) & ~31;
+    const int Hh = HT > 0 ? HT : H;
+    const int seg = min(5, kRoThreads / T);                 // row segments per column for the sparse build
+    const int rps = (T + seg - 1) / seg;
+
+    for (int tile = blockIdx.x; tile < L * B; tile += gridDim.x) {
+        const int l = tile / B, b = tile - l * B;
+        // ---- 1. stream the H head maps once, fuse (deit_models_attn.py:102-107); 8 x H loads in flight per thread ----
+        const float* A = layers.p[l] + (size_t)b * Hh * n;
+        for (int e0 = 0; e0 < n; e0 += 8 * kRoThreads) {
+            float s[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int e = e0 + i * kRoThreads + tid;
+                s[i] = e < n ? __ldcs(A + e) : 0.0f;
+            }
+#pragma unroll
+            for (int h = 1; h < Hh; ++h) {
+                float t[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int e = e0 + i * kRoThreads + tid;
+                    t[i] = e < n ? __ldcs(A + (size_t)h * n + e) : 0.0f;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    s[i] = head_fusion == 0 ? s[i] + t[i] : head_fusion == 1 ? fmaxf(s[i], t[i]) : fminf(s[i], t[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int e = e0 + i * kRoThreads + tid;
+                if (e < n) M[e] = head_fusion == 0 ? s[i] / (float)Hh : s[i];      // torch.mean = sum / count
+            }
+        }
+        __syncthreads();
+
+        // ---- 2. exact k-th smallest by radix select (4 passes x 8 bits, MSB first) ----
+        uint32_t prefix = 0, eq_total = 0;
+        int krem = k_discard < n ? k_discard : n;
+        if (krem > 0) {
+            for (int pass = 0; pass < 4; ++pass) {
+                const int shift = 24 - 8 * pass;
+                const uint32_t himask = pass == 0 ? 0u : (0xFFFFFFFFu << (shift + 8));
+                if (tid < 256) hist[tid] = 0;
+                __syncthreads();
+                for (int e = tid; e < n_pad; e += kRoThreads) {      // whole warps stay converged for the ballot
+                    const uint32_t key = e < n ? ro_key(M[e]) : 0u;
+                    const bool act = e < n && (key & himask) == prefix;
+                    const uint32_t digit = (key >> shift) & 0xFFu;
+                    const unsigned m_act = __ballot_sync(0xffffffffu, act);
+                    if (act) {
+                        const unsigned peers = __match_any_sync(m_act, digit);
+                        if (lane == __ffs(peers) - 1) atomicAdd(&hist[digit], (uint32_t)__popc(peers));
+                    }
+                }
+                __syncthreads();
+                if (warp == 0) {
+                    uint32_t c[8], s = 0;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) { c[i] = hist[lane * 8 + i]; s += c[i]; }
+                    uint32_t incl = s;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                        if (lane >= o) incl += t;
+                    }
+                    const uint32_t excl = incl - s;
+                    if (excl < (uint32_t)krem && (uint32_t)krem <= incl) {      // exactly one lane
+                        uint32_t run = excl;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if ((uint32_t)krem > run && (uint32_t)krem <= run + c[i]) {
+                                s_prefix = prefix | ((uint32_t)(lane * 8 + i) << shift);
+                                s_krem = krem - (int)run;
+                                s_cnt = c[i];
+                            }
+                            run += c[i];
+                        }
+                    }
+                }
+                __syncthreads();
+                prefix = s_prefix;
+                krem = s_krem;
+                eq_total = s_cnt;
+                __syncthreads();
+            }
+            // ---- 3. discard (deit_models_attn.py:110-113): everything below the threshold ... ----
+            const bool all_equal_go = (uint32_t)krem == eq_total;
+            for (int e = tid; e < n; e += kRoThreads) {
+                const uint32_t key = ro_key(M[e]);
+                if (key < prefix || (all_equal_go && key == prefix)) M[e] = 0.0f;
+            }
+            __syncthreads();
+            // ... and `krem` of the entries EQUAL to it, lowest flat index first
+            if (!all_equal_go && warp == 0) {                                   // rare: a tie straddles the threshold
+                int seen = 0;
+                for (int e0 = 0; e0 < n && seen < krem; e0 += 32) {
+                    const int e = e0 + lane;
+                    const bool eq = e < n && ro_key(M[e]) == prefix;
+                    const unsigned m = __ballot_sync(0xffffffffu, eq);
+                    if (eq && seen + __popc(m & ((1u << lane) - 1u)) < krem) M[e] = 0.0f;
+                    seen += __popc(m);
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- 4. a = (A + w I) / (1 + w), rows normalised (deit_models_attn.py:118-121); warp = row ----
+        const float inv_den = 1.0f + identity_w;
+        for (int r = warp; r < T; r += kRoThreads / 32) {
+            float* row = M + r * T;
+            float s = 0.f;
+            for (int j = lane; j < T; j += 32) {
+                const float a = (row[j] + (j == r ? identity_w : 0.0f)) / inv_den;
+                row[j] = a;
+                s += a;
+            }
+            s = warp_sum(s);
+            for (int j = lane; j < T; j += 32) row[j] = row[j] / s;
+        }
+        __syncthreads();
+
+        // ---- 5. column-compressed sparse output: thread = (row segment sg, column j), entries ordered by (j, row) ----
+        const bool worker = tid < seg * T;
+        const int sg = tid / T, j = tid - sg * T;
+        const int r0 = sg * rps, r1 = min(T, r0 + rps);
+        int mine = 0;
+        if (worker)
+            for (int r = r0; r < r1; ++r) mine += (M[r * T + j] != 0.0f);
+        cnt[tid] = 0;
+        __syncthreads();
+        if (worker) cnt[j * seg + sg] = mine;
+        __syncthreads();
+        int total;
+        const int excl = block_excl_scan(cnt[tid], wsum, total);
+        cnt[tid] = excl;
+        __syncthreads();
+        int32_t* cp = col_ptr + (size_t)tile * (T + 1);
+        if (worker) {
+            int o = cnt[j * seg + sg];
+            if (sg == 0) cp[j] = o;
+            float* ev = ent_val + (size_t)tile * cap;
+            uint16_t* er = ent_row + (size_t)tile * cap;
+            for (int r = r0; r < r1; ++r) {
+                const float a = M[r * T + j];
+                if (a != 0.0f && o < cap) {
+                    ev[o] = a;
+                    er[o] = (uint16_t)r;
+                    ++o;
+                }
+            }
+        }
+        if (tid == 0) cp[T] = total < cap ? total : cap;
+        __syncthreads();                                              // M is overwritten by the next tile
+    }
+}
+
+__global__ void __launch_bounds__(kRoChainThreads)
+rollout_chain_kernel(int L, int B, int T, int cap, const int32_t* __restrict__ col_ptr,
+                     const float* __restrict__ ent_val, const uint16_t* __restrict__ ent_row,
+                     const float* __restrict__ v0, int drop_first, float* __restrict__ scores) {
+    pdl_sync();
+    __shared__ float v[2][kRoMaxT];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int j = tid; j < T; j += kRoChainThreads) v[0][j] = v0 ? v0[(size_t)b * T + j] : (j == 0 ? 1.0f : 0.0f);
+    __syncthreads();
+    int cur = 0;
+    for (int l = L - 1; l >= 0; --l) {
+        const size_t tile = (size_t)l * B + b;
+        const int32_t* cp = col_ptr + tile * (T + 1);
+        const float* ev = ent_val + tile * cap;
+        const uint16_t* er = ent_row + tile * cap;
+        for (int j = warp; j < T; j += kRoChainThreads / 32) {
+            const int beg = cp[j], end = cp[j + 1];
+            float s = 0.f;
+            for (int e = beg + lane; e < end; e += 32) s = fmaf(v[cur][er[e]], ev[e], s);
+            s = warp_sum(s);
+            if (lane == 0) v[cur ^ 1][j] = s;
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    const int W = T - drop_first;
+    for (int j = tid; j < W; j += kRoChainThreads) scores[(size_t)b * W + j] = v[cur][j + drop_first];
+}
+
+}  // namespace pph
+
+extern "C" int pph_rollout_ws_bytes(int L, int B, int T, int k_discard, long long* bytes) {
+    using namespace pph;
+    PPH_REQUIRE(bytes && L >= 1 && B >= 0 && T >= 1 && k_discard >= 0, PPH_EINVAL, "pph_rollout_ws_bytes: bad arguments");
+    *bytes = rollout_ws_bytes(L, B, T, k_discard < T * T ? k_discard : T * T);
+    return 0;
+}
+
+extern "C" int pph_rollout_scores(const float* const* attn_layers, int L, int B, int H, int T, int k_discard,
+                                  int head_fusion, float identity_w, const float* v0, int drop_first, void* workspace,
+                                  float* scores, pph_stream_t stream) {
+    using namespace pph;
+    PPH_REQUIRE(attn_layers && workspace && scores, PPH_EINVAL, "pph_rollout_scores: null pointer");
+    PPH_REQUIRE(L >= 1 && L <= kRoMaxLayers, PPH_EUNSUP, "pph_rollout_scores: 1 <= L <= %d (L=%d)", kRoMaxLayers, L);
+    PPH_REQUIRE(B >= 0 && H >= 1 && T >= 2 && k_discard >= 0 && (drop_first == 0 || drop_first == 1), PPH_EINVAL,
+                "pph_rollout_scores: bad dims B=%d H=%d T=%d k=%d", B, H, T, k_discard);
+    PPH_REQUIRE(T <= kRoMaxT, PPH_EUNSUP, "pph_rollout_scores: T=%d > %d (the fused map must fit in shared memory)", T,
+                kRoMaxT);
+    PPH_REQUIRE(head_fusion >= 0 && head_fusion <= 2, PPH_EINVAL, "pph_rollout_scores: head_fusion %d", head_fusion);
+    if (B == 0) return 0;
+    if (k_discard > T * T) k_discard = T * T;
+    RoLayers layers;
+    for (int l = 0; l < kRoMaxLayers; ++l) layers.p[l] = l < L ? attn_layers[l] : nullptr;
+    for (int l = 0; l < L; ++l) PPH_REQUIRE(layers.p[l], PPH_EINVAL, "pph_rollout_scores: layer %d is null", l);
+    const RoWorkspace w = rollout_carve(workspace, L, B, T, k_discard);
+    const int n = T * T;
+    const size_t smem = (size_t)((n + 3) & ~3) * 4 + 256 * 4 + (kRoThreads + 40) * 4;
+    static int sms = 0;
+    if (sms <= 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    const int tiles = L * B;
+    cudaStream_t st = as_stream(stream);
+    const dim3 grid(tiles < sms ? tiles : sms);
+    auto go = [&](auto kern) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e != cudaSuccess) { set_error("pph_rollout_scores: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        launch_k(kern, grid, dim3(kRoThreads), smem, st, layers, L, B, H, T, k_discard, head_fusion, identity_w, w.cap,
+                 w.col_ptr, w.ent_val, w.ent_row);
+        return launch_status("pph_rollout_scores(prepare)");
+    };
+    // head counts of the reference's backbones: DeiT-Ti 3, CaiT-XXS 4, DeiT-S 6 (deit_models_attn.py:288,303)
+    int rc = H == 3 ? go(rollout_prepare_kernel<3>) : H == 4 ? go(rollout_prepare_kernel<4>)
+             : H == 6 ? go(rollout_prepare_kernel<6>) : go(rollout_prepare_kernel<0>);
+    if (rc) return rc;
+    launch_k(rollout_chain_kernel, dim3(B), dim3(kRoChainThreads), (size_t)0, st, L, B, T, w.cap, w.col_ptr, w.ent_val,
+             w.ent_row, v0, drop_first, scores);
+    return launch_status("pph_rollout_scores(chain)");
+}

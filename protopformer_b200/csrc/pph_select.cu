@@ -18,6 +18,7 @@ constexpr int kSelMaxN = 1024;
 __global__ void __launch_bounds__(kSelThreads)
 select_topk_kernel(const float* __restrict__ scores, int H, int N, int K,
                    int32_t* __restrict__ idx32, int64_t* __restrict__ idx64) {
+    pdl_sync();
     __shared__ __align__(16) float s[kSelMaxN];
     __shared__ int warp_cnt[kSelThreads / 32];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -76,6 +77,6 @@ extern "C" int pph_select_topk(const float* scores, int B, int H, int N, int K,
                 "pph_select_topk: bad dims B=%d H=%d N=%d K=%d", B, H, N, K);
     PPH_REQUIRE(N <= pph::kSelMaxN, PPH_EUNSUP, "pph_select_topk: N=%d > %d", N, pph::kSelMaxN);
     if (B == 0) return 0;
-    pph::select_topk_kernel<<<B, pph::kSelThreads, 0, pph::as_stream(stream)>>>(scores, H, N, K, idx32, idx64);
+    pph::launch_k(pph::select_topk_kernel, dim3(B), dim3(pph::kSelThreads), (size_t)(0), pph::as_stream(stream), scores, H, N, K, idx32, idx64);
     return pph::launch_status("pph_select_topk");
 }

@@ -39,6 +39,7 @@ __device__ __forceinline__ void gemm_load_tile(float (*dst)[kGemmBM + kGemmPad],
 template <bool kRowSum, class AOp, class BOp, class Epi>
 __global__ void __launch_bounds__(kGemmThreads)
 sgemm_kernel(int M, int N, int Kd, int k_per_split, AOp a_op, BOp b_op, Epi epi) {
+    pdl_sync();
     __shared__ __align__(16) float As[kGemmBK][kGemmBM + kGemmPad];
     __shared__ __align__(16) float Bs[kGemmBK][kGemmBN + kGemmPad];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -102,7 +103,7 @@ inline void launch_sgemm(int M, int N, int Kd, int splits, AOp a, BOp b, Epi e, 
     splits = ceil_div(Kd, k_per_split);
     if (splits < 1) splits = 1;
     dim3 grid(ceil_div(N, kGemmBN), ceil_div(M, kGemmBM), splits);
-    sgemm_kernel<kRowSum><<<grid, kGemmThreads, 0, st>>>(M, N, Kd, k_per_split, a, b, e);
+    launch_k(sgemm_kernel<kRowSum, AOp, BOp, Epi>, dim3(grid), dim3(kGemmThreads), (size_t)(0), st, M, N, Kd, k_per_split, a, b, e);
 }
 
 }  // namespace pph

@@ -23,6 +23,7 @@ constexpr int kBinChunk = 32;
 __global__ void __launch_bounds__(256)
 bin_tokens_kernel(const int32_t* __restrict__ argmin_l, int K, int P, int32_t* __restrict__ bin_start,
                   int32_t* __restrict__ item_start, int32_t* __restrict__ bin_list) {
+    pdl_sync();
     extern __shared__ int smi[];
     int* hist = smi;                      // [8][K]   per-warp histogram, then per-warp cursor
     int* tot = smi + 8 * K;               // [K+1]    bin offsets
@@ -366,6 +367,7 @@ sim_grads_kernel(const float* __restrict__ g_l, const float* __restrict__ g_g, c
                  float* tok_part, float* tok_gsum, unsigned int* tok_counters, float* cls_part,
                  unsigned int* cls_counters, const float* __restrict__ add_dZs, const float* __restrict__ add_dPl,
                  float* __restrict__ dZs, float* __restrict__ dZc, float* __restrict__ dPl, float* __restrict__ dPg) {
+    pdl_sync();
     int vb = blockIdx.x;
     if (vb < n_cls) {
         cls_grad_body(vb % n_slices, vb / n_slices, n_slices, g_g, Zc, Pgl, B, D, Pg, p_per_slice, cls_part, cls_counters, dZc);
@@ -392,10 +394,7 @@ static int launch_bwd(const float* g_l, const float* g_g, const int32_t* argmin_
     const int n_cls = nsl * ceil_div(B, kClsTB);
     const int n_proto = ceil_div(P + Pg, 8);
     const int n_tok = ceil_div(B * w.items_per_image, 8);
-    sim_grads_kernel<DV, FULL><<<n_cls + n_proto + n_tok, 256, 0, st>>>(
-        g_l, g_g, argmin_l, w.bin_start, w.item_start, w.bin_list, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, w.items_per_image,
-        n_cls, nsl, p_per_slice, n_proto, w.tok_part, w.tok_gsum, w.tok_counters, w.cls_part, w.cls_counters, add_dZs,
-        add_dPl, dZs, dZc, dPl, dPg);
+    launch_k(sim_grads_kernel<DV, FULL>, dim3(n_cls + n_proto + n_tok), dim3(256), (size_t)(0), st, g_l, g_g, argmin_l, w.bin_start, w.item_start, w.bin_list, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, w.items_per_image, n_cls, nsl, p_per_slice, n_proto, w.tok_part, w.tok_gsum, w.tok_counters, w.cls_part, w.cls_counters, add_dZs, add_dPl, dZs, dZc, dPl, dPg);
     return launch_status("pph_similarity_bwd(grads)");
 }
 
@@ -420,7 +419,7 @@ extern "C" int pph_similarity_bwd(const float* g_l, const float* g_g, const int3
         const size_t bs = sizeof(int) * ((size_t)8 * K + 2 * (size_t)(K + 1));
         PPH_REQUIRE(bs <= 48 * 1024, PPH_EUNSUP, "pph_similarity_bwd: K too large");
         const BwdWorkspace wb = carve_ws(workspace, B, K, D, P, Pg);
-        bin_tokens_kernel<<<B, 256, bs, as_stream(stream)>>>(argmin_l, K, P, wb.bin_start, wb.item_start, wb.bin_list);
+        launch_k(bin_tokens_kernel, dim3(B), dim3(256), (size_t)(bs), as_stream(stream), argmin_l, K, P, wb.bin_start, wb.item_start, wb.bin_list);
         return launch_status("pph_similarity_bwd(bin)");
     }
     PPH_REQUIRE(g_l && argmin_l && Zs && Pl && dZs && dPl, PPH_EINVAL, "pph_similarity_bwd: null local pointer");
@@ -439,7 +438,7 @@ extern "C" int pph_similarity_bwd(const float* g_l, const float* g_g, const int3
     const BwdWorkspace w = carve_ws(workspace, B, K, D, P, Pg);
     int rc = 0;
     if (parts & PPH_BWD_BIN) {
-        bin_tokens_kernel<<<B, 256, bin_smem, st>>>(argmin_l, K, P, w.bin_start, w.item_start, w.bin_list);
+        launch_k(bin_tokens_kernel, dim3(B), dim3(256), (size_t)(bin_smem), st, argmin_l, K, P, w.bin_start, w.item_start, w.bin_list);
         rc = launch_status("pph_similarity_bwd(bin)");
         if (rc) return rc;
     }

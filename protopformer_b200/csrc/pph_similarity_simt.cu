@@ -19,6 +19,7 @@ similarity_local_simt_kernel(const float* __restrict__ Zs, const float* __restri
                              int K, int D, int P, int act_fn, float eps,
                              float* __restrict__ dmin, int32_t* __restrict__ argmin, float* __restrict__ act,
                              float* __restrict__ dist_map, float* __restrict__ act_map) {
+    pdl_sync();
     __shared__ __align__(16) float Zt[kSimBK][kSimTok + 4];
     __shared__ __align__(16) float Pt[kSimBK][kSimProt + 4];
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -115,8 +116,7 @@ int similarity_fwd_simt(int act_fn, float eps, int B, int K, int D, int P, int P
                         float* dist_map, float* act_map, cudaStream_t st) {
     if (P > 0) {
         dim3 grid(ceil_div(P, kSimProt), B);
-        similarity_local_simt_kernel<<<grid, kSimThreads, 0, st>>>(Zs, z2s, Pl, p2l, K, D, P, act_fn, eps, dmin_l,
-                                                                 argmin_l, act_l, dist_map, act_map);
+        launch_k(similarity_local_simt_kernel, dim3(grid), dim3(kSimThreads), (size_t)(0), st, Zs, z2s, Pl, p2l, K, D, P, act_fn, eps, dmin_l, argmin_l, act_l, dist_map, act_map);
         int rc = launch_status("pph_similarity_fwd(fp32 local)");
         if (rc) return rc;
     }

@@ -18,6 +18,7 @@
 // accumulator ring (2 x 256 columns; tmem_full by tcgen05.commit, tmem_empty by the epilogue warps), so the
 // epilogue of tile i overlaps the MMAs of tile i+1 and the other group's epilogue of tile i-1.
 #include <math.h>
+#include <stdlib.h>
 
 #include "pph_common.cuh"
 #include "pph_tc_ptx.cuh"
@@ -41,6 +42,7 @@ struct TcParams {
     int MT_g, NB_g;           // global tiles: prototype tiles x image chunks (256 images)
     int n_local, n_tiles;
     int umma_n_l, umma_n_g;   // UMMA N (multiple of 16)
+    int gN;                   // images per global tile (<= 256)
     int box_rows_l, box_rows_g;
     int act_fn;
     float eps;
@@ -74,10 +76,81 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// Drain one accumulator tile: thread = prototype row (TMEM lane), walks its columns with tcgen05.ld.
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+
+// Local tile, compile-time token count, latency-tolerant form (EPI = 1).  The straightforward running
+// (min, argmin) scan is ONE dependent compare->select chain of K links per image (~10 cycles per link with 1-2
+// epilogue warps per scheduler: ncu put the 128 x 243 tile at ~4.3 k cycles, 3x the MMA time of the bf16 mode).
+// Here every image keeps four independent (min, argmin) chains over the token slots k = 0,1,2,3 (mod 4), merged at the
+// image boundary with the lowest-index tie rule, and the tcgen05.ld of chunk i+1 is in flight while chunk i is
+// scanned.  Results are identical to the sequential scan (lowest k among equal minima).
 template <int KT>
+__device__ __forceinline__ void tc_epilogue_local_ilp(const TcParams& prm, const TcTile& t, uint32_t taddr,
+                                                      uint32_t x2_saddr, int quarter, int lane) {
+    static_assert(KT >= 4, "four chains need four token slots");
+    constexpr int GS = kTcMaxN / KT, TC = GS * KT, NCH = (TC + 31) / 32;
+    const int p = t.mt * kTcBlockM + quarter * 32 + lane;
+    const bool pv = p < prm.P;
+    const float p2 = pv ? __ldg(prm.p2l + p) : 0.f;
+    const int b0 = t.grp * prm.G;
+    float best[4];
+    int bk[4];
+    uint32_t va[32], vb[32];
+    ptx::tmem_ld_32x32(taddr, va);
+    ptx::tmem_ld_wait(va);
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+        uint32_t(&cur)[32] = (ch & 1) ? vb : va;
+        uint32_t(&nxt)[32] = (ch & 1) ? va : vb;
+        if (ch + 1 < NCH) ptx::tmem_ld_32x32(taddr + (ch + 1) * 32, nxt);
+        float4 xq[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) xq[i] = lds_f4(x2_saddr + (uint32_t)(ch * 8 + i) * 16u);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int col = ch * 32 + j;
+            if (col < TC) {
+                const int k = col % KT, g = col / KT, c = k & 3;
+                const float4 q = xq[j >> 2];
+                const float xx = (j & 3) == 0 ? q.x : (j & 3) == 1 ? q.y : (j & 3) == 2 ? q.z : q.w;
+                const float d = fmaf(-2.0f, __uint_as_float(cur[j]), xx);
+                if (k < 4) { best[c] = d; bk[c] = k; }
+                else if (d < best[c]) { best[c] = d; bk[c] = k; }
+                if (k == KT - 1) {
+                    float bb = best[0];
+                    int kk = bk[0];
+#pragma unroll
+                    for (int cc = 1; cc < 4; ++cc)
+                        if (best[cc] < bb || (best[cc] == bb && bk[cc] < kk)) { bb = best[cc]; kk = bk[cc]; }
+                    const int b = b0 + g;
+                    if (pv && b < prm.B) {
+                        const float dd = fmaxf(bb + p2, 0.0f);
+                        const size_t o = (size_t)b * prm.P + p;
+                        prm.dmin_l[o] = dd;
+                        prm.argmin_l[o] = kk;
+                        prm.act_l[o] = act_of_dist(dd, prm.act_fn, prm.eps);
+                    }
+                }
+            }
+        }
+        if (ch + 1 < NCH) ptx::tmem_ld_wait(nxt);
+    }
+}
+
+// Drain one accumulator tile: thread = prototype row (TMEM lane), walks its columns with tcgen05.ld.
+template <int KT, int EPI = 1>
 __device__ __forceinline__ void tc_epilogue_tile(const TcParams& prm, const TcTile& t, uint32_t taddr, const float* x2,
                                                  const float4* x2v, int quarter, int lane) {
+    if constexpr (KT >= 4 && EPI == 1) {
+        if (!t.is_global) {
+            tc_epilogue_local_ilp<KT>(prm, t, taddr, ptx::smem_u32(x2), quarter, lane);
+            return;
+        }
+    }
     const int p = t.mt * kTcBlockM + quarter * 32 + lane;
     if (!t.is_global) {
         const bool pv = p < prm.P;
@@ -144,8 +217,8 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& prm, const TcTi
     } else {
         const bool pv = p < prm.Pg;
         const float p2 = pv ? __ldg(prm.p2g + p) : 0.f;
-        const int b0 = t.grp * kTcMaxN;
-        const int ncols = min(prm.B - b0, kTcMaxN);
+        const int b0 = t.grp * prm.gN;
+        const int ncols = min(prm.B - b0, prm.gN);
         for (int c0 = 0; c0 < ncols; c0 += 32) {
             uint32_t v[32];
             ptx::tmem_ld_32x32(taddr + c0, v);
@@ -194,6 +267,7 @@ similarity_tc_kernel(const __grid_constant__ CUtensorMap tmAl_hi, const __grid_c
         for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 4); }
         ptx::fence_mbar_init();
     }
+    pdl_sync();   // barriers and tensor-map prefetch overlap the previous kernel; TMEM and all global reads wait for it
     if (warp == 2) ptx::tmem_alloc(tmem_ptr, 512);
     ptx::tc_fence_before();
     __syncthreads();
@@ -207,7 +281,7 @@ similarity_tc_kernel(const __grid_constant__ CUtensorMap tmAl_hi, const __grid_c
         for (int tile = blockIdx.x; tile < prm.n_tiles; tile += gridDim.x) {
             const TcTile t = tc_decode(prm, tile);
             const int rowA = t.mt * kTcBlockM;
-            const int rowB = t.is_global ? t.grp * kTcMaxN : t.grp * prm.G * prm.K;
+            const int rowB = t.is_global ? t.grp * prm.gN : t.grp * prm.G * prm.K;
             const uint32_t bytes = kTcABytes + (uint32_t)(t.is_global ? prm.box_rows_g : prm.box_rows_l) * kTcBlockK * 2;
 #pragma unroll 1
             for (int term = 0; term < NTERMS; ++term) {
@@ -284,7 +358,7 @@ similarity_tc_kernel(const __grid_constant__ CUtensorMap tmAl_hi, const __grid_c
                 const long r0 = (long)t.grp * prm.G * prm.K, rmax = (long)prm.B * prm.K;
                 for (int c = gtid; c < kTcMaxN; c += 128) x2[c] = (r0 + c < rmax) ? __ldg(prm.z2s + r0 + c) : 0.f;
             } else {
-                const int b0 = t.grp * kTcMaxN;
+                const int b0 = t.grp * prm.gN;
                 for (int c = gtid; c < kTcMaxN; c += 128) x2[c] = (b0 + c < prm.B) ? __ldg(prm.z2c + b0 + c) : 0.f;
             }
             named_bar_sync(1 + grp_id, 128);
@@ -318,24 +392,30 @@ similarity_tc_kernel(const __grid_constant__ CUtensorMap tmAl_hi, const __grid_c
 //   remaining CTAs       : global prototype tiles, round robin (each reloads its resident tile per phase)
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kTc2MaxStages = 6;
+constexpr int kTc2MaxKBlocks = 8;                           // D <= 512
 
 struct Tc2Job {
     bool is_global;
     int mt, t_begin, t_step, t_end;
 };
 
-__device__ __forceinline__ bool tc2_phase(const TcParams& prm, int cta, int p, int lanes_l, int n_local_ctas, int grid_g,
+__device__ __forceinline__ bool tc2_phase(const TcParams& prm, int cta, int p, int lanes_l, int n_local_ctas, int grid,
                                           Tc2Job& j) {
+    int q = p;
     if (cta < n_local_ctas) {
-        if (p > 0) return false;
-        j.is_global = false;
-        j.mt = cta % prm.MT_l;
-        j.t_begin = cta / prm.MT_l;
-        j.t_step = lanes_l;
-        j.t_end = prm.NG_l;
-        return true;
+        if (p == 0) {
+            j.is_global = false;
+            j.mt = cta % prm.MT_l;
+            j.t_begin = cta / prm.MT_l;
+            j.t_step = lanes_l;
+            j.t_end = prm.NG_l;
+            return true;
+        }
+        q = p - 1;
     }
-    const int mt = (cta - n_local_ctas) + p * grid_g;
+    // global prototype tiles are dealt from the END of the grid: first to the CTAs without a local job, then to the
+    // highest local lanes (the ones with the fewest image groups when NG_l % lanes_l != 0)
+    const int mt = (grid - 1 - cta) + q * grid;
     if (mt >= prm.MT_g) return false;
     j.is_global = true;
     j.mt = mt;
@@ -345,13 +425,13 @@ __device__ __forceinline__ bool tc2_phase(const TcParams& prm, int cta, int p, i
     return true;
 }
 
-template <int NTERMS, int KT>
+template <int NTERMS, int KT, int EPI>
 __global__ void __launch_bounds__(kTcThreads, 1)
 similarity_tc2_kernel(const __grid_constant__ CUtensorMap tmAl_hi, const __grid_constant__ CUtensorMap tmAl_lo,
                       const __grid_constant__ CUtensorMap tmBl_hi, const __grid_constant__ CUtensorMap tmBl_lo,
                       const __grid_constant__ CUtensorMap tmAg_hi, const __grid_constant__ CUtensorMap tmAg_lo,
                       const __grid_constant__ CUtensorMap tmBg_hi, const __grid_constant__ CUtensorMap tmBg_lo,
-                      const TcParams prm, int lanes_l, int n_local_ctas, int grid_g, int stages, int b_tile_bytes) {
+                      const TcParams prm, int lanes_l, int n_local_ctas, int stages, int b_tile_bytes) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr int NOPS = NTERMS == 3 ? 2 : 1;                 // hi (+ lo) copies of each operand
@@ -366,11 +446,11 @@ similarity_tc2_kernel(const __grid_constant__ CUtensorMap tmAl_hi, const __grid_
     uint64_t* empty = bars + kTc2MaxStages;                   // [kTc2MaxStages]
     uint64_t* tmem_full = bars + 2 * kTc2MaxStages;           // [2]
     uint64_t* tmem_empty = tmem_full + 2;                     // [2]
-    uint64_t* a_full = tmem_empty + 2;                        // [1]
-    uint64_t* a_empty = a_full + 1;                           // [1]
+    uint64_t* a_full = tmem_empty + 2;                        // [kTc2MaxKBlocks] one per k-block of the resident tile
+    uint64_t* a_empty = a_full + kTc2MaxKBlocks;              // [1]
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_empty + 1);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cta = blockIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, cta = blockIdx.x, grid = gridDim.x;
 
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tmap(&tmAl_hi);
@@ -380,10 +460,11 @@ similarity_tc2_kernel(const __grid_constant__ CUtensorMap tmAl_hi, const __grid_
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kTc2MaxStages; ++s) { ptx::mbar_init(&full[s], 1); ptx::mbar_init(&empty[s], 1); }
         for (int s = 0; s < 2; ++s) { ptx::mbar_init(&tmem_full[s], 1); ptx::mbar_init(&tmem_empty[s], 4); }
-        ptx::mbar_init(a_full, 1);
+        for (int kb = 0; kb < kTc2MaxKBlocks; ++kb) ptx::mbar_init(&a_full[kb], 1);
         ptx::mbar_init(a_empty, 1);
         ptx::fence_mbar_init();
     }
+    pdl_sync();   // barriers and tensor-map prefetch overlap the previous kernel; TMEM and all global reads wait for it
     if (warp == 2) ptx::tmem_alloc(tmem_ptr, 512);
     ptx::tc_fence_before();
     __syncthreads();
@@ -395,24 +476,26 @@ similarity_tc2_kernel(const __grid_constant__ CUtensorMap tmAl_hi, const __grid_
         int stage = 0;
         uint32_t phase = 0;
         Tc2Job job;
-        for (int p = 0; tc2_phase(prm, cta, p, lanes_l, n_local_ctas, grid_g, job); ++p) {
-            if (lane == 0) {
-                if (p > 0) ptx::mbar_wait(a_empty, (uint32_t)(p - 1) & 1u);      // MMAs of the previous tile set retired
-                ptx::mbar_expect_tx(a_full, (uint32_t)a_bytes);
-                for (int op = 0; op < NOPS; ++op) {
-                    const CUtensorMap* ma = job.is_global ? (op ? &tmAg_lo : &tmAg_hi) : (op ? &tmAl_lo : &tmAl_hi);
-                    for (int kb = 0; kb < kblocks; ++kb)
-                        ptx::tma_load_2d(a_res + (size_t)(op * kblocks + kb) * kTcABytes, ma, a_full, kb * kTcBlockK,
-                                         job.mt * kTcBlockM);
-                }
-            }
+        for (int p = 0; tc2_phase(prm, cta, p, lanes_l, n_local_ctas, grid, job); ++p) {
+            // the resident prototype tile is loaded k-block by k-block, interleaved with the first tile's token
+            // k-blocks, each k-block on its own barrier: the first MMAs start after 1/kblocks of the tile has landed
+            if (lane == 0 && p > 0) ptx::mbar_wait(a_empty, (uint32_t)(p - 1) & 1u);   // MMAs of the previous job retired
             __syncwarp();
             const uint32_t bytes = (uint32_t)NOPS * (uint32_t)(job.is_global ? prm.box_rows_g : prm.box_rows_l) * kTcBlockK * 2;
             for (int t = job.t_begin; t < job.t_end; t += job.t_step) {
-                const int rowB = job.is_global ? t * kTcMaxN : t * prm.G * prm.K;
+                const int rowB = job.is_global ? t * prm.gN : t * prm.G * prm.K;
 #pragma unroll 1
                 for (int kb = 0; kb < kblocks; ++kb) {
                     if (lane == 0) {
+                        if (t == job.t_begin) {
+                            ptx::mbar_expect_tx(&a_full[kb], (uint32_t)(NOPS * kTcABytes));
+                            for (int op = 0; op < NOPS; ++op) {
+                                const CUtensorMap* ma =
+                                    job.is_global ? (op ? &tmAg_lo : &tmAg_hi) : (op ? &tmAl_lo : &tmAl_hi);
+                                ptx::tma_load_2d(a_res + (size_t)(op * kblocks + kb) * kTcABytes, ma, &a_full[kb],
+                                                 kb * kTcBlockK, job.mt * kTcBlockM);
+                            }
+                        }
                         ptx::mbar_wait(&empty[stage], phase ^ 1u);
                         ptx::mbar_expect_tx(&full[stage], bytes);
                         uint8_t* sB = ring + (size_t)stage * stage_bytes;
@@ -435,9 +518,7 @@ similarity_tc2_kernel(const __grid_constant__ CUtensorMap tmAl_hi, const __grid_
         const uint32_t idesc_g = ptx::umma_idesc_bf16(kTcBlockM, prm.umma_n_g);
         const uint32_t a_base = ptx::smem_u32(a_res);
         Tc2Job job;
-        for (int p = 0; tc2_phase(prm, cta, p, lanes_l, n_local_ctas, grid_g, job); ++p) {
-            if (lane == 0) ptx::mbar_wait(a_full, (uint32_t)p & 1u);
-            __syncwarp();
+        for (int p = 0; tc2_phase(prm, cta, p, lanes_l, n_local_ctas, grid, job); ++p) {
             const uint32_t idesc = job.is_global ? idesc_g : idesc_l;
             for (int t = job.t_begin; t < job.t_end; t += job.t_step, ++it) {
                 const int acc = it & 1;
@@ -450,6 +531,7 @@ similarity_tc2_kernel(const __grid_constant__ CUtensorMap tmAl_hi, const __grid_
 #pragma unroll 1
                 for (int kb = 0; kb < kblocks; ++kb) {
                     if (lane == 0) {
+                        if (t == job.t_begin) ptx::mbar_wait(&a_full[kb], (uint32_t)p & 1u);   // resident k-block landed
                         ptx::mbar_wait(&full[stage], phase);
                         ptx::tc_fence_after();
                         const uint32_t b_hi = ptx::smem_u32(ring + (size_t)stage * stage_bytes);
@@ -491,7 +573,7 @@ similarity_tc2_kernel(const __grid_constant__ CUtensorMap tmAl_hi, const __grid_
         const float4* x2v = reinterpret_cast<const float4*>(x2);
         int it = 0;
         Tc2Job job;
-        for (int p = 0; tc2_phase(prm, cta, p, lanes_l, n_local_ctas, grid_g, job); ++p) {
+        for (int p = 0; tc2_phase(prm, cta, p, lanes_l, n_local_ctas, grid, job); ++p) {
             for (int tt = job.t_begin; tt < job.t_end; tt += job.t_step, ++it) {
                 if ((it & 1) != grp_id) continue;
                 TcTile t;
@@ -502,14 +584,14 @@ similarity_tc2_kernel(const __grid_constant__ CUtensorMap tmAl_hi, const __grid_
                     const long r0 = (long)t.grp * prm.G * prm.K, rmax = (long)prm.B * prm.K;
                     for (int c = gtid; c < kTcMaxN; c += 128) x2[c] = (r0 + c < rmax) ? __ldg(prm.z2s + r0 + c) : 0.f;
                 } else {
-                    const int b0 = t.grp * kTcMaxN;
+                    const int b0 = t.grp * prm.gN;
                     for (int c = gtid; c < kTcMaxN; c += 128) x2[c] = (b0 + c < prm.B) ? __ldg(prm.z2c + b0 + c) : 0.f;
                 }
                 named_bar_sync(1 + grp_id, 128);
                 const uint32_t taddr = tmem_base + (uint32_t)grp_id * kTcMaxN + ((uint32_t)(quarter * 32) << 16);
                 ptx::mbar_wait(&tmem_full[grp_id], acc_phase);
                 ptx::tc_fence_after();
-                tc_epilogue_tile<KT>(prm, t, taddr, x2, x2v, quarter, lane);
+                tc_epilogue_tile<KT, EPI>(prm, t, taddr, x2, x2v, quarter, lane);
                 ptx::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) ptx::mbar_arrive(&tmem_empty[grp_id]);
@@ -568,7 +650,7 @@ constexpr int kTcSmemLimit = 232448;     // 227 KB opt-in maximum per CTA on sm_
 
 struct Tc2Plan {
     bool ok;
-    int stages, b_tile_bytes, lanes_l, n_local_ctas, grid_g, grid, smem;
+    int stages, b_tile_bytes, lanes_l, n_local_ctas, grid, smem;
 };
 
 static Tc2Plan plan_tc2(const TcParams& prm, int nterms, int sms) {
@@ -583,31 +665,39 @@ static Tc2Plan plan_tc2(const TcParams& prm, int nterms, int sms) {
     int stages = (kTcSmemLimit - fixed) / stage_bytes;
     if (stages > kTc2MaxStages) stages = kTc2MaxStages;
     pl.stages = stages;
-    pl.ok = stages >= 2;
+    pl.ok = stages >= 2 && kblocks <= kTc2MaxKBlocks;
     pl.smem = fixed + stages * stage_bytes;
-    // one CTA per global prototype tile when they fit beside the local CTAs (each reload of the resident tile costs a
-    // full TMA latency, so serialising several global tiles on one CTA becomes the critical path)
-    pl.grid_g = prm.Pg > 0 ? (prm.MT_g <= sms / 4 ? prm.MT_g : sms / 4) : 0;
-    int lanes = (sms - pl.grid_g) / prm.MT_l;
+    // one CTA per global prototype tile beside the local CTAs (lanes = image-group walkers per prototype tile).
+    // Measured on B200 (profiles/r1b_sim_plan_ab.txt): giving the local walkers all 148 SMs and dealing the global
+    // tiles out as second jobs (9 lanes instead of 8 at the CUB shape) is 1.5-1.7x SLOWER at every batch size, so
+    // the dedicated plan stays; PPH_SIM_SHARED=1 / PPH_SIM_LANES=n select the alternatives for measurements.
+    static const int knob_lanes = [] { const char* e = getenv("PPH_SIM_LANES"); return e ? atoi(e) : 0; }();
+    static const bool knob_shared = [] { const char* e = getenv("PPH_SIM_SHARED"); return e && e[0] == '1'; }();
+    int avail = sms;
+    if (!knob_shared) avail = sms - (prm.MT_g <= sms / 4 ? prm.MT_g : sms / 4);
+    int lanes = avail / prm.MT_l;
+    if (knob_lanes > 0) lanes = knob_lanes;
     if (lanes < 1) lanes = 1;
     if (lanes > prm.NG_l) lanes = prm.NG_l;
     pl.lanes_l = lanes;
     pl.n_local_ctas = prm.MT_l * lanes;
-    pl.grid = pl.n_local_ctas + pl.grid_g;
+    int grid = pl.n_local_ctas + prm.MT_g;
+    if (grid > sms) grid = sms;
+    if (grid < pl.n_local_ctas) grid = pl.n_local_ctas;
+    pl.grid = grid;
     return pl;
 }
 
-template <int NTERMS, int KT>
+template <int NTERMS, int KT, int EPI = 1>
 static int launch_tc2(const CUtensorMap* maps, const TcParams& prm, const Tc2Plan& pl, cudaStream_t st) {
-    auto kern = similarity_tc2_kernel<NTERMS, KT>;
+    auto kern = similarity_tc2_kernel<NTERMS, KT, EPI>;
     static int configured = 0;
     if (configured < pl.smem) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         configured = kTcSmemLimit;
     }
-    kern<<<pl.grid, kTcThreads, pl.smem, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], prm,
-                                               pl.lanes_l, pl.n_local_ctas, pl.grid_g, pl.stages, pl.b_tile_bytes);
+    launch_k(kern, dim3(pl.grid), dim3(kTcThreads), (size_t)(pl.smem), st, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], prm, pl.lanes_l, pl.n_local_ctas, pl.stages, pl.b_tile_bytes);
     return launch_status("pph_similarity_fwd(tcgen05, resident prototypes)");
 }
 
@@ -620,8 +710,7 @@ static int launch_tc(const CUtensorMap* maps, const TcParams& prm, int grid, cud
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         configured = true;
     }
-    kern<<<grid, kTcThreads, kTcSmemBytes, st>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6],
-                                                 maps[7], prm);
+    launch_k(kern, dim3(grid), dim3(kTcThreads), (size_t)(kTcSmemBytes), st, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], prm);
     return launch_status("pph_similarity_fwd(tcgen05)");
 }
 
@@ -647,16 +736,36 @@ int similarity_fwd_tc(int mode, int act_fn, float eps, int B, int K, int D, int 
     prm.MT_l = ceil_div(P, kTcBlockM);
     prm.NG_l = ceil_div(B, prm.G);
     prm.MT_g = Pg > 0 ? ceil_div(Pg, kTcBlockM) : 0;
-    prm.NB_g = Pg > 0 ? ceil_div(B, kTcMaxN) : 0;
     prm.n_local = prm.MT_l * prm.NG_l;
-    prm.n_tiles = prm.n_local + prm.MT_g * prm.NB_g;
     prm.box_rows_l = prm.G * K;
     prm.umma_n_l = ceil_div(prm.box_rows_l, 16) * 16;
-    prm.umma_n_g = ceil_div(B < kTcMaxN ? B : kTcMaxN, 16) * 16;
-    prm.box_rows_g = prm.umma_n_g;
+    auto set_global_chunk = [&](int gN) {            // images per global tile
+        prm.gN = gN;
+        prm.NB_g = Pg > 0 ? ceil_div(B, gN) : 0;
+        prm.n_tiles = prm.n_local + prm.MT_g * prm.NB_g;
+        prm.umma_n_g = ceil_div(B < gN ? B : gN, 16) * 16;
+        prm.box_rows_g = prm.umma_n_g;
+    };
+    set_global_chunk(kTcMaxN);
     prm.act_fn = act_fn; prm.eps = eps;
     prm.z2s = z2s; prm.z2c = z2c; prm.p2l = p2l; prm.p2g = p2g;
     prm.dmin_l = dmin_l; prm.act_l = act_l; prm.dmin_g = dmin_g; prm.act_g = act_g; prm.argmin_l = argmin_l;
+
+    static int sms = 0;
+    if (sms <= 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (sms <= 0) sms = 148;
+    }
+    // resident-prototype kernel (v2) whenever >= 2 token stages fit beside the resident tile; a 256-image global tile
+    // is what breaks that for BF16X3 at D = 192, so large batches chunk the global branch by 128 images instead
+    Tc2Plan pl = plan_tc2(prm, x3 ? 3 : 1, sms);
+    if (!pl.ok && B > 128) {
+        set_global_chunk(128);
+        pl = plan_tc2(prm, x3 ? 3 : 1, sms);
+        if (!pl.ok) set_global_chunk(kTcMaxN);
+    }
 
     CUtensorMap maps[8];
     int rc;
@@ -672,14 +781,6 @@ int similarity_fwd_tc(int mode, int act_fn, float eps, int B, int K, int D, int 
     } else {
         for (int i = 4; i < 8; ++i) maps[i] = maps[i - 4];
     }
-    static int sms = 0;
-    if (sms <= 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
-    const Tc2Plan pl = plan_tc2(prm, x3 ? 3 : 1, sms);
     const int grid = prm.n_tiles < sms ? prm.n_tiles : sms;
     // compile-time token counts: every K of the BASELINE sweep (49..196 squares) gets an epilogue whose image
     // boundaries are static; any other K takes the generic epilogue (KT = 0)
@@ -688,6 +789,10 @@ int similarity_fwd_tc(int mode, int act_fn, float eps, int B, int K, int D, int 
         if (pl.ok) return x3 ? launch_tc2<3, KT>(maps, prm, pl, st) : launch_tc2<1, KT>(maps, prm, pl, st); \
         return x3 ? launch_tc<3, KT>(maps, prm, grid, st) : launch_tc<1, KT>(maps, prm, grid, st);   \
     } while (0)
+    // A/B switch for measurements: PPH_SIM_EPI=0 selects the sequential-scan epilogue (built for K = 81 only)
+    static const bool old_epi = [] { const char* e = getenv("PPH_SIM_EPI"); return e && e[0] == '0'; }();
+    if (old_epi && K == 81 && pl.ok)
+        return x3 ? launch_tc2<3, 81, 0>(maps, prm, pl, st) : launch_tc2<1, 81, 0>(maps, prm, pl, st);
     switch (K) {
         case 49: PPH_TC_DISPATCH(49);
         case 64: PPH_TC_DISPATCH(64);

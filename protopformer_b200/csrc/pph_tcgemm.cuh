@@ -94,6 +94,7 @@ tcgemm_kernel(int M, int N, int Kd, int BN, int k_per_split, AOp a_op, BOp b_op,
         ptx::mbar_init(acc_done, 1);
         ptx::fence_mbar_init();
     }
+    pdl_sync();   // everything below reads global memory or allocates TMEM: wait for the prerequisite grids
     if (warp == 1) ptx::tmem_alloc(tmem_ptr, 256);
     if (tid >= 128 && tid < 256) {
         void* p3[3] = {nullptr, nullptr, nullptr};
@@ -271,7 +272,7 @@ inline int launch_tcgemm(int M, int N, int Kd, int BN, int splits, AOp a, BOp b,
     int k_per_split = ceil_div(ceil_div(Kd, splits), kTgBK) * kTgBK;
     splits = ceil_div(Kd, k_per_split);
     dim3 grid(ceil_div(M, kTgBM), splits);
-    kern<<<grid, kTgThreads, smem, st>>>(M, N, Kd, BN, k_per_split, a, b, e);
+    launch_k(kern, dim3(grid), dim3(kTgThreads), (size_t)(smem), st, M, N, Kd, BN, k_per_split, a, b, e);
     return launch_status(what);
 }
 

@@ -66,6 +66,59 @@ def select_topk(scores: torch.Tensor, K: int, want_int64: bool = False):
 
 
 # ------------------------------------------------------------------------------------------------------------------
+# (next #1) attention rollout -> CLS-row score -- tools/deit_models_attn.py:99-124, :226
+# ------------------------------------------------------------------------------------------------------------------
+FUSIONS = {"mean": 0, "max": 1, "min": 2}
+_rollout_ws: dict = {}
+
+
+def rollout_workspace(L: int, B: int, T: int, k_discard: int, device) -> torch.Tensor:
+    import ctypes
+    n = ctypes.c_longlong(0)
+    if _lib.load().pph_rollout_ws_bytes(L, B, T, k_discard, ctypes.byref(n)) != 0:
+        raise RuntimeError("pph_rollout_ws_bytes failed")
+    return torch.empty(max(int(n.value), 256), dtype=torch.uint8, device=device)
+
+
+def rollout_scores(all_attn, discard_ratio: float = 0.9, head_fusion: str = "mean", identity_w: float = 0.2,
+                   v0: torch.Tensor | None = None, drop_first: bool = True, workspace: torch.Tensor | None = None):
+    """``attn_rollout(all_attn)[:, 0, 1:]`` of the reference (deit_models_attn.py:99-124, :226) without the (T,T)
+    products.  all_attn: list of L fp32 CUDA tensors (B,H,T,T) (the attention maps of the first L blocks);
+    returns the detached score (B, T-1) [(B,T) when drop_first is False].  ``v0`` (B,T): start row instead of e_0
+    (CaiT, cait_models_attn.py:255-259).  The result is not differentiable -- the reference detaches it (:225)."""
+    import ctypes
+    L = len(all_attn)
+    assert L >= 1
+    layers = []
+    for a in all_attn:
+        a = a.detach()
+        if a.dtype != torch.float32:
+            a = a.float()
+        layers.append(a.contiguous())
+    B, H, T, T2 = layers[0].shape
+    assert T == T2 and all(a.shape == layers[0].shape for a in layers), "square (B,H,T,T) maps of one shape expected"
+    k = int(T * T * discard_ratio)                    # deit_models_attn.py:110
+    dev = layers[0].device
+    if workspace is None:
+        key = (L, B, T, k, dev)
+        workspace = _rollout_ws.get(key)
+        if workspace is None:
+            workspace = _rollout_ws[key] = rollout_workspace(L, B, T, k, dev)
+    scores = _empty((B, T - int(drop_first)), torch.float32, layers[0])
+    table = (ctypes.c_void_p * L)(*[_ptr_of(a) for a in layers])
+    if v0 is not None:
+        v0 = v0.detach().float().contiguous()
+    _lib.call("pph_rollout_scores", table, L, B, H, T, k, FUSIONS[head_fusion], float(identity_w), v0,
+              int(drop_first), workspace, scores)
+    return scores
+
+
+def _ptr_of(t: torch.Tensor) -> int:
+    assert t.is_cuda and t.is_contiguous()
+    return t.data_ptr()
+
+
+# ------------------------------------------------------------------------------------------------------------------
 # (a2) gather + add-on layer -- protopformer.py:159-172
 # ------------------------------------------------------------------------------------------------------------------
 class _Addon(torch.autograd.Function):
@@ -376,8 +429,15 @@ class FusedHeadStep:
     (keys Wa, ba, P, Pg -- e.g. views of one flat all-reduce buffer)."""
 
     def __init__(self, cfg: HeadConfig, B, N, Din, D, P, Pg, C, m, device, heads: int = 0, ppc_cov_coe: float = 0.1,
-                 ppc_mean_coe: float = 0.5, train: bool = True, use_ppc: bool = True):
+                 ppc_mean_coe: float = 0.5, train: bool = True, use_ppc: bool = True, schedule: int | None = None):
+        import os
         self.cfg, self.train, self.use_ppc = cfg, train, use_ppc
+        # stream schedule of the training step: 1 (default) = three streams (token bins on their own branch, the
+        # cross-entropy tail does not wait for the PPC loss: the weighted sum is a separate 1-thread kernel on the
+        # side branch, PPC gradient buffer cleared at the start of the step); 0 = the first round-1 schedule, two
+        # streams (PPC loss, token bins and PPC backward in one side chain; the loss tail joins the PPC forward).
+        # Measured (profiles/r1b_ab_variants.txt): 187.6 -> 171.8 us per step at the CUB shape, B = 64.
+        self.schedule = int(os.environ.get("PPH_SCHEDULE", "1")) if schedule is None else int(schedule)
         self.dims = (B, N, Din, D, P, Pg, C, m, heads)
         self.cov_coe, self.mean_coe = float(ppc_cov_coe), float(ppc_mean_coe)
         K = cfg.K
@@ -403,6 +463,7 @@ class FusedHeadStep:
         self.dslice, self.stats, self.ppc_partial = e(B, m, K), e(B, m, 8), e(B, 2)
         self.ppc_counter, self.ppc_losses = z(1, dt=i32), z(2)
         self.ce_partial, self.ce_counter, self.losses = e(B), z(1, dt=i32), z(4)
+        self.losses_ce = z(4)
         if train:
             self.dlogits, self.g_l, self.g_g = e(B, C), e(B, P), e(B, Pg)
             self.dZs, self.dZc = e(B, K, D), e(B, D)
@@ -412,17 +473,21 @@ class FusedHeadStep:
             self.ws_addon = addon_bwd_workspace(B, N, Din, D, K, device)
         # independent kernels run on a forked stream (under CUDA-graph capture this becomes a parallel branch)
         self.side = torch.cuda.Stream(device=device)
-        self.ev = [torch.cuda.Event() for _ in range(7)]
+        self.side2 = torch.cuda.Stream(device=device)
+        self.ev = [torch.cuda.Event() for _ in range(10)]
 
     def step(self, tokens, scores, labels, Wa, ba, P, Pg, Wl, Wg, grads=None, upstream: float = 1.0):
         B, N, Din, D, Pn, Pgn, C, m, H = self.dims
         cfg, K = self.cfg, self.cfg.K
         c = _lib.call
         main, side, ev = torch.cuda.current_stream(), self.side, self.ev
+        sched1 = self.schedule == 1 and self.use_ppc and self.train
         # branch: prototype operand preparation || selection + add-on
         ev[0].record(main)
         side.wait_event(ev[0])
         with torch.cuda.stream(side):
+            if sched1:
+                self.dP_ppc.zero_()
             c("pph_split_rows", P, Pn, D, float(cfg.center), self.P_hi, self.P_lo, self.p2, self.p2_ctr, self.p2_hi)
             c("pph_split_rows", Pg, Pgn, D, float(cfg.center), self.Pg_hi, self.Pg_lo, self.pg2, self.pg2_ctr, self.pg2_hi)
             ev[1].record(side)
@@ -440,6 +505,13 @@ class FusedHeadStep:
           (self.p2, self.p2_ctr, self.p2_hi)[sel], (self.pg2, self.pg2_ctr, self.pg2_hi)[sel],
           self.P_hi, self.P_lo, self.Pg_hi, self.Pg_lo,
           self.dmin_l, self.argmin, self.act_l, self.dmin_g, self.act_g, None, None)
+
+        def ppc_bwd_side():
+            c("pph_ppc_bwd", self.Zs, P, self.idx32, labels, self.dslice, self.stats, None,
+              self.cov_coe * float(upstream), self.mean_coe * float(upstream), B, K, D, Pn, m, N, cfg.act_id,
+              float(cfg.eps), float(cfg.ppc_cov_thresh), float(cfg.ppc_mean_thresh), 0, self.dZs_ppc,
+              self.dP_ppc)
+
         if ppc:   # branch: PPC loss || last layers (forked after the persistent similarity kernel so it cannot delay it)
             ev[2].record(main)
             side.wait_event(ev[2])
@@ -448,30 +520,46 @@ class FusedHeadStep:
                   float(cfg.eps), float(cfg.ppc_cov_thresh), float(cfg.ppc_mean_thresh), self.dslice, self.stats,
                   self.ppc_partial, self.ppc_counter, self.ppc_losses)
                 ev[3].record(side)
-                if self.train:   # the token bins of the backward only need argmin: off the critical path
+                if sched1:
+                    ppc_bwd_side()
+                elif self.train:   # the token bins of the backward only need argmin: off the critical path
                     c("pph_similarity_bwd", None, None, self.argmin, None, None, None, None, B, K, D, Pn, Pgn, self.ws,
                       1, None, None, None, None, None, None)
                     # ... and the PPC backward only needs the PPC forward: its contributions go to side buffers that
                     # the gradient kernel adds while it writes dZs / dP
                     self.dP_ppc.zero_()
-                    c("pph_ppc_bwd", self.Zs, P, self.idx32, labels, self.dslice, self.stats, None,
-                      self.cov_coe * float(upstream), self.mean_coe * float(upstream), B, K, D, Pn, m, N, cfg.act_id,
-                      float(cfg.eps), float(cfg.ppc_cov_thresh), float(cfg.ppc_mean_thresh), 0, self.dZs_ppc,
-                      self.dP_ppc)
+                    ppc_bwd_side()
                     ev[4].record(side)
+            if sched1:   # token bins on a third branch
+                self.side2.wait_event(ev[2])
+                with torch.cuda.stream(self.side2):
+                    c("pph_similarity_bwd", None, None, self.argmin, None, None, None, None, B, K, D, Pn, Pgn, self.ws,
+                      1, None, None, None, None, None, None)
+                    ev[7].record(self.side2)
         c("pph_logits_fwd", self.act_l, self.act_g, Wl, Wg, B, Pn, Pgn, C, float(cfg.global_coe), self.logits,
           self.logits_g, self.logits_l)
-        if ppc:
-            main.wait_event(ev[3])
-        c("pph_loss_tail", self.logits, labels, self.ppc_losses if ppc else None, self.cov_coe, self.mean_coe,
-          float(upstream), B, C, self.ce_partial, self.ce_counter, self.losses, self.dlogits if self.train else None)
+        if sched1:
+            c("pph_loss_tail", self.logits, labels, None, self.cov_coe, self.mean_coe, float(upstream), B, C,
+              self.ce_partial, self.ce_counter, self.losses_ce, self.dlogits)
+            ev[8].record(main)
+            side.wait_event(ev[8])
+            with torch.cuda.stream(side):
+                c("pph_loss_combine", self.losses_ce, self.ppc_losses, self.cov_coe, self.mean_coe, self.losses)
+                ev[4].record(side)
+        else:
+            if ppc:
+                main.wait_event(ev[3])
+            c("pph_loss_tail", self.logits, labels, self.ppc_losses if ppc else None, self.cov_coe, self.mean_coe,
+              float(upstream), B, C, self.ce_partial, self.ce_counter, self.losses, self.dlogits if self.train else None)
         if not self.train:
             return self.losses
         c("pph_logits_bwd", self.dlogits, None, None, Wl, Wg, self.dmin_l, self.dmin_g, B, Pn, Pgn, C,
           float(cfg.global_coe), cfg.act_id, float(cfg.eps), self.g_l, self.g_g)
-        binned = ppc                                   # bins were produced on the side stream next to the PPC loss
+        binned = ppc                                   # bins were produced on a side stream next to the PPC loss
         if binned:
             main.wait_event(ev[4])
+            if sched1:
+                main.wait_event(ev[7])
         c("pph_similarity_bwd", self.g_l, self.g_g, self.argmin, self.Zs, self.Zc, P, Pg, B, K, D, Pn, Pgn, self.ws,
           2 if binned else 3, self.dZs_ppc if ppc else None, self.dP_ppc if ppc else None,
           self.dZs, self.dZc, grads["P"], grads["Pg"])

@@ -34,6 +34,8 @@ def graph_time(fn, rep=20, outer=10):
 rows = []
 cfgs = [(64, 81, 2000, 192), (256, 81, 2000, 192), (1024, 81, 2000, 192), (32, 49, 1000, 192), (256, 121, 2000, 192),
         (256, 196, 4000, 192), (128, 81, 8000, 192), (256, 81, 1200, 384), (1024, 196, 8000, 192), (512, 144, 4000, 384)]
+if len(sys.argv) > 1:      # e.g. "64,81,2000,192;1024,81,2000,192"
+    cfgs = [tuple(int(x) for x in c.split(",")) for c in sys.argv[1].split(";")]
 for B, K, P, D in cfgs:
     s = synth.HeadShape(f"B{B}K{K}P{P}D{D}", B, 196, D, D, K, P, P, P // 10)
     g = torch.Generator(device="cpu").manual_seed(0)

@@ -12,7 +12,7 @@ from tests.util import GOLDEN_CASES, load_golden, norm_rel, rel_close
 pytestmark = pytest.mark.gpu
 
 
-def _make(shape, case, mode, n_slots=1, train=True, fused=True):
+def _make(shape, case, mode, n_slots=1, train=True, fused=True, schedule=None):
     from protopformer_b200 import ops
     from protopformer_b200.graph import GraphedHeadStep
     dev = torch.device("cuda:0")
@@ -22,7 +22,7 @@ def _make(shape, case, mode, n_slots=1, train=True, fused=True):
     cfg = ops.HeadConfig(K=shape.K, global_coe=shape.global_coe, mode=mode, ppc_cov_thresh=shape.ppc_cov_thresh,
                          ppc_mean_thresh=shape.ppc_mean_thresh)
     step = GraphedHeadStep(params, cfg, B=shape.B, N=shape.N, C=shape.C, m=shape.m, n_slots=n_slots, train=train,
-                           fused=fused)
+                           fused=fused, schedule=schedule)
     for i in range(n_slots):
         step.load(i, case["tokens"], case["scores"], case["labels"])
     torch.cuda.synchronize()
@@ -33,9 +33,10 @@ def _make(shape, case, mode, n_slots=1, train=True, fused=True):
 @pytest.mark.parametrize("name,mode", [("cub_b8_s1", "fp32"), ("cub_b8_s1", "bf16"), ("cars_b4_s1", "fp32"),
                                        ("dogs_b4_s1", "fp32"), ("small_s1", "fp32_fma"), ("tiny_s1", "fp32_fma"),
                                        ("cub_b8_s2_matched", "fp32")])
-def test_fused_graphed_step_matches_reference(name, mode):
+@pytest.mark.parametrize("schedule", [0, 1])
+def test_fused_graphed_step_matches_reference(name, mode, schedule):
     shape, case, g, fn = load_golden(name)
-    step, params = _make(shape, case, mode)
+    step, params = _make(shape, case, mode, schedule=schedule)
     step.run(0)
     step.run(0)                      # replay twice: counters / accumulate buffers must self-reset
     torch.cuda.synchronize()
@@ -77,6 +78,23 @@ def test_fused_step_is_bit_reproducible_and_matches_modular_path():
     for k in ("P", "Pg", "Wa", "ba"):
         assert norm_rel(mparams[k].grad.cpu(), params[k].grad.cpu()) < 1e-4, k
     assert norm_rel(mod.dtokens[0].cpu(), dta.cpu()) < 1e-4
+
+
+def test_stream_schedules_agree_bitwise():
+    """schedule 1 (three streams, cross-entropy tail decoupled from the PPC loss) computes exactly what schedule 0 does."""
+    shape = synth.SHAPES["cub_b64"]
+    case = synth.make_case(shape, seed=6)
+    s0, p0 = _make(shape, case, "fp32", schedule=0)
+    s1, p1 = _make(shape, case, "fp32", schedule=1)
+    for s in (s0, s1):
+        s.run(0)
+        s.run(0)
+    torch.cuda.synchronize()
+    assert torch.equal(s0.fused.losses, s1.fused.losses)
+    assert torch.equal(s0.fused.dtokens, s1.fused.dtokens)
+    assert torch.equal(p0["Pg"].grad, p1["Pg"].grad)
+    assert norm_rel(p0["P"].grad, p1["P"].grad) < 1e-6          # PPC rows of shared labels are atomics
+    assert norm_rel(p0["Wa"].grad, p1["Wa"].grad) < 1e-6
 
 
 def test_fused_eval_step():

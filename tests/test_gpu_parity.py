@@ -276,7 +276,10 @@ def test_full_size_properties(key, B):
 
 
 @pytest.mark.parametrize("K,P,D,B", [(49, 1000, 192, 32), (64, 1000, 384, 9), (100, 2000, 192, 17),
-                                     (144, 1000, 192, 6), (169, 1000, 64, 4), (196, 8000, 192, 3)])
+                                     (144, 1000, 192, 6), (169, 1000, 64, 4), (196, 8000, 192, 3),
+                                     (36, 1000, 64, 10),        # token count without a static epilogue (generic K)
+                                     (81, 2000, 192, 300),      # 128-image global chunks, ragged last chunk and group
+                                     (81, 300, 128, 150)])      # more SMs than tiles: lanes clamp, idle CTAs
 def test_sweep_shapes_tensor_core_vs_cuda_core(K, P, D, B):
     """BASELINE config 5 (head-only sweep) corners: generic-K epilogue, ragged image groups, partial prototype tiles."""
     shape = synth.HeadShape("sweep", B, 196, D, D, K, P, P // 10 * 5, P // 10)
