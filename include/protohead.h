@@ -203,6 +203,20 @@ int pph_rollout_scores(const float* const* attn_layers /* host array of device p
                        int k_discard, int head_fusion, float identity_w, const float* v0, int drop_first,
                        void* workspace, float* scores, pph_stream_t stream);
 
+/* (next #3, optimizer tail) torch.optim.AdamW as the reference builds it for the head's parameter groups
+ * (tools/create_optimizer.py:31-39, :92; engine_proto.py:76-78), all tensors in ONE launch:
+ *   p *= 1 - lr*wd;  m += (1-b1)(g - m);  v = b2 v + (1-b2) g g;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
+ * n_seg <= 8 tensors: params / grads / exp_avg / exp_avg_sq are HOST arrays of DEVICE pointers (fp32, numel[i] elements,
+ * copied into the kernel arguments); group[i] (host) selects the tensor's row of hyper.
+ * hyper: DEVICE [8][2] = (lr, weight_decay) per parameter group -- device memory so that a CUDA graph holding this
+ * launch follows the lr schedule.  step_state: DEVICE int[2] = {t, ticket}: t = updates done so far (0 before the
+ * first call), incremented by the kernel; ticket must be 0.  grads are multiplied by grad_scale first (loss scaling /
+ * sum-reduced gradients). */
+int pph_adamw_step(int n_seg, float* const* params, const float* const* grads, float* const* exp_avg,
+                   float* const* exp_avg_sq, const long long* numel /* host */, const int* group /* host */,
+                   const float* hyper, double beta1, double beta2, float eps, float grad_scale,
+                   int* step_state, pph_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
