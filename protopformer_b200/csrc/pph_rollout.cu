@@ -17,6 +17,7 @@
 //    for l = L-1 .. 0: v <- v @ a_l as a gather over the columns' entry lists (one warp per column, fixed summation
 //    order -> bit-reproducible); scores[b, :] = v[1:] (or all of v).
 #include <math.h>
+#include <stdlib.h>
 
 #include "pph_common.cuh"
 
@@ -297,6 +298,223 @@ rollout_chain_kernel(int L, int B, int T, int cap, const int32_t* __restrict__ c
     for (int j = tid; j < W; j += kRoChainThreads) scores[(size_t)b * W + j] = v[cur][j + drop_first];
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// v2 (default).  ncu on v1 (profiles/r1b_ncu_rollout_v1.txt): 449 us for 328 MB = 9 % of HBM, 13 k instructions per
+// warp per tile, ADU (vote / match / shared atomics) and XU (IEEE divisions) pipes busiest -- instruction bound, not
+// memory bound.  Changes:
+//   * radix select in 3 passes of 11/11/10 bits with plain shared-memory atomics on a 2048-bin histogram: the
+//     8-bit first digit of v1 put ~40 % of all entries into ONE bin (same exponent), so its warp-aggregated atomics
+//     still serialised on one address; with 11 bits the hottest bin holds a few percent and no vote / match is needed;
+//   * zero entries (90 % after the discard) skip both divisions of the normalisation;
+//   * the chain kernel stages each layer's sparse matrix in shared memory with coalesced loads and walks one column
+//     per THREAD (independent sequential sums) instead of one dependent global-load chain per warp and column.
+// Results are bit-identical to v1 (same arithmetic, same summation order per column is NOT kept: v1 summed a column
+// lane-strided then by shuffle tree, v2 sums it in row order; both are fixed orders -> each version is reproducible).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kRo2Bins = 2048;
+
+template <int HT>
+__global__ void __launch_bounds__(kRoThreads, 1)
+rollout_prepare2_kernel(const RoLayers layers, int L, int B, int H, int T, int k_discard, int head_fusion,
+                        float identity_w, int cap, int32_t* __restrict__ col_ptr, float* __restrict__ ent_val,
+                        uint16_t* __restrict__ ent_row) {
+    pdl_sync();
+    extern __shared__ __align__(16) uint8_t ro_smem[];
+    const int n = T * T;
+    float* M = reinterpret_cast<float*>(ro_smem);                            // [T*T]
+    uint32_t* hist = reinterpret_cast<uint32_t*>(M + ((n + 3) & ~3));        // [2048]
+    int* cnt = reinterpret_cast<int*>(hist + kRo2Bins);                      // [1024]
+    int* wsum = cnt + kRoThreads;                                            // [33]
+    __shared__ uint32_t s_prefix, s_cnt;
+    __shared__ int s_krem;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int Hh = HT > 0 ? HT : H;
+    const int seg = min(5, kRoThreads / T);
+    const int rps = (T + seg - 1) / seg;
+
+    for (int tile = blockIdx.x; tile < L * B; tile += gridDim.x) {
+        const int l = tile / B, b = tile - l * B;
+        // ---- 1. stream + fuse the head maps (as v1) ----
+        const float* A = layers.p[l] + (size_t)b * Hh * n;
+        for (int e0 = 0; e0 < n; e0 += 8 * kRoThreads) {
+            float s[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int e = e0 + i * kRoThreads + tid;
+                s[i] = e < n ? __ldcs(A + e) : 0.0f;
+            }
+#pragma unroll
+            for (int h = 1; h < Hh; ++h) {
+                float t[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int e = e0 + i * kRoThreads + tid;
+                    t[i] = e < n ? __ldcs(A + (size_t)h * n + e) : 0.0f;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    s[i] = head_fusion == 0 ? s[i] + t[i] : head_fusion == 1 ? fmaxf(s[i], t[i]) : fminf(s[i], t[i]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int e = e0 + i * kRoThreads + tid;
+                if (e < n) M[e] = head_fusion == 0 ? s[i] / (float)Hh : s[i];
+            }
+        }
+        __syncthreads();
+
+        // ---- 2. exact k-th smallest: radix select, digits of 11 / 11 / 10 bits, MSB first ----
+        uint32_t prefix = 0, eq_total = 0;
+        int krem = k_discard < n ? k_discard : n;
+        if (krem > 0) {
+#pragma unroll 1
+            for (int pass = 0; pass < 3; ++pass) {
+                const int shift = pass == 0 ? 21 : pass == 1 ? 10 : 0;
+                const uint32_t dmask = pass == 2 ? 0x3FFu : 0x7FFu;
+                const uint32_t himask = pass == 0 ? 0u : pass == 1 ? 0xFFE00000u : 0xFFFFFC00u;
+                hist[tid] = 0;
+                hist[tid + kRoThreads] = 0;
+                __syncthreads();
+                for (int e = tid; e < n; e += kRoThreads) {
+                    const uint32_t key = ro_key(M[e]);
+                    if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & dmask], 1u);
+                }
+                __syncthreads();
+                // bin holding the krem-th active entry: thread = 2 consecutive bins, exclusive scan over the CTA
+                const uint32_t c0 = hist[2 * tid], c1 = hist[2 * tid + 1];
+                int total;
+                const int excl = block_excl_scan((int)(c0 + c1), wsum, total);
+                if (excl < krem && krem <= excl + (int)(c0 + c1)) {            // exactly one thread
+                    const bool first = krem <= excl + (int)c0;
+                    s_prefix = prefix | ((uint32_t)(2 * tid + (first ? 0 : 1)) << shift);
+                    s_krem = first ? krem - excl : krem - excl - (int)c0;
+                    s_cnt = first ? c0 : c1;
+                }
+                __syncthreads();
+                prefix = s_prefix;
+                krem = s_krem;
+                eq_total = s_cnt;
+                __syncthreads();
+            }
+            // ---- 3. discard ----
+            const bool all_equal_go = (uint32_t)krem == eq_total;
+            for (int e = tid; e < n; e += kRoThreads) {
+                const uint32_t key = ro_key(M[e]);
+                if (key < prefix || (all_equal_go && key == prefix)) M[e] = 0.0f;
+            }
+            __syncthreads();
+            if (!all_equal_go && warp == 0) {                                   // rare: a tie straddles the threshold
+                int seen = 0;
+                for (int e0 = 0; e0 < n && seen < krem; e0 += 32) {
+                    const int e = e0 + lane;
+                    const bool eq = e < n && ro_key(M[e]) == prefix;
+                    const unsigned m = __ballot_sync(0xffffffffu, eq);
+                    if (eq && seen + __popc(m & ((1u << lane) - 1u)) < krem) M[e] = 0.0f;
+                    seen += __popc(m);
+                }
+            }
+            __syncthreads();
+        }
+
+        // ---- 4. a = (A + w I) / (1 + w), rows normalised; zero off-diagonal entries stay zero without arithmetic ----
+        const float den = 1.0f + identity_w;
+        for (int r = warp; r < T; r += kRoThreads / 32) {
+            float* row = M + r * T;
+            float s = 0.f;
+            for (int j = lane; j < T; j += 32) {
+                const float x = row[j];
+                if (x != 0.0f || j == r) {
+                    const float a = (x + (j == r ? identity_w : 0.0f)) / den;
+                    row[j] = a;
+                    s += a;
+                }
+            }
+            s = warp_sum(s);
+            for (int j = lane; j < T; j += 32) {
+                const float a = row[j];
+                if (a != 0.0f) row[j] = a / s;
+            }
+        }
+        __syncthreads();
+
+        // ---- 5. column-compressed sparse output (as v1) ----
+        const bool worker = tid < seg * T;
+        const int sg = tid / T, j = tid - sg * T;
+        const int r0 = sg * rps, r1 = min(T, r0 + rps);
+        int mine = 0;
+        if (worker)
+            for (int r = r0; r < r1; ++r) mine += (M[r * T + j] != 0.0f);
+        cnt[tid] = 0;
+        __syncthreads();
+        if (worker) cnt[j * seg + sg] = mine;
+        __syncthreads();
+        int total;
+        const int excl = block_excl_scan(cnt[tid], wsum, total);
+        cnt[tid] = excl;
+        __syncthreads();
+        int32_t* cp = col_ptr + (size_t)tile * (T + 1);
+        if (worker) {
+            int o = cnt[j * seg + sg];
+            if (sg == 0) cp[j] = o;
+            float* ev = ent_val + (size_t)tile * cap;
+            uint16_t* er = ent_row + (size_t)tile * cap;
+            for (int r = r0; r < r1; ++r) {
+                const float a = M[r * T + j];
+                if (a != 0.0f && o < cap) {
+                    ev[o] = a;
+                    er[o] = (uint16_t)r;
+                    ++o;
+                }
+            }
+        }
+        if (tid == 0) cp[T] = total < cap ? total : cap;
+        __syncthreads();
+    }
+}
+
+// chain, v2: the layer's sparse matrix is staged in shared memory (coalesced), then thread = column.
+__global__ void __launch_bounds__(kRoChainThreads)
+rollout_chain2_kernel(int L, int B, int T, int cap, const int32_t* __restrict__ col_ptr,
+                      const float* __restrict__ ent_val, const uint16_t* __restrict__ ent_row,
+                      const float* __restrict__ v0, int drop_first, float* __restrict__ scores) {
+    pdl_sync();
+    extern __shared__ __align__(16) uint8_t ch_smem[];
+    float* sval = reinterpret_cast<float*>(ch_smem);                          // [cap]
+    int* scp = reinterpret_cast<int*>(sval + cap);                            // [T+1]
+    uint16_t* srow = reinterpret_cast<uint16_t*>(scp + T + 1);                // [cap]
+    __shared__ float v[2][kRoMaxT];
+    const int b = blockIdx.x, tid = threadIdx.x;
+    for (int j = tid; j < T; j += kRoChainThreads) v[0][j] = v0 ? v0[(size_t)b * T + j] : (j == 0 ? 1.0f : 0.0f);
+    int cur = 0;
+    for (int l = L - 1; l >= 0; --l) {
+        const size_t tile = (size_t)l * B + b;
+        const int32_t* cp = col_ptr + tile * (T + 1);
+        const float* ev = ent_val + tile * cap;
+        const uint16_t* er = ent_row + tile * cap;
+        __syncthreads();                                  // previous layer's readers are done with the stage
+        for (int j = tid; j <= T; j += kRoChainThreads) scp[j] = cp[j];
+        __syncthreads();
+        const int total = scp[T];
+        for (int e = tid; e < total; e += kRoChainThreads) {
+            sval[e] = ev[e];
+            srow[e] = er[e];
+        }
+        __syncthreads();
+        for (int j = tid; j < T; j += kRoChainThreads) {
+            const int beg = scp[j], end = scp[j + 1];
+            float s = 0.f;
+            for (int e = beg; e < end; ++e) s = fmaf(v[cur][srow[e]], sval[e], s);
+            v[cur ^ 1][j] = s;
+        }
+        cur ^= 1;
+    }
+    __syncthreads();
+    const int W = T - drop_first;
+    for (int j = tid; j < W; j += kRoChainThreads) scores[(size_t)b * W + j] = v[cur][j + drop_first];
+}
+
 }  // namespace pph
 
 extern "C" int pph_rollout_ws_bytes(int L, int B, int T, int k_discard, long long* bytes) {
@@ -324,7 +542,12 @@ extern "C" int pph_rollout_scores(const float* const* attn_layers, int L, int B,
     for (int l = 0; l < L; ++l) PPH_REQUIRE(layers.p[l], PPH_EINVAL, "pph_rollout_scores: layer %d is null", l);
     const RoWorkspace w = rollout_carve(workspace, L, B, T, k_discard);
     const int n = T * T;
-    const size_t smem = (size_t)((n + 3) & ~3) * 4 + 256 * 4 + (kRoThreads + 40) * 4;
+    // PPH_ROLLOUT=1 selects the first version of both kernels (kept for A/B measurements)
+    static const bool use_v1 = [] { const char* e = getenv("PPH_ROLLOUT"); return e && e[0] == '1'; }();
+    const size_t smem1 = (size_t)((n + 3) & ~3) * 4 + 256 * 4 + (kRoThreads + 40) * 4;
+    const size_t smem2 = (size_t)((n + 3) & ~3) * 4 + kRo2Bins * 4 + (kRoThreads + 40) * 4;
+    const bool v1 = use_v1 || smem2 > 220 * 1024;
+    const size_t smem = v1 ? smem1 : smem2;
     static int sms = 0;
     if (sms <= 0) {
         int dev = 0;
@@ -343,10 +566,25 @@ extern "C" int pph_rollout_scores(const float* const* attn_layers, int L, int B,
         return launch_status("pph_rollout_scores(prepare)");
     };
     // head counts of the reference's backbones: DeiT-Ti 3, CaiT-XXS 4, DeiT-S 6 (deit_models_attn.py:288,303)
-    int rc = H == 3 ? go(rollout_prepare_kernel<3>) : H == 4 ? go(rollout_prepare_kernel<4>)
+    int rc;
+    if (v1)
+        rc = H == 3 ? go(rollout_prepare_kernel<3>) : H == 4 ? go(rollout_prepare_kernel<4>)
              : H == 6 ? go(rollout_prepare_kernel<6>) : go(rollout_prepare_kernel<0>);
+    else
+        rc = H == 3 ? go(rollout_prepare2_kernel<3>) : H == 4 ? go(rollout_prepare2_kernel<4>)
+             : H == 6 ? go(rollout_prepare2_kernel<6>) : go(rollout_prepare2_kernel<0>);
     if (rc) return rc;
-    launch_k(rollout_chain_kernel, dim3(B), dim3(kRoChainThreads), (size_t)0, st, L, B, T, w.cap, w.col_ptr, w.ent_val,
-             w.ent_row, v0, drop_first, scores);
+    // staged chain needs the layer's entry list in shared memory (cap * 6 B): small discard ratios fall back to v1
+    const size_t csmem = (size_t)w.cap * 4 + (size_t)(T + 1) * 4 + (size_t)w.cap * 2 + 16;
+    if (!use_v1 && csmem <= 160 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(rollout_chain2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             160 * 1024);
+        if (e != cudaSuccess) { set_error("pph_rollout_scores: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        launch_k(rollout_chain2_kernel, dim3(B), dim3(kRoChainThreads), csmem, st, L, B, T, w.cap, w.col_ptr, w.ent_val,
+                 w.ent_row, v0, drop_first, scores);
+    } else {
+        launch_k(rollout_chain_kernel, dim3(B), dim3(kRoChainThreads), (size_t)0, st, L, B, T, w.cap, w.col_ptr,
+                 w.ent_val, w.ent_row, v0, drop_first, scores);
+    }
     return launch_status("pph_rollout_scores(chain)");
 }
