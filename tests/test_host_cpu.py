@@ -114,13 +114,16 @@ def test_flat_gradient_allreduce_gloo_world2():
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + os.getpid() % 2000
+    import socket
+    with socket.socket() as sk:            # a port the kernel just handed out: no clash with a lingering listener
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
     procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    res = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda t: t[0])
     for p in procs:
-        p.join(timeout=60)
+        p.join(timeout=120)
         assert p.exitcode == 0
     (_, lo0, hi0, gP0, gW0), (_, lo1, hi1, gP1, gW1) = res
     assert (lo0, hi0, lo1, hi1) == (0, 5, 5, 10)
