@@ -217,6 +217,23 @@ int pph_adamw_step(int n_seg, float* const* params, const float* const* grads, f
                    const float* hyper, double beta1, double beta2, float eps, float grad_scale,
                    int* step_state, pph_stream_t stream);
 
+/* CaiT start row for pph_rollout_scores (tools/cait_models_attn.py:223-259): the n_cls class-attention maps
+ * cls_layers[c] = [B,H,1,Tc] (host array of device pointers) are fused over heads, their k_discard = int(Tc*ratio)
+ * smallest entries zeroed (ties: lowest index first), identity_w added on the CLS column (`I[:1]`), rows normalised;
+ * v0 [B, Tc-1] = mean over the n_cls rows without the CLS column.  Then
+ * pph_rollout_scores(patch_layers, ..., T = Tc-1, v0, drop_first = 0) = `cls_attn_ma[:, 0]` (cait_models_attn.py:328-330). */
+int pph_rollout_cls_rows(const float* const* cls_layers /* host array of device pointers */, int n_cls, int B, int H,
+                         int Tc, int k_discard, int head_fusion, float identity_w, float* v0, pph_stream_t stream);
+
+/* (next #4, consumers of the materialised map) eval_interpretability.py:195-225 / main_visualize.py:343-388:
+ * activation maps of the m prototypes of each image's label on the ORIGINAL side x side token grid, zeros on pruned
+ * tokens: maps[b, q, idx32[b,k]] = act(relu(z2s[b,k] + (p2l[p] - 2 Zs[b,k].Pl[p]))), p = labels[b]*m + q.
+ * Zs [B,K,D], z2s [B,K] (= |Zs|^2, from pph_addon_fwd), Pl [P,D], p2l [P] (from pph_split_rows), labels [B] int64,
+ * maps [B,m,N] fully OVERWRITTEN.  The (B,P,K) map is never formed. */
+int pph_class_maps(const float* Zs, const float* z2s, const float* Pl, const float* p2l,
+                   const int32_t* idx32, const int64_t* labels, int B, int K, int D, int P, int m, int N,
+                   int act_fn, float eps, float* maps, pph_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -117,6 +117,17 @@ def logits_from_activations(act_l, act_g, Wl, Wg, global_coe: float):
     return global_coe * lg + (1.0 - global_coe) * ll, lg, ll
 
 
+def class_activation_maps(act_map: torch.Tensor, idx: torch.Tensor, labels: torch.Tensor, m: int, N: int):
+    """eval_interpretability.py:195-225: gather the m prototypes of each image's label from the (B,P,K) activation map
+    (:198-202) and scatter the K reserved-token activations to the grid of all N tokens (:218-223) -> (B,m,N)."""
+    B, _, K = act_map.shape
+    rows = labels[:, None] * m + torch.arange(m)[None, :]
+    sel = torch.gather(act_map, 1, rows[:, :, None].expand(-1, -1, K))
+    out = torch.zeros(B, m, N, dtype=act_map.dtype)
+    out.scatter_(2, idx[:, None, :].expand(-1, m, -1), sel)
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # a7: PPC loss  (protopformer.py:249-288)
 # ----------------------------------------------------------------------------------------------------------------

@@ -109,3 +109,25 @@ def threshold_tie_free(all_attn, discard_ratio: float = 0.9, head_fusion: str = 
         if bool((s[:, k - 1] == s[:, k]).any()):
             return False
     return True
+
+
+def rollout_cait(all_attn, pre_layer_num: int, discard_ratio: float = 0.9, head_fusion: str = "mean") -> torch.Tensor:
+    """tools/cait_models_attn.py:223-261 as written: every map is processed (:225-246), the first ``pre_layer_num``
+    form the (T,T) product (:251-253), the mean of the remaining class-attention rows without the CLS column (:255-257)
+    multiplies it (:258); returns ``cls_result[:, 0]`` (B,T) -- what :328-330 feed the token selection."""
+    proc = [process_layer(a, discard_ratio, head_fusion) for a in all_attn]
+    patch, cls = proc[:pre_layer_num], proc[pre_layer_num:]
+    B, T = patch[0].shape[0], patch[0].shape[-1]
+    result = torch.eye(T, dtype=patch[0].dtype).unsqueeze(0).repeat(B, 1, 1)
+    for a in patch:
+        result = torch.matmul(a, result)
+    cls_result = torch.cat(cls, dim=1).mean(dim=1, keepdim=True)[:, :, 1:]
+    return (cls_result @ result)[:, 0]
+
+
+def synth_cait_attention(n_patch: int, n_cls: int, B: int, H: int, T: int, seed: int = 1, sharp: float = 2.0):
+    """n_patch maps (B,H,T,T) followed by n_cls class-attention maps (B,H,1,T+1)."""
+    g = torch.Generator().manual_seed(5000 + seed)
+    maps = [torch.softmax(sharp * torch.randn(B, H, T, T, generator=g), dim=-1) for _ in range(n_patch)]
+    maps += [torch.softmax(sharp * torch.randn(B, H, 1, T + 1, generator=g), dim=-1) for _ in range(n_cls)]
+    return maps

@@ -40,6 +40,8 @@ SIGNATURES = {
     "pph_rollout_ws_bytes": [_i, _i, _i, _i, C.POINTER(C.c_longlong)],
     "pph_rollout_scores": [_p, _i, _i, _i, _i, _i, _i, _f, _p, _i, _p, _p, _p],
     "pph_adamw_step": [_i, _p, _p, _p, _p, _p, _p, _p, C.c_double, C.c_double, _f, _f, _p, _p],
+    "pph_rollout_cls_rows": [_p, _i, _i, _i, _i, _i, _i, _f, _p, _p],
+    "pph_class_maps": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p],
     "pph_addon_bwd_ws_bytes": [_i, _i, _i, _i, _i, C.POINTER(C.c_longlong)],
     "pph_addon_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p],
 }
@@ -48,7 +50,7 @@ _RESTYPES = {"pph_last_error_string": C.c_char_p}
 # kernels launched per entry-point call (memset nodes are not counted); used for the bench's `gpu_launches` claim
 KERNELS_PER_CALL = {
     "pph_select_topk": 1, "pph_addon_fwd": 1, "pph_split_rows": 1, "pph_logits_fwd": 1, "pph_ppc_fwd": 1,
-    "pph_ppc_bwd": 1, "pph_logits_bwd": 1, "pph_similarity_bwd": 2, "pph_addon_bwd": 3, "pph_loss_tail": 1, "pph_loss_combine": 1, "pph_rollout_scores": 2, "pph_adamw_step": 1,
+    "pph_ppc_bwd": 1, "pph_logits_bwd": 1, "pph_similarity_bwd": 2, "pph_addon_bwd": 3, "pph_loss_tail": 1, "pph_loss_combine": 1, "pph_rollout_scores": 2, "pph_adamw_step": 1, "pph_class_maps": 1, "pph_rollout_cls_rows": 1,
 }
 
 _lib = None

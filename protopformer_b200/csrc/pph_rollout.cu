@@ -515,6 +515,51 @@ rollout_chain2_kernel(int L, int B, int T, int cap, const int32_t* __restrict__ 
     for (int j = tid; j < W; j += kRoChainThreads) scores[(size_t)b * W + j] = v[cur][j + drop_first];
 }
 
+
+// CaiT start row (cait_models_attn.py:223-259): the class-attention maps (B,H,1,Tc) of the token-only blocks go
+// through the same per-layer processing (head fusion, discard of the int(Tc*ratio) smallest entries, + w on the
+// CLS column -- `I[:1]` --, row normalisation); the mean over those layers without the CLS column is the row that
+// multiplies the patch-layer product.  One CTA per image, thread = entry; the discard is a rank count (stable: among
+// equal values the lowest index is discarded first).
+constexpr int kRoClsThreads = 256;
+
+__global__ void __launch_bounds__(kRoClsThreads)
+rollout_cls_rows_kernel(const RoLayers layers, int n_cls, int B, int H, int Tc, int k_discard, int head_fusion,
+                        float identity_w, float* __restrict__ v0) {
+    pdl_sync();
+    __shared__ float x[kRoClsThreads], acc[kRoClsThreads], wred[kRoClsThreads / 32];
+    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    acc[tid] = 0.0f;
+    for (int c = 0; c < n_cls; ++c) {
+        const float* A = layers.p[c] + (size_t)b * H * Tc;
+        float s = 0.0f;
+        if (tid < Tc) {
+            s = A[tid];
+            for (int h = 1; h < H; ++h) {
+                const float t = A[(size_t)h * Tc + tid];
+                s = head_fusion == 0 ? s + t : head_fusion == 1 ? fmaxf(s, t) : fminf(s, t);
+            }
+            if (head_fusion == 0) s = s / (float)H;
+        }
+        __syncthreads();                      // previous layer's readers of x[] are done
+        x[tid] = s;
+        __syncthreads();
+        float a = 0.0f;
+        if (tid < Tc) {
+            int rank = 0;
+            for (int j = 0; j < Tc; ++j) rank += (x[j] < s) || (x[j] == s && j < tid);
+            const float kept = rank < k_discard ? 0.0f : s;
+            a = (kept + (tid == 0 ? identity_w : 0.0f)) / (1.0f + identity_w);
+        }
+        float part = warp_sum(a);
+        if (lane == 0) wred[warp] = part;
+        __syncthreads();
+        float tot = 0.0f;
+        for (int w = 0; w < kRoClsThreads / 32; ++w) tot += wred[w];
+        if (tid < Tc) acc[tid] += a / tot;
+    }
+    if (tid >= 1 && tid < Tc) v0[(size_t)b * (Tc - 1) + tid - 1] = acc[tid] / (float)n_cls;
+}
 }  // namespace pph
 
 extern "C" int pph_rollout_ws_bytes(int L, int B, int T, int k_discard, long long* bytes) {
@@ -587,4 +632,21 @@ extern "C" int pph_rollout_scores(const float* const* attn_layers, int L, int B,
                  w.ent_val, w.ent_row, v0, drop_first, scores);
     }
     return launch_status("pph_rollout_scores(chain)");
+}
+
+extern "C" int pph_rollout_cls_rows(const float* const* cls_layers, int n_cls, int B, int H, int Tc, int k_discard,
+                                    int head_fusion, float identity_w, float* v0, pph_stream_t stream) {
+    using namespace pph;
+    PPH_REQUIRE(cls_layers && v0, PPH_EINVAL, "pph_rollout_cls_rows: null pointer");
+    PPH_REQUIRE(n_cls >= 1 && n_cls <= kRoMaxLayers, PPH_EUNSUP, "pph_rollout_cls_rows: 1 <= n_cls <= %d", kRoMaxLayers);
+    PPH_REQUIRE(B >= 0 && H >= 1 && Tc >= 2 && k_discard >= 0, PPH_EINVAL, "pph_rollout_cls_rows: bad dims");
+    PPH_REQUIRE(Tc <= kRoClsThreads, PPH_EUNSUP, "pph_rollout_cls_rows: Tc=%d > %d", Tc, kRoClsThreads);
+    PPH_REQUIRE(head_fusion >= 0 && head_fusion <= 2, PPH_EINVAL, "pph_rollout_cls_rows: head_fusion %d", head_fusion);
+    if (B == 0) return 0;
+    RoLayers layers;
+    for (int l = 0; l < kRoMaxLayers; ++l) layers.p[l] = l < n_cls ? cls_layers[l] : nullptr;
+    for (int l = 0; l < n_cls; ++l) PPH_REQUIRE(layers.p[l], PPH_EINVAL, "pph_rollout_cls_rows: layer %d is null", l);
+    launch_k(rollout_cls_rows_kernel, dim3(B), dim3(kRoClsThreads), (size_t)0, as_stream(stream), layers, n_cls, B, H, Tc,
+             k_discard, head_fusion, identity_w, v0);
+    return launch_status("pph_rollout_cls_rows");
 }

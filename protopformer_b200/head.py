@@ -190,6 +190,20 @@ class PPNet(nn.Module):
             pm = ProtoMap(cfg, tf, self.prototype_vectors, self.prototype_vectors_global, None, "act")
             return cls_token_attn, pm.materialize()
 
+    def push_forward_class_maps(self, x, targets):
+        """(cls_token_attn (B,N), maps (B, m, side, side)): the activation maps of each image's label-class prototypes
+        on the grid of ALL tokens (zeros on pruned ones) -- what eval_interpretability.py:195-225 derives from
+        ``push_forward`` by a gather and a scatter -- without ever forming the (B,P,h,w) map."""
+        tokens, cls_token_attn = self._backbone(x)
+        cfg = self._cfg()
+        idx32 = ops.select_topk(cls_token_attn, cfg.K)
+        conv = self.add_on_layers[0]
+        with torch.no_grad():
+            tf = ops.addon(tokens, idx32, conv.weight, conv.bias, False)
+            maps = ops.class_activation_maps(cfg, tf, self.prototype_vectors, targets, self.num_prototypes_per_class,
+                                             cls_token_attn.shape[-1])
+        return cls_token_attn, maps
+
     # ------------------------------------------------------------------------------------------------------------
     def __repr__(self):
         return ('PPNet(\n\tfeatures: {},\n\timg_size: {},\n\tprototype_shape: {},\n\tproto_layer_rf_info: {},\n'

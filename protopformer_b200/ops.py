@@ -113,6 +113,24 @@ def rollout_scores(all_attn, discard_ratio: float = 0.9, head_fusion: str = "mea
     return scores
 
 
+def rollout_scores_cait(all_attn, pre_layer_num: int, discard_ratio: float = 0.9, head_fusion: str = "mean",
+                        identity_w: float = 0.2):
+    """``attn_rollout_cait(all_attn, discard_ratio, head_fusion, layer_nums=[pre_layer_num, i])[1][:, 0]`` of the
+    reference (tools/cait_models_attn.py:223-261, :328-330): all_attn = pre_layer_num patch-layer maps (B,H,T,T)
+    followed by i >= 1 class-attention maps (B,H,1,T+1).  Returns the detached token score (B,T)."""
+    import ctypes
+    patch, cls = list(all_attn[:pre_layer_num]), list(all_attn[pre_layer_num:])
+    assert patch and cls, "CaiT rollout needs patch layers and at least one class-attention layer"
+    cls = [c.detach().float().contiguous() for c in cls]
+    B, H, R, Tc = cls[0].shape
+    assert R == 1 and all(c.shape == cls[0].shape for c in cls)
+    v0 = _empty((B, Tc - 1), torch.float32, cls[0])
+    table = (ctypes.c_void_p * len(cls))(*[_ptr_of(c) for c in cls])
+    _lib.call("pph_rollout_cls_rows", table, len(cls), B, H, Tc, int(Tc * discard_ratio), FUSIONS[head_fusion],
+              float(identity_w), v0)
+    return rollout_scores(patch, discard_ratio, head_fusion, identity_w, v0=v0, drop_first=False)
+
+
 def _ptr_of(t: torch.Tensor) -> int:
     assert t.is_cuda and t.is_contiguous()
     return t.data_ptr()
@@ -364,6 +382,23 @@ def materialize_maps(cfg: HeadConfig, tf: TokenFeatures, P, Pg):
     pg = prepare_prototypes(Pg.reshape(Pg.shape[0], -1), False)
     _, _, _, _, _, dist_map, act_map = _similarity_raw(cfg, tf, pl, pg, want_maps=True, mode_id=_lib.MODE_FP32_FMA)
     return dist_map, act_map
+
+
+def class_activation_maps(cfg: HeadConfig, tf: TokenFeatures, P, labels, m: int, N: int, p2l=None):
+    """(B, m, side, side) activation maps of each image's label-class prototypes on the original token grid, zeros on
+    pruned tokens -- eval_interpretability.py:195-225 (gather of the class rows of `proto_acts` + scatter from the
+    h x w reserved tokens to the 14 x 14 grid) without materialising the (B,P,h,w) map.  Not differentiable."""
+    side = int(round(math.sqrt(N)))
+    assert side * side == N
+    P2d = P.detach().reshape(P.shape[0], -1).float().contiguous()
+    if p2l is None:
+        p2l = prepare_prototypes(P2d, False).p2
+    Zs = tf.Zs.detach()
+    B, K, D = Zs.shape
+    maps = _empty((B, m, N), torch.float32, Zs)
+    _lib.call("pph_class_maps", Zs, tf.z2s, P2d, p2l, tf.idx32, labels.to(torch.int64).contiguous(), B, K, D,
+              P2d.shape[0], m, N, cfg.act_id, float(cfg.eps), maps)
+    return maps.view(B, m, side, side)
 
 
 # ------------------------------------------------------------------------------------------------------------------

@@ -30,6 +30,30 @@ CASES = {
 }
 
 
+# name: (n_patch, n_cls, B, H, T, seed, K)   -- tools/cait_models_attn.py:223-261 (cait_xxs24: 24 patch layers, 4 heads)
+CAIT_CASES = {
+    "rollout_cait_tiny": (3, 1, 2, 2, 16, 1, 2),
+    "rollout_cait_xxs24_b2": (24, 2, 2, 4, 196, 2, 121),
+}
+
+
+def cait():
+    import tools.cait_models_attn as cm
+    for name, (n_patch, n_cls, B, H, T, seed, K) in CAIT_CASES.items():
+        attn = R.synth_cait_attention(n_patch, n_cls, B, H, T, seed)
+        assert R.threshold_tie_free(attn, 0.9, "mean"), f"{name}: tie at the discard threshold"
+        _, cls_result = cm.MyCait.attn_rollout_cait(None, [a.clone() for a in attn], discard_ratio=0.9,
+                                                    head_fusion="mean", layer_nums=[n_patch, n_cls])
+        scores = cls_result[:, 0].contiguous()                      # cls_attn_ma[:, 0], cait_models_attn.py:330
+        idx = torch.topk(scores, k=K, dim=-1)[1].sort(dim=-1)[0]
+        srt = scores.sort(dim=-1, descending=True)[0]
+        out = dict(scores=scores.numpy(), idx=idx.numpy().astype(np.int32),
+                   sel_gap=np.float32(((srt[:, K - 1] - srt[:, K]) / srt[:, K - 1].clamp_min(1e-30)).min().item()),
+                   chk=np.array([synth.checksum(a) for a in attn]))
+        np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), name + ".npz"), **out)
+        print(name, "scores", tuple(scores.shape), "relative selection gap %.2e" % float(out["sel_gap"]))
+
+
 def main():
     ref_harness.import_reference()
     import tools.deit_models_attn as dm          # the reference's module (timm stubbed by ref_harness)
@@ -48,6 +72,7 @@ def main():
                    chk=np.array([synth.checksum(a) for a in attn]))
         np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), name + ".npz"), **out)
         print(name, "scores", tuple(scores.shape), "relative selection gap %.2e" % float(out["sel_gap"]))
+    cait()
 
 
 if __name__ == "__main__":

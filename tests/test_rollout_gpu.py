@@ -4,7 +4,7 @@ import pytest
 import torch
 
 from oracle import rollout_oracle as R
-from tests.test_rollout_oracle import ROLLOUT_CASES, load_rollout
+from tests.test_rollout_oracle import CAIT_CASES, ROLLOUT_CASES, load_cait, load_rollout
 from tests.util import max_rel, rel_close
 
 pytestmark = pytest.mark.gpu
@@ -76,3 +76,24 @@ def test_rollout_is_bit_reproducible_and_batch_independent():
     perm = torch.tensor([2, 0, 3, 1])
     c = ops.rollout_scores([x[perm].contiguous() for x in d])
     assert torch.equal(c, a[perm.to(DEV)])
+
+
+@pytest.mark.parametrize("name", list(CAIT_CASES))
+def test_cait_rollout_matches_reference_fixture(name):
+    """pph_rollout_cls_rows + pph_rollout_scores(v0) against the reference's attn_rollout_cait (fixture)."""
+    attn, g, n_patch, K = load_cait(name)
+    ops = _ops()
+    scores = ops.rollout_scores_cait([a.to(DEV) for a in attn], n_patch, 0.9, "mean")
+    assert scores.shape == g["scores"].shape
+    assert rel_close(scores.cpu(), g["scores"], 1e-5, 1e-9), max_rel(scores.cpu(), g["scores"], 1e-9)
+    assert np.array_equal(ops.select_topk(scores, K).cpu().numpy(), g["idx"])
+
+
+def test_cait_start_row_ties_and_fusions_against_oracle():
+    g = torch.Generator().manual_seed(8)
+    for fusion in ("mean", "max", "min"):
+        attn = R.synth_cait_attention(2, 3, 3, 3, 25, seed=4)
+        attn[-1] = torch.randint(1, 4, attn[-1].shape, generator=g).float() / 4.0       # quantised row: ties everywhere
+        got = _ops().rollout_scores_cait([a.to(DEV) for a in attn], 2, 0.9, fusion)
+        want = R.rollout_cait(attn, 2, 0.9, fusion)
+        assert rel_close(got.cpu(), want, 1e-5, 1e-9), (fusion, max_rel(got.cpu(), want, 1e-9))

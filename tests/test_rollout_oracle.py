@@ -61,3 +61,29 @@ def test_start_row_variant_matches_manual_chain():
     got = R.rollout_cls_row(attn, v0=v0, drop_first=False)
     full = R.rollout_full(attn)
     assert rel_close(got, torch.einsum("bi,bij->bj", v0, full), 1e-5, 1e-9)
+
+
+CAIT_CASES = {
+    "rollout_cait_tiny": (3, 1, 2, 2, 16, 1, 2),
+    "rollout_cait_xxs24_b2": (24, 2, 2, 4, 196, 2, 121),
+}
+
+
+def load_cait(name):
+    n_patch, n_cls, B, H, T, seed, K = CAIT_CASES[name]
+    attn = R.synth_cait_attention(n_patch, n_cls, B, H, T, seed)
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    chk = np.array([synth.checksum(a) for a in attn])
+    assert np.allclose(chk, g["chk"], rtol=1e-9), "synthetic attention drifted from the fixture"
+    return attn, g, n_patch, K
+
+
+@pytest.mark.parametrize("name", list(CAIT_CASES))
+def test_cait_restatement_and_start_row_chain_match_the_reference(name):
+    """tools/cait_models_attn.py:223-261 through the reference's own attn_rollout_cait (fixture)."""
+    attn, g, n_patch, K = load_cait(name)
+    assert rel_close(R.rollout_cait(attn, n_patch), g["scores"], 1e-6, 1e-9)
+    v0 = torch.cat([R.process_layer(a) for a in attn[n_patch:]], dim=1).mean(dim=1)[:, 1:]
+    chain = R.rollout_cls_row(attn[:n_patch], v0=v0, drop_first=False)
+    assert rel_close(chain, g["scores"], 1e-5, 1e-9)
+    assert np.array_equal(torch.topk(chain, k=K, dim=-1)[1].sort(dim=-1)[0].numpy(), g["idx"])
