@@ -194,6 +194,9 @@ int pph_loss_combine(const float* ce_losses, const float* ppc_losses, float cov_
  * arguments: nothing is retained).  head_fusion: 0 mean, 1 max, 2 min.  identity_w = 0.2 in the reference.
  * v0 [B,T] optional start row (CaiT, cait_models_attn.py:255-259); drop_first = 1 drops the CLS column (DeiT).
  * scores [B, T - drop_first].  workspace: pph_rollout_ws_bytes() bytes of device scratch (sparse per-layer matrices).
+ * Fused selection (north_star (a): score reduction + per-image top-k in one pass): K > 0 also writes the ascending
+ * index list of the K largest scores of each image, idx32 [B,K] (and idx64 [B,K] unless NULL), exactly what
+ * pph_select_topk would return on `scores` (protopformer.py:157-158, deit_models_attn.py:229-230); K = 0: scores only.
  * L <= 32, 2 <= T <= 224. */
 #define PPH_FUSE_MEAN 0
 #define PPH_FUSE_MAX  1
@@ -201,7 +204,7 @@ int pph_loss_combine(const float* ce_losses, const float* ppc_losses, float cov_
 int pph_rollout_ws_bytes(int L, int B, int T, int k_discard, long long* bytes /* host */);
 int pph_rollout_scores(const float* const* attn_layers /* host array of device pointers */, int L, int B, int H, int T,
                        int k_discard, int head_fusion, float identity_w, const float* v0, int drop_first,
-                       void* workspace, float* scores, pph_stream_t stream);
+                       void* workspace, float* scores, int K, int32_t* idx32, int64_t* idx64, pph_stream_t stream);
 
 /* (next #3, optimizer tail) torch.optim.AdamW as the reference builds it for the head's parameter groups
  * (tools/create_optimizer.py:31-39, :92; engine_proto.py:76-78), all tensors in ONE launch:

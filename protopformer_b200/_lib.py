@@ -38,7 +38,7 @@ SIGNATURES = {
     "pph_loss_tail": [_p, _p, _p, _f, _f, _f, _i, _i, _p, _p, _p, _p, _p],
     "pph_loss_combine": [_p, _p, _f, _f, _p, _p],
     "pph_rollout_ws_bytes": [_i, _i, _i, _i, C.POINTER(C.c_longlong)],
-    "pph_rollout_scores": [_p, _i, _i, _i, _i, _i, _i, _f, _p, _i, _p, _p, _p],
+    "pph_rollout_scores": [_p, _i, _i, _i, _i, _i, _i, _f, _p, _i, _p, _p, _i, _p, _p, _p],
     "pph_adamw_step": [_i, _p, _p, _p, _p, _p, _p, _p, C.c_double, C.c_double, _f, _f, _p, _p],
     "pph_rollout_cls_rows": [_p, _i, _i, _i, _i, _i, _i, _f, _p, _p],
     "pph_class_maps": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p],

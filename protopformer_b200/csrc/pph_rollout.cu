@@ -269,11 +269,41 @@ rollout_prepare_kernel(const RoLayers layers, int L, int B, int H, int T, int k_
     }
 }
 
+// Fused foreground-token selection (protopformer.py:157-158 / deit_models_attn.py:229-230) on the finished score row:
+// rank by counting over the W scores in shared memory (larger score first, lower index first on ties -- the rule of
+// pph_select_topk), emitted in ascending token order.  All kRoChainThreads threads call it; W <= kRoChainThreads.
+__device__ __forceinline__ void ro_emit_topk(const float* sc, int W, int K, int32_t* __restrict__ idx32,
+                                             int64_t* __restrict__ idx64, int* wcnt) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    bool sel = false;
+    if (tid < W) {
+        const float v = sc[tid];
+        int rank = 0;
+        for (int j = 0; j < W; ++j) {
+            const float q = sc[j];
+            rank += (q > v) || (q == v && j < tid);
+        }
+        sel = rank < K;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, sel);
+    if (lane == 0) wcnt[warp] = __popc(m);
+    __syncthreads();
+    if (sel) {
+        int off = 0;
+        for (int w = 0; w < warp; ++w) off += wcnt[w];
+        const int pos = off + __popc(m & ((1u << lane) - 1u));
+        idx32[pos] = tid;
+        if (idx64) idx64[pos] = tid;
+    }
+}
+
 __global__ void __launch_bounds__(kRoChainThreads)
 rollout_chain_kernel(int L, int B, int T, int cap, const int32_t* __restrict__ col_ptr,
                      const float* __restrict__ ent_val, const uint16_t* __restrict__ ent_row,
-                     const float* __restrict__ v0, int drop_first, float* __restrict__ scores) {
+                     const float* __restrict__ v0, int drop_first, float* __restrict__ scores, int K,
+                      int32_t* __restrict__ idx32, int64_t* __restrict__ idx64) {
     pdl_sync();
+    __shared__ int wcnt[kRoChainThreads / 32];
     __shared__ float v[2][kRoMaxT];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int j = tid; j < T; j += kRoChainThreads) v[0][j] = v0 ? v0[(size_t)b * T + j] : (j == 0 ? 1.0f : 0.0f);
@@ -295,7 +325,15 @@ rollout_chain_kernel(int L, int B, int T, int cap, const int32_t* __restrict__ c
         cur ^= 1;
     }
     const int W = T - drop_first;
-    for (int j = tid; j < W; j += kRoChainThreads) scores[(size_t)b * W + j] = v[cur][j + drop_first];
+    for (int j = tid; j < W; j += kRoChainThreads) {
+        const float sc = v[cur][j + drop_first];
+        scores[(size_t)b * W + j] = sc;
+        v[cur ^ 1][j] = sc;                              // the other buffer is free: score row for the selection
+    }
+    if (K > 0) {
+        __syncthreads();
+        ro_emit_topk(v[cur ^ 1], W, K, idx32 + (size_t)b * K, idx64 ? idx64 + (size_t)b * K : nullptr, wcnt);
+    }
 }
 
 
@@ -478,8 +516,10 @@ rollout_prepare2_kernel(const RoLayers layers, int L, int B, int H, int T, int k
 __global__ void __launch_bounds__(kRoChainThreads)
 rollout_chain2_kernel(int L, int B, int T, int cap, const int32_t* __restrict__ col_ptr,
                       const float* __restrict__ ent_val, const uint16_t* __restrict__ ent_row,
-                      const float* __restrict__ v0, int drop_first, float* __restrict__ scores) {
+                      const float* __restrict__ v0, int drop_first, float* __restrict__ scores, int K,
+                      int32_t* __restrict__ idx32, int64_t* __restrict__ idx64) {
     pdl_sync();
+    __shared__ int wcnt[kRoChainThreads / 32];
     extern __shared__ __align__(16) uint8_t ch_smem[];
     float* sval = reinterpret_cast<float*>(ch_smem);                          // [cap]
     int* scp = reinterpret_cast<int*>(sval + cap);                            // [T+1]
@@ -512,7 +552,15 @@ rollout_chain2_kernel(int L, int B, int T, int cap, const int32_t* __restrict__ 
     }
     __syncthreads();
     const int W = T - drop_first;
-    for (int j = tid; j < W; j += kRoChainThreads) scores[(size_t)b * W + j] = v[cur][j + drop_first];
+    for (int j = tid; j < W; j += kRoChainThreads) {
+        const float sc = v[cur][j + drop_first];
+        scores[(size_t)b * W + j] = sc;
+        v[cur ^ 1][j] = sc;                              // the other buffer is free: score row for the selection
+    }
+    if (K > 0) {
+        __syncthreads();
+        ro_emit_topk(v[cur ^ 1], W, K, idx32 + (size_t)b * K, idx64 ? idx64 + (size_t)b * K : nullptr, wcnt);
+    }
 }
 
 
@@ -571,7 +619,7 @@ extern "C" int pph_rollout_ws_bytes(int L, int B, int T, int k_discard, long lon
 
 extern "C" int pph_rollout_scores(const float* const* attn_layers, int L, int B, int H, int T, int k_discard,
                                   int head_fusion, float identity_w, const float* v0, int drop_first, void* workspace,
-                                  float* scores, pph_stream_t stream) {
+                                  float* scores, int K, int32_t* idx32, int64_t* idx64, pph_stream_t stream) {
     using namespace pph;
     PPH_REQUIRE(attn_layers && workspace && scores, PPH_EINVAL, "pph_rollout_scores: null pointer");
     PPH_REQUIRE(L >= 1 && L <= kRoMaxLayers, PPH_EUNSUP, "pph_rollout_scores: 1 <= L <= %d (L=%d)", kRoMaxLayers, L);
@@ -580,6 +628,8 @@ extern "C" int pph_rollout_scores(const float* const* attn_layers, int L, int B,
     PPH_REQUIRE(T <= kRoMaxT, PPH_EUNSUP, "pph_rollout_scores: T=%d > %d (the fused map must fit in shared memory)", T,
                 kRoMaxT);
     PPH_REQUIRE(head_fusion >= 0 && head_fusion <= 2, PPH_EINVAL, "pph_rollout_scores: head_fusion %d", head_fusion);
+    PPH_REQUIRE(K == 0 || (K >= 1 && K <= T - drop_first && idx32), PPH_EINVAL,
+                "pph_rollout_scores: fused selection needs 1 <= K <= %d and idx32 (K=%d)", T - drop_first, K);
     if (B == 0) return 0;
     if (k_discard > T * T) k_discard = T * T;
     RoLayers layers;
@@ -626,10 +676,10 @@ extern "C" int pph_rollout_scores(const float* const* attn_layers, int L, int B,
                                              160 * 1024);
         if (e != cudaSuccess) { set_error("pph_rollout_scores: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         launch_k(rollout_chain2_kernel, dim3(B), dim3(kRoChainThreads), csmem, st, L, B, T, w.cap, w.col_ptr, w.ent_val,
-                 w.ent_row, v0, drop_first, scores);
+                 w.ent_row, v0, drop_first, scores, K, idx32, idx64);
     } else {
         launch_k(rollout_chain_kernel, dim3(B), dim3(kRoChainThreads), (size_t)0, st, L, B, T, w.cap, w.col_ptr,
-                 w.ent_val, w.ent_row, v0, drop_first, scores);
+                 w.ent_val, w.ent_row, v0, drop_first, scores, K, idx32, idx64);
     }
     return launch_status("pph_rollout_scores(chain)");
 }

@@ -81,11 +81,14 @@ def rollout_workspace(L: int, B: int, T: int, k_discard: int, device) -> torch.T
 
 
 def rollout_scores(all_attn, discard_ratio: float = 0.9, head_fusion: str = "mean", identity_w: float = 0.2,
-                   v0: torch.Tensor | None = None, drop_first: bool = True, workspace: torch.Tensor | None = None):
+                   v0: torch.Tensor | None = None, drop_first: bool = True, workspace: torch.Tensor | None = None,
+                   topk: int = 0, want_int64: bool = False):
     """``attn_rollout(all_attn)[:, 0, 1:]`` of the reference (deit_models_attn.py:99-124, :226) without the (T,T)
     products.  all_attn: list of L fp32 CUDA tensors (B,H,T,T) (the attention maps of the first L blocks);
     returns the detached score (B, T-1) [(B,T) when drop_first is False].  ``v0`` (B,T): start row instead of e_0
-    (CaiT, cait_models_attn.py:255-259).  The result is not differentiable -- the reference detaches it (:225)."""
+    (CaiT, cait_models_attn.py:255-259).  The result is not differentiable -- the reference detaches it (:225).
+    ``topk`` = K > 0: the same launch also selects the K highest-scoring tokens of every image (ascending int32 index
+    list, deit_models_attn.py:229-230 / protopformer.py:157-158) and ``(scores, idx32[, idx64])`` is returned."""
     import ctypes
     L = len(all_attn)
     assert L >= 1
@@ -108,8 +111,12 @@ def rollout_scores(all_attn, discard_ratio: float = 0.9, head_fusion: str = "mea
     table = (ctypes.c_void_p * L)(*[_ptr_of(a) for a in layers])
     if v0 is not None:
         v0 = v0.detach().float().contiguous()
+    idx32 = _empty((B, topk), torch.int32, layers[0]) if topk > 0 else None
+    idx64 = _empty((B, topk), torch.int64, layers[0]) if (topk > 0 and want_int64) else None
     _lib.call("pph_rollout_scores", table, L, B, H, T, k, FUSIONS[head_fusion], float(identity_w), v0,
-              int(drop_first), workspace, scores)
+              int(drop_first), workspace, scores, int(topk), idx32, idx64)
+    if topk > 0:
+        return (scores, idx32, idx64) if want_int64 else (scores, idx32)
     return scores
 
 

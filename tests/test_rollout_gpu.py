@@ -28,6 +28,9 @@ def test_rollout_matches_reference_fixture(name):
     assert rel_close(scores.cpu(), g["scores"], 1e-5, 1e-9), max_rel(scores.cpu(), g["scores"], 1e-9)
     idx = ops.select_topk(scores, K)
     assert np.array_equal(idx.cpu().numpy(), g["idx"])                # bit-exact selection downstream
+    # the fused form (score reduction + top-K in one launch sequence) returns the same scores and index lists
+    s2, i32, i64 = ops.rollout_scores(d_attn, 0.9, fusion, topk=K, want_int64=True)
+    assert torch.equal(s2, scores) and torch.equal(i32, idx) and torch.equal(i64, idx.long())
 
 
 @pytest.mark.parametrize("L,B,H,T,fusion", [(1, 1, 1, 2, "mean"), (2, 3, 1, 33, "min"), (5, 4, 3, 64, "mean"),
@@ -50,6 +53,10 @@ def test_rollout_threshold_ties_discard_lowest_index_first():
     want = R.rollout_cls_row(attn, 0.9, "mean")
     got = _ops().rollout_scores([a.to(DEV) for a in attn], 0.9, "mean")
     assert rel_close(got.cpu(), want, 1e-5, 1e-9), max_rel(got.cpu(), want, 1e-9)
+    # tied SCORES (rows the rollout leaves at exactly zero): the fused selection breaks ties like pph_select_topk
+    s2, i32 = _ops().rollout_scores([a.to(DEV) for a in attn], 1.0, "mean", topk=7)
+    assert torch.equal(i32, _ops().select_topk(s2, 7))
+    assert torch.equal(i32.cpu(), torch.arange(7, dtype=torch.int32).repeat(2, 1))      # all-zero scores: first 7 tokens
 
 
 def test_rollout_start_row_and_discard_ratio_edges():
