@@ -91,6 +91,42 @@ def test_module_constructs_on_cpu_with_reference_attribute_names():
         PPNet(MyVisionTransformer(), 224, [20, 16, 1, 1], [14, 16, 16, 8.0], 4, use_global=False)
 
 
+def test_widened_rows_validate_arguments_and_refuse_cpu_tensors():
+    """rollout / AdamW / class maps: argument errors come back through the C ABI before any launch, CPU tensors never
+    reach a kernel, and the optimizer's parameter groups mirror tools/create_optimizer.py:31-39."""
+    import ctypes
+    import torch.nn as nn
+    from protopformer_b200 import PPNet, _lib, ops
+    from protopformer_b200.optim import FusedHeadAdamW, head_param_groups
+    lib = _lib.load()
+    n = ctypes.c_longlong(0)
+    assert lib.pph_rollout_ws_bytes(11, 64, 197, 34928, ctypes.byref(n)) == 0
+    cap = ((197 * 197 - 34928 + 197) + 7) // 8 * 8
+    assert n.value >= 11 * 64 * (198 * 4 + cap * 6)                  # column pointers + (value, row) entries
+    assert lib.pph_rollout_scores(None, 1, 1, 1, 8, 0, 0, 0.2, None, 1, None, None, 0, None, None, None) == -1
+    assert lib.pph_adamw_step(0, None, None, None, None, None, None, None, 0.9, 0.999, 1e-8, 1.0, None, None) == -1
+    assert lib.pph_class_maps(None, None, None, None, None, None, 1, 1, 1, 1, 1, 1, 0, 1e-4, None, None) == -1
+    with pytest.raises((AssertionError, RuntimeError)):
+        ops.rollout_scores([torch.rand(1, 2, 5, 5)])
+    with pytest.raises(ValueError):
+        FusedHeadAdamW([torch.zeros(4, 4)])
+
+    class MyVisionTransformer(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc = nn.Linear(24, 24)
+            self.patch_embed = nn.Module()
+            self.patch_embed.num_patches = 16
+
+    net = PPNet(MyVisionTransformer(), 224, [20, 16, 1, 1], [14, 16, 16, 8.0], 4, reserve_layers=[11],
+                reserve_token_nums=[9], use_global=True, use_ppc_loss=True, global_proto_per_class=2,
+                add_on_layers_type='regular')
+    groups = head_param_groups(net, {"add_on_layers": 3e-3, "prototype_vectors": 2e-3}, 0.05)
+    assert [g["lr"] for g in groups] == [3e-3, 2e-3, 2e-3] and [g["weight_decay"] for g in groups] == [1e-3, 0.05, 0.05]
+    assert groups[0]["params"][0] is net.add_on_layers[0].weight and groups[1]["params"][0] is net.prototype_vectors
+    assert groups[2]["params"][0] is net.prototype_vectors_global
+
+
 def _gloo_worker(rank, world, port, q):
     import torch.distributed as dist
     from protopformer_b200.dist import FlatGradReducer, shard_batch
@@ -106,7 +142,7 @@ def _gloo_worker(rank, world, port, q):
     loss.backward()
     assert P.grad.data_ptr() == red.views[0].data_ptr()       # autograd accumulated in place into the flat buffer
     red.allreduce()
-    q.put((rank, lo, hi, P.grad.clone(), W.grad.clone()))
+    q.put((rank, lo, hi, P.grad.tolist(), W.grad.tolist()))     # plain lists: no fd passing that can outlive the worker
     dist.destroy_process_group()
 
 
@@ -126,6 +162,7 @@ def test_flat_gradient_allreduce_gloo_world2():
         p.join(timeout=120)
         assert p.exitcode == 0
     (_, lo0, hi0, gP0, gW0), (_, lo1, hi1, gP1, gW1) = res
+    gP0, gW0, gP1, gW1 = (torch.tensor(t) for t in (gP0, gW0, gP1, gW1))
     assert (lo0, hi0, lo1, hi1) == (0, 5, 5, 10)
     assert torch.allclose(gP0, gP1) and torch.allclose(gW0, gW1)
     assert torch.allclose(gP0, torch.full((6, 4), 45.0 / 2))      # mean over ranks of sum(x_shard)
