@@ -60,3 +60,39 @@ def argmax_mismatch_outside_near_ties(arg_a, arg_b, near_tie):
     for b, p in np.asarray(near_tie).reshape(-1, 2):
         diff[b, p] = False
     return int(diff.sum())
+
+
+class FakeAttnBlock(torch.nn.Module):
+    """Seeded stand-in for a transformer block with the reference's calling convention ``blk(x, policy) -> (x, attn)``
+    (tools/deit_models_attn.py:76-82): multi-head softmax attention whose keys are masked by ``policy`` (pruned tokens
+    only attend to themselves, as :29-43 does), plus a residual.  TEST INFRASTRUCTURE for the backbone-loop tests."""
+
+    def __init__(self, dim: int, heads: int, seed: int):
+        super().__init__()
+        g = torch.Generator().manual_seed(9000 + seed)
+        self.heads = heads
+        self.wq = torch.nn.Parameter(torch.randn(dim, dim, generator=g) / dim ** 0.5)
+        self.wk = torch.nn.Parameter(torch.randn(dim, dim, generator=g) / dim ** 0.5)
+        self.wv = torch.nn.Parameter(torch.randn(dim, dim, generator=g) / dim ** 0.5)
+
+    def forward(self, x, policy):
+        B, T, C = x.shape
+        H, hd = self.heads, C // self.heads
+        q = (x @ self.wq).reshape(B, T, H, hd).transpose(1, 2)
+        k = (x @ self.wk).reshape(B, T, H, hd).transpose(1, 2)
+        v = (x @ self.wv).reshape(B, T, H, hd).transpose(1, 2)
+        logits = (q @ k.transpose(-2, -1)) * (3.0 * hd ** -0.5)
+        mask = policy.reshape(B, 1, 1, T)
+        mask = mask + (1.0 - mask) * torch.eye(T, device=x.device).view(1, 1, T, T)
+        e = torch.exp(logits - logits.max(dim=-1, keepdim=True)[0]) * mask
+        attn = e / e.sum(dim=-1, keepdim=True)
+        return x + 0.5 * (attn @ v).transpose(1, 2).reshape(B, T, C), attn
+
+
+class FakeDeit(torch.nn.Module):
+    """``blocks`` + ``norm``: what forward_feature_mask_train_direct touches (tools/deit_models_attn.py:205-241)."""
+
+    def __init__(self, dim: int, heads: int, depth: int):
+        super().__init__()
+        self.blocks = torch.nn.ModuleList([FakeAttnBlock(dim, heads, i) for i in range(depth)])
+        self.norm = torch.nn.LayerNorm(dim)
