@@ -97,6 +97,15 @@ int pph_similarity_fwd(int mode, int act_fn, float eps, int B, int K, int D, int
                        float* dmin_l, int32_t* argmin_l, float* act_l, float* dmin_g, float* act_g,
                        float* dist_map, float* act_map, pph_stream_t stream);
 
+/* Host-side introspection of the tensor-core launch plan for a shape (no device access, no launch): which kernel
+ * (resident-prototype v2 or streaming v1), grid, image-group walkers per prototype tile, pipeline stages, global chunk.
+ * out (host int[16]) = {v2, grid, lanes, n_local_ctas, stages, b_tile_bytes, smem_bytes, global_chunk, MT_l, NG_l, MT_g,
+ * NB_g, images_per_tile, umma_n_local, umma_n_global, n_tiles}; coverage (host, optional, n_tiles ints, caller-zeroed):
+ * incremented once per visit of tile (local: group*MT_l + mt; global: n_local + chunk*MT_g + mt) by the CTA/job walk
+ * the kernels perform -- the CPU test suite checks that every entry ends at exactly 1.  sms <= 0: 148. */
+int pph_similarity_plan(int mode, int B, int K, int D, int P, int Pg, int sms, int* out /* host */,
+                        int* coverage /* host */);
+
 /* (a6) protopformer.py:297-300 / 314-316  logits = gc * act_g Wg^T + (1-gc) * act_l Wl^T
  * Wl [C,P], Wg [C,Pg] -> logits, logits_g, logits_l [B,C] */
 int pph_logits_fwd(const float* act_l, const float* act_g, const float* Wl, const float* Wg,

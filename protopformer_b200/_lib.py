@@ -29,6 +29,7 @@ SIGNATURES = {
     "pph_addon_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "pph_split_rows": [_p, _i, _i, _f, _p, _p, _p, _p, _p, _p],
     "pph_similarity_fwd": [_i, _i, _f, _i, _i, _i, _i, _i] + [_p] * 24,
+    "pph_similarity_plan": [_i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "pph_logits_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p],
     "pph_ppc_fwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _p, _p, _p, _p, _p, _p],
     "pph_ppc_bwd": [_p, _p, _p, _p, _p, _p, _p, _f, _f, _i, _i, _i, _i, _i, _i, _i, _f, _f, _f, _i, _p, _p, _p],

@@ -14,7 +14,16 @@ int similarity_fwd_tc(int mode, int act_fn, float eps, int B, int K, int D, int 
                       const float* p2l, const float* p2g,
                       const uint16_t* Pl_hi, const uint16_t* Pl_lo, const uint16_t* Pg_hi, const uint16_t* Pg_lo,
                       float* dmin_l, int32_t* argmin_l, float* act_l, float* dmin_g, float* act_g, cudaStream_t st);
+int similarity_plan(int mode, int B, int K, int D, int P, int Pg, int sms, int* out, int* coverage);
 }  // namespace pph
+
+extern "C" int pph_similarity_plan(int mode, int B, int K, int D, int P, int Pg, int sms, int* out, int* coverage) {
+    using namespace pph;
+    PPH_REQUIRE(mode == PPH_MODE_BF16X3 || mode == PPH_MODE_BF16, PPH_EINVAL, "pph_similarity_plan: tensor-core modes only");
+    PPH_REQUIRE(B >= 1 && P >= 1 && Pg >= 0 && D % 64 == 0 && D >= 64 && D <= 512 && K >= 1 && K <= 256, PPH_EUNSUP,
+                "pph_similarity_plan: shape outside the tcgen05 build range (B=%d K=%d D=%d P=%d Pg=%d)", B, K, D, P, Pg);
+    return similarity_plan(mode, B, K, D, P, Pg, sms, out, coverage);
+}
 
 extern "C" int pph_similarity_fwd(int mode, int act_fn, float eps, int B, int K, int D, int P, int Pg,
                                   const float* Zs, const float* Zc, const float* z2s, const float* z2c,

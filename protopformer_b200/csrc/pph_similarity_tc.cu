@@ -57,7 +57,7 @@ struct TcTile {
     int grp;       // image group (local) or image chunk (global)
 };
 
-__device__ __forceinline__ TcTile tc_decode(const TcParams& prm, int tile) {
+__host__ __device__ __forceinline__ TcTile tc_decode(const TcParams& prm, int tile) {
     TcTile t;
     if (tile < prm.n_local) {
         t.is_global = false;
@@ -399,7 +399,7 @@ struct Tc2Job {
     int mt, t_begin, t_step, t_end;
 };
 
-__device__ __forceinline__ bool tc2_phase(const TcParams& prm, int cta, int p, int lanes_l, int n_local_ctas, int grid,
+__host__ __device__ __forceinline__ bool tc2_phase(const TcParams& prm, int cta, int p, int lanes_l, int n_local_ctas, int grid,
                                           Tc2Job& j) {
     int q = p;
     if (cta < n_local_ctas) {
@@ -688,6 +688,36 @@ static Tc2Plan plan_tc2(const TcParams& prm, int nterms, int sms) {
     return pl;
 }
 
+// Shape-dependent part of the launch: tile counts, UMMA / TMA box sizes, global-branch chunking and the CTA plan.
+// Host-only logic, shared by the launcher and by pph_similarity_plan (which lets the CPU test suite check that every
+// tile of every shape is visited exactly once).
+static void tc_shape_plan(bool x3, int B, int K, int D, int P, int Pg, int sms, TcParams& prm, Tc2Plan& pl) {
+    prm.B = B; prm.K = K; prm.D = D; prm.P = P; prm.Pg = Pg;
+    prm.G = kTcMaxN / K;
+    prm.MT_l = ceil_div(P, kTcBlockM);
+    prm.NG_l = ceil_div(B, prm.G);
+    prm.MT_g = Pg > 0 ? ceil_div(Pg, kTcBlockM) : 0;
+    prm.n_local = prm.MT_l * prm.NG_l;
+    prm.box_rows_l = prm.G * K;
+    prm.umma_n_l = ceil_div(prm.box_rows_l, 16) * 16;
+    auto set_global_chunk = [&](int gN) {            // images per global tile
+        prm.gN = gN;
+        prm.NB_g = Pg > 0 ? ceil_div(B, gN) : 0;
+        prm.n_tiles = prm.n_local + prm.MT_g * prm.NB_g;
+        prm.umma_n_g = ceil_div(B < gN ? B : gN, 16) * 16;
+        prm.box_rows_g = prm.umma_n_g;
+    };
+    set_global_chunk(kTcMaxN);
+    // resident-prototype kernel (v2) whenever >= 2 token stages fit beside the resident tile; a 256-image global tile
+    // is what breaks that for BF16X3 at D = 192, so large batches chunk the global branch by 128 images instead
+    pl = plan_tc2(prm, x3 ? 3 : 1, sms);
+    if (!pl.ok && B > 128) {
+        set_global_chunk(128);
+        pl = plan_tc2(prm, x3 ? 3 : 1, sms);
+        if (!pl.ok) set_global_chunk(kTcMaxN);
+    }
+}
+
 template <int NTERMS, int KT, int EPI = 1>
 static int launch_tc2(const CUtensorMap* maps, const TcParams& prm, const Tc2Plan& pl, cudaStream_t st) {
     auto kern = similarity_tc2_kernel<NTERMS, KT, EPI>;
@@ -730,27 +760,6 @@ int similarity_fwd_tc(int mode, int act_fn, float eps, int B, int K, int D, int 
     PPH_REQUIRE(Pg == 0 || (Zc_hi && Pg_hi && z2c && p2g && dmin_g && act_g && (!x3 || (Zc_lo && Pg_lo))), PPH_EINVAL,
                 "tcgen05 similarity: null global operand");
 
-    TcParams prm;
-    prm.B = B; prm.K = K; prm.D = D; prm.P = P; prm.Pg = Pg;
-    prm.G = kTcMaxN / K;
-    prm.MT_l = ceil_div(P, kTcBlockM);
-    prm.NG_l = ceil_div(B, prm.G);
-    prm.MT_g = Pg > 0 ? ceil_div(Pg, kTcBlockM) : 0;
-    prm.n_local = prm.MT_l * prm.NG_l;
-    prm.box_rows_l = prm.G * K;
-    prm.umma_n_l = ceil_div(prm.box_rows_l, 16) * 16;
-    auto set_global_chunk = [&](int gN) {            // images per global tile
-        prm.gN = gN;
-        prm.NB_g = Pg > 0 ? ceil_div(B, gN) : 0;
-        prm.n_tiles = prm.n_local + prm.MT_g * prm.NB_g;
-        prm.umma_n_g = ceil_div(B < gN ? B : gN, 16) * 16;
-        prm.box_rows_g = prm.umma_n_g;
-    };
-    set_global_chunk(kTcMaxN);
-    prm.act_fn = act_fn; prm.eps = eps;
-    prm.z2s = z2s; prm.z2c = z2c; prm.p2l = p2l; prm.p2g = p2g;
-    prm.dmin_l = dmin_l; prm.act_l = act_l; prm.dmin_g = dmin_g; prm.act_g = act_g; prm.argmin_l = argmin_l;
-
     static int sms = 0;
     if (sms <= 0) {
         int dev = 0;
@@ -758,14 +767,12 @@ int similarity_fwd_tc(int mode, int act_fn, float eps, int B, int K, int D, int 
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms <= 0) sms = 148;
     }
-    // resident-prototype kernel (v2) whenever >= 2 token stages fit beside the resident tile; a 256-image global tile
-    // is what breaks that for BF16X3 at D = 192, so large batches chunk the global branch by 128 images instead
-    Tc2Plan pl = plan_tc2(prm, x3 ? 3 : 1, sms);
-    if (!pl.ok && B > 128) {
-        set_global_chunk(128);
-        pl = plan_tc2(prm, x3 ? 3 : 1, sms);
-        if (!pl.ok) set_global_chunk(kTcMaxN);
-    }
+    TcParams prm;
+    Tc2Plan pl;
+    tc_shape_plan(x3, B, K, D, P, Pg, sms, prm, pl);
+    prm.act_fn = act_fn; prm.eps = eps;
+    prm.z2s = z2s; prm.z2c = z2c; prm.p2l = p2l; prm.p2g = p2g;
+    prm.dmin_l = dmin_l; prm.act_l = act_l; prm.dmin_g = dmin_g; prm.act_g = act_g; prm.argmin_l = argmin_l;
 
     CUtensorMap maps[8];
     int rc;
@@ -805,6 +812,39 @@ int similarity_fwd_tc(int mode, int act_fn, float eps, int B, int K, int D, int 
         default: PPH_TC_DISPATCH(0);
     }
 #undef PPH_TC_DISPATCH
+}
+
+// Host-side view of the launch plan (no device access, no launch): see include/protohead.h.
+int similarity_plan(int mode, int B, int K, int D, int P, int Pg, int sms, int* out, int* coverage) {
+    if (sms <= 0) sms = 148;
+    const bool x3 = (mode == PPH_MODE_BF16X3);
+    TcParams prm;
+    Tc2Plan pl;
+    tc_shape_plan(x3, B, K, D, P, Pg, sms, prm, pl);
+    const int grid_v1 = prm.n_tiles < sms ? prm.n_tiles : sms;
+    if (out) {
+        const int v[16] = {pl.ok ? 1 : 0, pl.ok ? pl.grid : grid_v1, pl.lanes_l, pl.n_local_ctas, pl.stages, pl.b_tile_bytes,
+                           pl.ok ? pl.smem : kTcSmemBytes, prm.gN, prm.MT_l, prm.NG_l, prm.MT_g, prm.NB_g, prm.G,
+                           prm.umma_n_l, prm.umma_n_g, prm.n_tiles};
+        for (int i = 0; i < 16; ++i) out[i] = v[i];
+    }
+    if (coverage) {
+        if (pl.ok) {
+            for (int cta = 0; cta < pl.grid; ++cta) {
+                Tc2Job job;
+                for (int p = 0; tc2_phase(prm, cta, p, pl.lanes_l, pl.n_local_ctas, pl.grid, job); ++p)
+                    for (int t = job.t_begin; t < job.t_end; t += job.t_step)
+                        coverage[job.is_global ? prm.n_local + t * prm.MT_g + job.mt : t * prm.MT_l + job.mt] += 1;
+            }
+        } else {
+            for (int cta = 0; cta < grid_v1; ++cta)
+                for (int tile = cta; tile < prm.n_tiles; tile += grid_v1) {
+                    const TcTile t = tc_decode(prm, tile);
+                    coverage[t.is_global ? prm.n_local + t.grp * prm.MT_g + t.mt : t.grp * prm.MT_l + t.mt] += 1;
+                }
+        }
+    }
+    return 0;
 }
 
 }  // namespace pph

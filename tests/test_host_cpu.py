@@ -167,3 +167,38 @@ def test_flat_gradient_allreduce_gloo_world2():
     assert torch.allclose(gP0, gP1) and torch.allclose(gW0, gW1)
     assert torch.allclose(gP0, torch.full((6, 4), 45.0 / 2))      # mean over ranks of sum(x_shard)
     assert torch.allclose(gW0, torch.full((3,), 1.5))
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_similarity_launch_plan_visits_every_tile_exactly_once(mode):
+    """Host logic of the tcgen05 similarity kernel (CTA/job walk, global-branch chunking, stage budget) for the BASELINE
+    shapes, the sweep corners and awkward sizes -- checked without a GPU through pph_similarity_plan."""
+    import ctypes
+    from protopformer_b200 import _lib
+    lib = _lib.load()
+    shapes = [(64, 81, 192, 2000, 2000), (8, 81, 192, 2000, 2000), (1, 81, 192, 2000, 2000), (256, 81, 384, 1200, 600),
+              (64, 121, 192, 1960, 980), (1024, 81, 192, 2000, 2000), (300, 81, 192, 2000, 1000), (150, 81, 128, 300, 150),
+              (1024, 196, 192, 8000, 8000), (512, 144, 384, 4000, 4000), (32, 49, 192, 1000, 1000), (10, 36, 64, 1000, 500),
+              (3, 196, 192, 8000, 4000), (5, 256, 64, 129, 0), (1000, 1, 64, 20000, 128), (257, 100, 512, 2000, 2000)]
+    for sms in (148, 132, 16):
+        for B, K, D, P, Pg in shapes:
+            out = (ctypes.c_int * 16)()
+            assert lib.pph_similarity_plan(mode, B, K, D, P, Pg, sms, out, None) == 0
+            v2, grid, lanes, n_local_ctas, stages, b_tile, smem, gN, MT_l, NG_l, MT_g, NB_g, G, un_l, un_g, n_tiles = out
+            assert n_tiles == MT_l * NG_l + MT_g * NB_g and G == 256 // K and NG_l == -(-B // G)
+            assert un_l % 16 == 0 and G * K <= un_l <= 256 and un_g % 16 == 0 and min(B, gN) <= un_g <= 256
+            assert NB_g == (-(-B // gN) if Pg else 0) and gN in (128, 256)
+            assert smem <= 232448 and grid >= 1
+            if v2:
+                assert stages >= 2 and 1 <= lanes <= NG_l and n_local_ctas == MT_l * lanes and grid >= n_local_ctas
+                assert b_tile % 1024 == 0 and b_tile >= max(G * K, un_g if Pg else 0) * 128
+            cov = (ctypes.c_int * n_tiles)()
+            assert lib.pph_similarity_plan(mode, B, K, D, P, Pg, sms, out, cov) == 0
+            assert list(cov) == [1] * n_tiles, (mode, sms, B, K, D, P, Pg)
+    # the round-1 finding encoded in the default plan: 8 walkers per prototype tile + 16 global CTAs at the CUB shape
+    out = (ctypes.c_int * 16)()
+    lib.pph_similarity_plan(1, 64, 81, 192, 2000, 2000, 148, out, None)
+    assert (out[0], out[1], out[2]) == (1, 144, 8)
+    lib.pph_similarity_plan(1, 1024, 81, 192, 2000, 2000, 148, out, None)
+    assert out[0] == 1 and out[7] == 128            # BF16X3 keeps the resident-prototype kernel by chunking the global branch
+    assert lib.pph_similarity_plan(0, 64, 81, 192, 2000, 2000, 148, out, None) == -1
