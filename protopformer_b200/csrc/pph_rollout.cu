@@ -356,7 +356,7 @@ template <int HT>
 __global__ void __launch_bounds__(kRoThreads, 1)
 rollout_prepare2_kernel(const RoLayers layers, int L, int B, int H, int T, int k_discard, int head_fusion,
                         float identity_w, int cap, int32_t* __restrict__ col_ptr, float* __restrict__ ent_val,
-                        uint16_t* __restrict__ ent_row) {
+                        uint16_t* __restrict__ ent_row, int norm_mode) {
     pdl_sync();
     extern __shared__ __align__(16) uint8_t ro_smem[];
     const int n = T * T;
@@ -458,21 +458,37 @@ rollout_prepare2_kernel(const RoLayers layers, int L, int B, int H, int T, int k
 
         // ---- 4. a = (A + w I) / (1 + w), rows normalised; zero off-diagonal entries stay zero without arithmetic ----
         const float den = 1.0f + identity_w;
-        for (int r = warp; r < T; r += kRoThreads / 32) {
-            float* row = M + r * T;
-            float s = 0.f;
-            for (int j = lane; j < T; j += 32) {
-                const float x = row[j];
-                if (x != 0.0f || j == r) {
-                    const float a = (x + (j == r ? identity_w : 0.0f)) / den;
-                    row[j] = a;
-                    s += a;
+        if (norm_mode == 0) {
+            for (int r = warp; r < T; r += kRoThreads / 32) {
+                float* row = M + r * T;
+                float s = 0.f;
+                for (int j = lane; j < T; j += 32) {
+                    const float x = row[j];
+                    if (x != 0.0f || j == r) {
+                        const float a = (x + (j == r ? identity_w : 0.0f)) / den;
+                        row[j] = a;
+                        s += a;
+                    }
+                }
+                s = warp_sum(s);
+                for (int j = lane; j < T; j += 32) {
+                    const float a = row[j];
+                    if (a != 0.0f) row[j] = a / s;
                 }
             }
-            s = warp_sum(s);
-            for (int j = lane; j < T; j += 32) {
-                const float a = row[j];
-                if (a != 0.0f) row[j] = a / s;
+        } else {
+            // PPH_ROLLOUT=3 (NOT yet validated on a GPU: written after round 1's budget was spent).  ncu on the exact
+            // form: this step is 33 % of the kernel's instructions -- two IEEE divisions per entry that warp divergence
+            // makes every lane pay although 90 % of the entries are zero.  The 1/(1+w) factor cancels in the row
+            // normalisation, so a_ij = (x_ij + w d_ij) * (1 / (sum_j x_ij + w)): one reciprocal per row, one multiply
+            // per entry; differs from the reference's two roundings by <= 2 ulp (parity bar of this row: 1e-5).
+            for (int r = warp; r < T; r += kRoThreads / 32) {
+                float* row = M + r * T;
+                float s = 0.f;
+                for (int j = lane; j < T; j += 32) s += row[j];
+                s = warp_sum(s) + identity_w;
+                const float rs = 1.0f / s;
+                for (int j = lane; j < T; j += 32) row[j] = (row[j] + (j == r ? identity_w : 0.0f)) * rs;
             }
         }
         __syncthreads();
@@ -639,6 +655,8 @@ extern "C" int pph_rollout_scores(const float* const* attn_layers, int L, int B,
     const int n = T * T;
     // PPH_ROLLOUT=1 selects the first version of both kernels (kept for A/B measurements)
     static const bool use_v1 = [] { const char* e = getenv("PPH_ROLLOUT"); return e && e[0] == '1'; }();
+    // PPH_ROLLOUT=3: v2 kernels with the reciprocal-scale normalisation (unvalidated, see the kernel)
+    static const int norm_mode = [] { const char* e = getenv("PPH_ROLLOUT"); return (e && e[0] == '3') ? 1 : 0; }();
     const size_t smem1 = (size_t)((n + 3) & ~3) * 4 + 256 * 4 + (kRoThreads + 40) * 4;
     const size_t smem2 = (size_t)((n + 3) & ~3) * 4 + kRo2Bins * 4 + (kRoThreads + 40) * 4;
     const bool v1 = use_v1 || smem2 > 220 * 1024;
@@ -660,14 +678,21 @@ extern "C" int pph_rollout_scores(const float* const* attn_layers, int L, int B,
                  w.col_ptr, w.ent_val, w.ent_row);
         return launch_status("pph_rollout_scores(prepare)");
     };
+    auto go2 = [&](auto kern) -> int {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e != cudaSuccess) { set_error("pph_rollout_scores: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
+        launch_k(kern, grid, dim3(kRoThreads), smem, st, layers, L, B, H, T, k_discard, head_fusion, identity_w, w.cap,
+                 w.col_ptr, w.ent_val, w.ent_row, norm_mode);
+        return launch_status("pph_rollout_scores(prepare)");
+    };
     // head counts of the reference's backbones: DeiT-Ti 3, CaiT-XXS 4, DeiT-S 6 (deit_models_attn.py:288,303)
     int rc;
     if (v1)
         rc = H == 3 ? go(rollout_prepare_kernel<3>) : H == 4 ? go(rollout_prepare_kernel<4>)
              : H == 6 ? go(rollout_prepare_kernel<6>) : go(rollout_prepare_kernel<0>);
     else
-        rc = H == 3 ? go(rollout_prepare2_kernel<3>) : H == 4 ? go(rollout_prepare2_kernel<4>)
-             : H == 6 ? go(rollout_prepare2_kernel<6>) : go(rollout_prepare2_kernel<0>);
+        rc = H == 3 ? go2(rollout_prepare2_kernel<3>) : H == 4 ? go2(rollout_prepare2_kernel<4>)
+             : H == 6 ? go2(rollout_prepare2_kernel<6>) : go2(rollout_prepare2_kernel<0>);
     if (rc) return rc;
     // staged chain needs the layer's entry list in shared memory (cap * 6 B): small discard ratios fall back to v1
     const size_t csmem = (size_t)w.cap * 4 + (size_t)(T + 1) * 4 + (size_t)w.cap * 2 + 16;
