@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 
 from oracle import ref_harness  # noqa: E402
-from tests.util import FakeDeit  # noqa: E402
+from tests.util import FakeCait, FakeDeit  # noqa: E402
 
 # name: (B, N patches, dim, heads, depth, reserve_layer_nums, seed)
 CASES = {
@@ -32,6 +32,30 @@ def main():
         cls_embed, x_embed = torch.randn(B, 1, dim, generator=g), torch.randn(B, N, dim, generator=g)
         with torch.no_grad():
             x, (score, _) = dm.MyVisionTransformer.forward_feature_mask_train_direct(net, cls_embed, x_embed, None, reserve)
+        keep = reserve[-1][1]
+        srt = score.sort(dim=-1, descending=True)[0]
+        gap = ((srt[:, keep - 1] - srt[:, keep]) / srt[:, keep - 1].clamp_min(1e-30)).min().item()
+        np.savez_compressed(os.path.join(os.path.dirname(os.path.abspath(__file__)), name + ".npz"),
+                            x=x.numpy(), score=score.numpy(), sel_gap=np.float32(gap))
+        print(name, tuple(x.shape), tuple(score.shape), "selection gap %.2e" % gap)
+    cait()
+
+
+# name: (B, N patches, dim, heads, patch depth, token-only depth, reserve_layer_nums, seed)   -- cait_models_attn.py:310-343
+CAIT_CASES = {
+    "backbone_loop_cait": (3, 36, 32, 2, 5, 2, [(1, 16)], 3),
+}
+
+
+def cait():
+    import tools.cait_models_attn as cm
+    for name, (B, N, dim, heads, depth, depth_t, reserve, seed) in CAIT_CASES.items():
+        net = FakeCait(dim, heads, depth, depth_t)
+        net.attn_rollout_cait = types.MethodType(cm.MyCait.attn_rollout_cait, net)
+        g = torch.Generator().manual_seed(100 + seed)
+        cls_embed, x_embed = torch.randn(B, 1, dim, generator=g), torch.randn(B, N, dim, generator=g)
+        with torch.no_grad():
+            x, (score, _) = cm.MyCait.forward_feature_mask_train_direct(net, cls_embed, x_embed, None, reserve)
         keep = reserve[-1][1]
         srt = score.sort(dim=-1, descending=True)[0]
         gap = ((srt[:, keep - 1] - srt[:, keep]) / srt[:, keep - 1].clamp_min(1e-30)).min().item()

@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import rollout_oracle as R
-from tests.util import GOLDEN_DIR, FakeDeit, rel_close
+from tests.util import GOLDEN_DIR, FakeCait, FakeDeit, rel_close
 
 CASES = {
     "backbone_loop_small": (3, 36, 32, 2, 6, [(4, 16)], 1),
@@ -38,6 +38,29 @@ def test_backbone_loop_matches_reference_method(name):
     assert rel_close(x, g["x"], 1e-5, 1e-6)           # same kept tokens -> same masked attention in the later blocks
     patched = patch_deit_features(FakeDeit(dim, heads, depth))
     assert patched.forward_feature_mask_train_direct.__func__ is forward_feature_mask_train_direct
+
+
+def test_cait_backbone_loop_matches_reference_method():
+    """tools/cait_models_attn.py:310-343 through the reference's own method (fixture), oracle rollout injected."""
+    from protopformer_b200.backbone import forward_feature_mask_train_direct_cait, patch_cait_features
+    B, N, dim, heads, depth, depth_t, reserve, seed = 3, 36, 32, 2, 5, 2, [(1, 16)], 3
+    g = dict(np.load(os.path.join(GOLDEN_DIR, "backbone_loop_cait.npz")))
+    net = FakeCait(dim, heads, depth, depth_t)
+    gen = torch.Generator().manual_seed(100 + seed)
+    cls_embed, x_embed = torch.randn(B, 1, dim, generator=gen), torch.randn(B, N, dim, generator=gen)
+
+    def select(scores, K, want_int64=False):
+        idx = torch.topk(scores, k=K, dim=-1)[1].sort(dim=-1)[0]
+        return idx.int(), idx
+
+    with torch.no_grad():
+        x, (score, none) = forward_feature_mask_train_direct_cait(
+            net, cls_embed, x_embed, None, reserve, rollout_cait=lambda a, pre: R.rollout_cait(a, pre), select=select)
+    assert none is None and float(g["sel_gap"]) > 1e-4
+    assert rel_close(score, g["score"], 1e-5, 1e-9)
+    assert rel_close(x, g["x"], 1e-5, 1e-6)
+    patched = patch_cait_features(FakeCait(dim, heads, depth, depth_t))
+    assert patched.forward_feature_mask_train_direct.__func__ is forward_feature_mask_train_direct_cait
 
 
 @pytest.mark.gpu

@@ -96,3 +96,51 @@ class FakeDeit(torch.nn.Module):
         super().__init__()
         self.blocks = torch.nn.ModuleList([FakeAttnBlock(dim, heads, i) for i in range(depth)])
         self.norm = torch.nn.LayerNorm(dim)
+
+
+class FakeClassAttnBlock(torch.nn.Module):
+    """Seeded stand-in for CaiT's token-only block (tools/cait_models_attn.py:161-186 calling convention):
+    ``blk(x, cls_tokens, policy) -> (cls_tokens, attn (B,H,1,1+N))``; pruned tokens (policy 0) get no attention."""
+
+    def __init__(self, dim: int, heads: int, seed: int):
+        super().__init__()
+        g = torch.Generator().manual_seed(9500 + seed)
+        self.heads = heads
+        self.wq = torch.nn.Parameter(torch.randn(dim, dim, generator=g) / dim ** 0.5)
+        self.wk = torch.nn.Parameter(torch.randn(dim, dim, generator=g) / dim ** 0.5)
+        self.wv = torch.nn.Parameter(torch.randn(dim, dim, generator=g) / dim ** 0.5)
+
+    def forward(self, x, cls_tokens, policy=None):
+        u = torch.cat((cls_tokens, x), dim=1)
+        B, T, C = u.shape
+        H, hd = self.heads, C // self.heads
+        q = (cls_tokens @ self.wq).reshape(B, 1, H, hd).transpose(1, 2)
+        k = (u @ self.wk).reshape(B, T, H, hd).transpose(1, 2)
+        v = (u @ self.wv).reshape(B, T, H, hd).transpose(1, 2)
+        logits = (q @ k.transpose(-2, -1)) * (3.0 * hd ** -0.5)                    # (B,H,1,T)
+        e = torch.exp(logits - logits.max(dim=-1, keepdim=True)[0])
+        if policy is not None:
+            e = e * policy.reshape(B, 1, 1, T)
+        attn = e / e.sum(dim=-1, keepdim=True)
+        return cls_tokens + 0.5 * (attn @ v).transpose(1, 2).reshape(B, 1, C), attn
+
+
+class _PatchOnly(torch.nn.Module):
+    def __init__(self, blk):
+        super().__init__()
+        self.blk = blk
+
+    def forward(self, x):
+        B, T, _ = x.shape
+        return self.blk(x, torch.ones(B, T, 1, device=x.device))
+
+
+class FakeCait(torch.nn.Module):
+    """``blocks`` / ``blocks_token_only`` / ``norm`` / ``layer_nums``: what MyCait.forward_feature_mask_train_direct uses."""
+
+    def __init__(self, dim: int, heads: int, depth: int, depth_token_only: int):
+        super().__init__()
+        self.blocks = torch.nn.ModuleList([_PatchOnly(FakeAttnBlock(dim, heads, i)) for i in range(depth)])
+        self.blocks_token_only = torch.nn.ModuleList([FakeClassAttnBlock(dim, heads, i) for i in range(depth_token_only)])
+        self.norm = torch.nn.LayerNorm(dim)
+        self.layer_nums = [depth, depth_token_only]
