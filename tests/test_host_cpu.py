@@ -202,3 +202,21 @@ def test_similarity_launch_plan_visits_every_tile_exactly_once(mode):
     lib.pph_similarity_plan(1, 1024, 81, 192, 2000, 2000, 148, out, None)
     assert out[0] == 1 and out[7] == 128            # BF16X3 keeps the resident-prototype kernel by chunking the global branch
     assert lib.pph_similarity_plan(0, 64, 81, 192, 2000, 2000, 148, out, None) == -1
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU port of the reference head, the one bench leg that may execute oracle/) runs
+    without a GPU and prints ONE JSON line with the keys the driver reads."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "prototype_head_train_images_per_sec" and d["unit"] == "images/s"
+    for k in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+              "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in d, k
+    assert d["config"]["workload"] == "cub_b64" and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["value"] > 0
