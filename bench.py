@@ -454,6 +454,16 @@ def main():
         rate, n = cpu_port_rate(shape, 12.0, shape.B)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{n} training steps of the full {shape.B}-image batch ({WORKLOAD}), fp32, torch CPU"}
+        try:                              # per-core figure: same port on ONE thread, small sample
+            torch.set_num_threads(1)
+            rate1, n1 = cpu_port_rate(shape, 4.0, 8, iters_min=2)
+            cpu["value_1_core"] = rate1
+            cpu["sample_1_core"] = f"{n1} training steps of an 8-image slice, 1 thread"
+        except Exception as exc:
+            cpu["value_1_core"] = None
+            cpu["sample_1_core"] = f"failed: {exc}"
+        finally:
+            torch.set_num_threads(cores)
 
     if rank == 0:
         line = {
