@@ -54,6 +54,10 @@ SHAPES = {
     "cub_b64": HeadShape("cub_b64", 64, 196, 192, 192, 81, 2000, 2000, 200, 0.5, 1.0, 2.0),
     "dogs_b256": HeadShape("dogs_b256", 256, 196, 384, 384, 81, 1200, 600, 120, 0.5, 1.0, 2.0),
     "cars_b64": HeadShape("cars_b64", 64, 196, 192, 192, 121, 1960, 980, 196, 0.5, 1.0, 2.0),
+    # corners of the BASELINE config 5 sweep (tokens 49-196, dim 192/384) at fixture-sized batches
+    "sweep_k49": HeadShape("sweep_k49", 3, 196, 192, 192, 49, 1000, 500, 100, 0.5, 1.0, 2.0),
+    "sweep_k196": HeadShape("sweep_k196", 2, 196, 192, 192, 196, 1000, 1000, 100, 0.5, 1.0, 2.0),
+    "sweep_k144_d384": HeadShape("sweep_k144_d384", 2, 196, 384, 384, 144, 1000, 500, 100, 0.5, 1.0, 2.0),
     # small shapes the pure-python/float64 checks finish instantly on
     "tiny": HeadShape("tiny", 3, 16, 24, 16, 9, 20, 8, 4, 0.3, 0.2, 1.5),
     "small": HeadShape("small", 5, 49, 40, 32, 25, 60, 30, 6, 0.5, 0.5, 2.0),

@@ -34,6 +34,10 @@ CASES = [
     ("cub_b8_s2_matched", "cub_b8", None, 2, "matched", "log"),
     ("cars_b4_s1", "cars_b64", 4, 1, "init", "log"),
     ("dogs_b4_s1", "dogs_b256", 4, 1, "init", "log"),
+    # sweep corners (tests/util.EXTRA_GOLDEN_CASES): every token of the image kept (K = N), few tokens, wide features
+    ("sweep_k49_s1", "sweep_k49", None, 1, "init", "log"),
+    ("sweep_k196_s1", "sweep_k196", None, 1, "init", "log"),
+    ("sweep_k144_d384_s1", "sweep_k144_d384", None, 1, "init", "log"),
 ]
 FULL = {"tiny", "small"}
 ROW_STRIDE = 16
@@ -76,7 +80,10 @@ def pack(name, shape, seed, mode, fn):
 def main():
     if not ref_harness.reference_available():
         raise SystemExit("reference tree not available; fixtures can only be produced in the build container")
+    only = set(sys.argv[1:])
     for name, key, b, seed, mode, fn in CASES:
+        if only and name not in only:
+            continue
         shape = synth.SHAPES[key]
         if b is not None:
             shape = shape.with_batch(b)

@@ -4,7 +4,9 @@ import pytest
 import torch
 
 from oracle import protohead_oracle as O
-from tests.util import GOLDEN_CASES, argmax_mismatch_outside_near_ties, load_golden, norm_rel, rel_close
+from tests.util import EXTRA_GOLDEN_CASES, GOLDEN_CASES, argmax_mismatch_outside_near_ties, load_golden, norm_rel, rel_close
+
+ALL_CASES = list(GOLDEN_CASES) + list(EXTRA_GOLDEN_CASES)
 
 FULL = ("tiny", "small")
 
@@ -16,7 +18,7 @@ def _rtol(name):
     return 1e-3 if "matched" in name else 1e-4
 
 
-@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+@pytest.mark.parametrize("name", ALL_CASES)
 def test_forward_matches_reference_fixture(name):
     shape, case, g, fn = load_golden(name)
     out = O.head_forward(case, shape.K, shape.global_coe, fn)
@@ -30,7 +32,7 @@ def test_forward_matches_reference_fixture(name):
     assert rel_close(out["dist_map"][:, ::stride], g["dist_map"], _rtol(name))
 
 
-@pytest.mark.parametrize("name", list(GOLDEN_CASES))
+@pytest.mark.parametrize("name", ALL_CASES)
 def test_train_step_matches_reference_fixture(name):
     shape, case, g, fn = load_golden(name)
     # route the oracle's pooling through the reference's own arg-max so near-ties cannot re-route gradients
