@@ -107,7 +107,8 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 def cpu_port_rate(shape, budget_s: float, sample_B: int, iters_min: int = 3):
     """images/s of RefStyleHead.train_step on a `sample_B`-image slice of the workload, within ~budget_s."""
-    from oracle import protohead_oracle as O, synth
+    from oracle import protohead_oracle as O
+    from protopformer_b200 import synth
     s = shape.with_batch(sample_B)
     case = synth.make_case(s, seed=1)
     head = O.RefStyleHead(case, s)
@@ -122,7 +123,8 @@ def cpu_port_rate(shape, budget_s: float, sample_B: int, iters_min: int = 3):
 
 
 def run_reference_arm(args):
-    from oracle import protohead_oracle as O, synth
+    from oracle import protohead_oracle as O
+    from protopformer_b200 import synth
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -237,7 +239,7 @@ def main():
         return run_reference_arm(args)
 
     import torch.distributed as dist
-    from oracle import synth                       # synthetic input generator (bench infrastructure)
+    from protopformer_b200 import synth                       # synthetic input generator (bench infrastructure)
     from protopformer_b200 import _lib, ops
     from protopformer_b200.graph import GraphedHeadStep
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PPH_VERSION 100
+#define PPH_VERSION 200
 
 /* argument errors */
 #define PPH_EINVAL   (-1)   /* bad dimension / null pointer */
@@ -245,6 +245,72 @@ int pph_rollout_cls_rows(const float* const* cls_layers /* host array of device 
 int pph_class_maps(const float* Zs, const float* z2s, const float* Pl, const float* p2l,
                    const int32_t* idx32, const int64_t* labels, int B, int K, int D, int P, int m, int N,
                    int act_fn, float eps, float* maps, pph_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Fused training / inference step (round 2): the same path in FIVE launches
+ *   pph_head_prep -> pph_similarity_fwd -> pph_head_mid -> pph_similarity_bwd2 -> pph_addon_bwd2
+ * (tools/engine_proto.py:49-76 for the head: forward, cross-entropy, PPC loss, backward).  The modular entry points
+ * above remain the operator-level API (autograd functions of the drop-in PPNet) and the fallback for shapes these
+ * kernels were not built for (every *_supported() below answers on the host, without a device).
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* (a1)+(a2)+operand preparation in one launch: pph_select_topk (NaN scores rank first, as torch.topk) -> pph_addon_fwd
+ * for scores [B,H,N], tokens [B,1+N,Din]; plus pph_split_rows of Pl [P,D] and Pgl [Pg,D] (either may be NULL / 0 rows).
+ * Outputs as documented at those entry points; idx64 and all bf16 / *_ctr / *_hi outputs may be NULL. */
+int pph_head_prep_supported(int B, int N, int Din, int D, int K);
+int pph_head_prep(const float* scores, const float* tokens, const float* Wa, const float* ba,
+                  int B, int H, int N, int Din, int D, int K, float center,
+                  int32_t* idx32, int64_t* idx64,
+                  float* Zs, float* Zc, float* z2s, float* z2c, float* z2s_ctr, float* z2c_ctr,
+                  float* z2s_hi, float* z2c_hi, uint16_t* Zs_hi, uint16_t* Zs_lo, uint16_t* Zc_hi, uint16_t* Zc_lo,
+                  const float* Pl, int P, uint16_t* Pl_hi, uint16_t* Pl_lo, float* p2l, float* p2l_ctr, float* p2l_hi,
+                  const float* Pgl, int Pg, uint16_t* Pg_hi, uint16_t* Pg_lo, float* p2g, float* p2g_ctr, float* p2g_hi,
+                  pph_stream_t stream);
+
+/* (a6) + loss tail + (a8 part 1) [+ token bins of (a8 part 2)] [+ (a7) PPC loss forward and backward] in one launch:
+ *   logits / logits_g / logits_l [B,C] as pph_logits_fwd; losses[4] = (ce + cov_coe*cov + mean_coe*mean, ce, cov, mean) as
+ *   pph_loss_tail + pph_loss_combine (cov = mean = 0 when use_ppc = 0); and, when train != 0:
+ *   dlogits [B,C]; g_l [B,P], g_g [B,Pg] as pph_logits_bwd (no upstream gradient on logits_global/local);
+ *   pairT [(P+Pg)][Bp][2] fp32, Bp = B rounded up to 64: (g, bit pattern of the int32 token slot) per (prototype, image),
+ *   token slot K (= the CLS row) for global prototypes, zeros for images >= B;
+ *   the token bins of pph_similarity_bwd2 in bwd_workspace (pph_similarity_bwd2_ws_bytes);
+ *   with use_ppc: dZs_ppc [B,K,D] = d(cov_coe*cov + mean_coe*mean)*upstream / dZs (OVERWRITTEN) and
+ *   dP_img [B,m,D] = the same gradient w.r.t. the m label-class prototype rows, per image (summed over the images of a
+ *   class by pph_similarity_bwd2 in image order: deterministic).
+ * workspace: pph_head_mid_ws_bytes() bytes, ZERO-FILLED once before first use (grid-barrier and ticket counters, all
+ * self-resetting).  C <= 256; B <= 64 * (SM count / 2).  Out-of-range labels are clamped. */
+int pph_head_mid_ws_bytes(int B, int K, int D, int P, int Pg, int C, int m, long long* bytes /* host */);
+int pph_head_mid(const float* act_l, const float* act_g, const float* dmin_l, const float* dmin_g,
+                 const int32_t* argmin_l, const float* Wl, const float* Wg, const int64_t* labels,
+                 int B, int K, int D, int P, int Pg, int C, int m, int N,
+                 float global_coe, int act_fn, float eps, float upstream, int train,
+                 int use_ppc, const float* Zs, const float* z2s, const float* Pl, const float* p2l,
+                 const int32_t* idx32, float cov_thresh, float mean_thresh, float cov_coe, float mean_coe,
+                 void* workspace, void* bwd_workspace,
+                 float* logits, float* logits_g, float* logits_l, float* losses, float* dlogits,
+                 float* g_l, float* g_g, float* pairT, float* dZs_ppc, float* dP_img, pph_stream_t stream);
+
+/* (a8 part 2), second implementation: same results as pph_similarity_bwd(PPH_BWD_GRADS) from operands staged in shared
+ * memory by 16-float feature slices (no L2 row gathers), every row summed in a fixed order.  g_l / g_g / pairT and the
+ * bins in bwd_workspace come from pph_head_mid.  add_dZs [B,K,D] (or NULL) is added to dZs; dP_img [B,m,D] (or NULL;
+ * needs labels [B] int64 and m) is added to the label-class rows of dPl.  D % 16 == 0. */
+int pph_similarity_bwd2_supported(int B, int K, int D, int P, int Pg);
+int pph_similarity_bwd2_ws_bytes(int B, int K, int P, long long* bytes /* host */);
+int pph_similarity_bwd2(const float* g_l, const float* g_g, const float* pairT, const void* bwd_workspace,
+                        const float* Zs, const float* Zc, const float* Pl, const float* Pgl,
+                        int B, int K, int D, int P, int Pg, int m,
+                        const float* add_dZs, const float* dP_img, const int64_t* labels,
+                        float* dZs, float* dZc, float* dPl, float* dPg, pph_stream_t stream);
+
+/* (a8 part 3), second implementation: pph_addon_bwd(PPH_ADDON_WGRAD | PPH_ADDON_DGRAD) in one launch, exact FP32,
+ * deterministic.  dtokens may be NULL (no gradient to the backbone).  workspace: pph_addon_bwd2_ws_bytes() bytes,
+ * ZERO-FILLED once before first use.  Din % 8 == 0, D % 4 == 0. */
+int pph_addon_bwd2_supported(int B, int N, int Din, int D, int K);
+int pph_addon_bwd2_ws_bytes(int B, int N, int Din, int D, int K, long long* bytes /* host */);
+int pph_addon_bwd2(const float* tokens, const int32_t* idx32, const float* Wa,
+                   const float* Zs, const float* Zc, const float* dZs, const float* dZc,
+                   int B, int N, int Din, int D, int K, void* workspace,
+                   float* dWa, float* dba, float* dtokens, pph_stream_t stream);
 
 #ifdef __cplusplus
 }

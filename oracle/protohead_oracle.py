@@ -3,7 +3,7 @@
 This file is a from-scratch CPU restatement (torch CPU tensors, fp32 or float64) of the reference algorithm
 in ``/root/reference/protopformer.py``.  It is the checker the CUDA path is compared against.  Only ``tests/``,
 ``__graft_entry__.smoke()`` and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it;
-the product package ``protopformer_b200`` never does (tests/test_no_oracle_in_product.py enforces that).
+the product package ``protopformer_b200`` never does (tests/test_host_cpu.py::test_product_never_imports_the_oracle enforces that).
 
 Parity pin: the reference ships no tests or golden vectors for this path.  The pin is the
 reference's own code, imported unmodified in the build container by ``tests/golden/make_golden.py`` (through

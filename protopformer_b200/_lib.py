@@ -45,6 +45,17 @@ SIGNATURES = {
     "pph_class_maps": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p],
     "pph_addon_bwd_ws_bytes": [_i, _i, _i, _i, _i, C.POINTER(C.c_longlong)],
     "pph_addon_bwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _i, _p, _p, _p, _p],
+    # fused step (round 2)
+    "pph_head_prep_supported": [_i, _i, _i, _i, _i],
+    "pph_head_prep": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f] + [_p] * 14 + [_p, _i, _p, _p, _p, _p, _p] * 2 + [_p],
+    "pph_head_mid_ws_bytes": [_i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_longlong)],
+    "pph_head_mid": [_p] * 8 + [_i] * 8 + [_f, _i, _f, _f, _i, _i] + [_p] * 5 + [_f] * 4 + [_p] * 13,
+    "pph_similarity_bwd2_supported": [_i, _i, _i, _i, _i],
+    "pph_similarity_bwd2_ws_bytes": [_i, _i, _i, C.POINTER(C.c_longlong)],
+    "pph_similarity_bwd2": [_p] * 8 + [_i] * 6 + [_p] * 8,
+    "pph_addon_bwd2_supported": [_i, _i, _i, _i, _i],
+    "pph_addon_bwd2_ws_bytes": [_i, _i, _i, _i, _i, C.POINTER(C.c_longlong)],
+    "pph_addon_bwd2": [_p] * 7 + [_i] * 5 + [_p] * 5,
 }
 _RESTYPES = {"pph_last_error_string": C.c_char_p}
 

@@ -74,6 +74,52 @@ __device__ __forceinline__ void pdl_sync() {
     pdl_wait();
 }
 
+// ---- cp.async (LDGSTS): 16-byte global -> shared copies that bypass the register file ---------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---- grid-wide barrier for kernels whose CTAs are all co-resident (grid <= SM count x resident CTAs per SM) ------
+// `counter` counts arrivals monotonically inside one launch (barrier i releases at i * n_ctas); the kernel's
+// finisher (grid_finish) resets it, so a CUDA-graph replay starts from zero again.  The spin is bounded: a protocol
+// bug traps (launch error reported to the caller) instead of hanging the device.
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        const long long t0 = clock64();
+        while (ld_acquire_u32(counter) < target) {
+            if (clock64() - t0 > 4000000000LL) __trap();
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+// Called by every participating CTA after its last barrier: the last one to arrive zeroes both counters.
+__device__ __forceinline__ void grid_finish(unsigned int* counter, unsigned int* done, unsigned int n_ctas) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(done, 1u) == n_ctas - 1u) {
+            *counter = 0u;
+            *done = 0u;
+            __threadfence();
+        }
+    }
+}
+__device__ __forceinline__ float4 ldcg4(const float* p) { return __ldcg(reinterpret_cast<const float4*>(p)); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -277,10 +277,12 @@ __device__ __forceinline__ void ro_emit_topk(const float* sc, int W, int K, int3
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     bool sel = false;
     if (tid < W) {
-        const float v = sc[tid];
+        float v = sc[tid];
+        if (v != v) v = INFINITY;          // NaN ranks first (torch.topk); with the index tie-break: a total order
         int rank = 0;
         for (int j = 0; j < W; ++j) {
-            const float q = sc[j];
+            float q = sc[j];
+            if (q != q) q = INFINITY;
             rank += (q > v) || (q == v && j < tid);
         }
         sel = rank < K;
@@ -292,8 +294,10 @@ __device__ __forceinline__ void ro_emit_topk(const float* sc, int W, int K, int3
         int off = 0;
         for (int w = 0; w < warp; ++w) off += wcnt[w];
         const int pos = off + __popc(m & ((1u << lane) - 1u));
-        idx32[pos] = tid;
-        if (idx64) idx64[pos] = tid;
+        if (pos < K) {
+            idx32[pos] = tid;
+            if (idx64) idx64[pos] = tid;
+        }
     }
 }
 

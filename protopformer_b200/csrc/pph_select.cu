@@ -30,6 +30,7 @@ select_topk_kernel(const float* __restrict__ scores, int H, int N, int K,
             float a = sc[n];
             for (int h = 1; h < H; ++h) a += sc[(size_t)h * N + n];
             v = H > 1 ? a / (float)H : a;      // torch.mean = sum / count
+            if (v != v) v = INFINITY;          // NaN ranks first (torch.topk); with the index tie-break: a total order
         }
         s[n] = v;
     }
@@ -60,8 +61,10 @@ select_topk_kernel(const float* __restrict__ scores, int H, int N, int K,
         for (int w = 0; w < kSelThreads / 32; ++w) total += warp_cnt[w];
         if (sel) {
             const int pos = off + __popc(m & ((1u << lane) - 1u));
-            idx32[(size_t)b * K + pos] = n;
-            if (idx64) idx64[(size_t)b * K + pos] = n;
+            if (pos < K) {                     // a total order selects exactly K; the guard keeps a bug inside the row
+                idx32[(size_t)b * K + pos] = n;
+                if (idx64) idx64[(size_t)b * K + pos] = n;
+            }
         }
         base += total;
         __syncthreads();

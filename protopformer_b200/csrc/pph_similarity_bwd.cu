@@ -9,93 +9,16 @@
 //   bin_tokens_kernel : per image, stable counting sort of the prototypes by argmin token (one warp, match.any) ->
 //                       deterministic bins, so every gradient row is summed in a fixed order (bit-reproducible).
 #include "pph_common.cuh"
+#include "pph_bins.cuh"
 
 namespace pph {
-
-// ---- binning ---------------------------------------------------------------------------------------------------
-// Stable counting sort of an image's prototypes by argmin token.  8 warps own 8 contiguous prototype ranges:
-// pass A builds per-warp histograms (match.any groups equal tokens inside a 32-prototype step), an exclusive scan
-// over (token, warp) turns them into per-warp write cursors, pass B replays the same steps and places every
-// prototype -> inside a bin prototypes are in ascending order, independent of scheduling (deterministic sums).
-// Also emits, per token, the first work item of the bin when bins are cut into chunks of kBinChunk entries.
-constexpr int kBinChunk = 32;
 
 __global__ void __launch_bounds__(256)
 bin_tokens_kernel(const int32_t* __restrict__ argmin_l, int K, int P, int32_t* __restrict__ bin_start,
                   int32_t* __restrict__ item_start, int32_t* __restrict__ bin_list) {
     pdl_sync();
     extern __shared__ int smi[];
-    int* hist = smi;                      // [8][K]   per-warp histogram, then per-warp cursor
-    int* tot = smi + 8 * K;               // [K+1]    bin offsets
-    int* itm = tot + K + 1;               // [K+1]    work-item offsets
-    const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int32_t* am = argmin_l + (size_t)b * P;
-    const int per = ((P + 7) / 8 + 31) & ~31;            // prototypes per warp, multiple of 32
-    const int pa = warp * per, pb = min(P, pa + per);
-    for (int i = tid; i < 8 * K; i += 256) hist[i] = 0;
-    __syncthreads();
-    for (int p0 = pa; p0 < pb; p0 += 32) {               // pass A
-        const int p = p0 + lane;
-        const bool valid = p < pb;
-        const int a = valid ? __ldg(am + p) : -1 - lane;
-        const unsigned peers = __match_any_sync(0xffffffffu, a);
-        if (valid && lane == __ffs(peers) - 1) hist[warp * K + a] += __popc(peers);
-        __syncwarp();
-    }
-    __syncthreads();
-    if (warp == 0) {                                      // scan over tokens of the 8-warp totals
-        int carry = 0, icarry = 0;
-        for (int k0 = 0; k0 < K; k0 += 32) {
-            const int k = k0 + lane;
-            int n = 0;
-            if (k < K)
-                for (int w = 0; w < 8; ++w) n += hist[w * K + k];
-            int v = n, c = (n + kBinChunk - 1) / kBinChunk;
-            if (k < K && c == 0) c = 1;                   // empty bins still own one item (they write zeros)
-            int ci = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int u = __shfl_up_sync(0xffffffffu, v, o);
-                const int ui = __shfl_up_sync(0xffffffffu, ci, o);
-                if (lane >= o) { v += u; ci += ui; }
-            }
-            if (k < K) { tot[k] = carry + v - n; itm[k] = icarry + ci - c; }
-            carry += __shfl_sync(0xffffffffu, v, 31);
-            icarry += __shfl_sync(0xffffffffu, ci, 31);
-        }
-        if (lane == 0) { tot[K] = carry; itm[K] = icarry; }
-    }
-    __syncthreads();
-    for (int k = tid; k < K; k += 256) {                  // per-warp cursors: bin offset + counts of earlier warps
-        int run = tot[k];
-        for (int w = 0; w < 8; ++w) {
-            const int n = hist[w * K + k];
-            hist[w * K + k] = run;
-            run += n;
-        }
-    }
-    for (int k = tid; k <= K; k += 256) {
-        bin_start[(size_t)b * (K + 1) + k] = tot[k];
-        item_start[(size_t)b * (K + 1) + k] = itm[k];
-    }
-    __syncthreads();
-    int32_t* list = bin_list + (size_t)b * P;
-    for (int p0 = pa; p0 < pb; p0 += 32) {               // pass B
-        const int p = p0 + lane;
-        const bool valid = p < pb;
-        const int a = valid ? __ldg(am + p) : -1 - lane;
-        const unsigned peers = __match_any_sync(0xffffffffu, a);
-        const int rank = __popc(peers & ((1u << lane) - 1u));
-        const int leader = __ffs(peers) - 1;
-        int base = 0;
-        if (valid && lane == leader) {
-            base = hist[warp * K + a];
-            hist[warp * K + a] = base + __popc(peers);
-        }
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (valid) list[base + rank] = p;
-        __syncwarp();
-    }
+    bin_tokens_body(blockIdx.x, argmin_l, K, P, bin_start, item_start, bin_list, smi);
 }
 
 // ---- gather kernels (templated on DV = ceil(D / 32) register slots per lane) ---------------------------------------

@@ -460,8 +460,9 @@ def ppc_loss(cfg: HeadConfig, tf: TokenFeatures, P, p2l, labels, m: int, N: int)
 # Fused training / inference step: the same entry points in a fixed sequence over pre-allocated buffers, no autograd
 # graph and no PyTorch glue kernels in between (what tools/engine_proto.py:49-76 amounts to for the head).
 # ------------------------------------------------------------------------------------------------------------------
-class FusedHeadStep:
-    """forward (+ PPC + cross-entropy + backward) of the head for a fixed shape.
+class FusedHeadStepV1:
+    """Round-1 launch sequence (16 launches over three streams), kept as the fallback for shapes the five-launch step
+    was not built for and as an A/B arm.  forward (+ PPC + cross-entropy + backward) of the head for a fixed shape.
 
     step(tokens, scores, labels, Wa, ba, P, Pg, Wl, Wg, grads) launches, in order:
       select_topk, addon_fwd, split_rows x2, similarity_fwd, logits_fwd, [ppc_fwd,] loss_tail,
@@ -615,4 +616,115 @@ class FusedHeadStep:
         c("pph_addon_bwd", tokens, self.idx32, Wa, self.Zs, self.Zc, self.dZs, self.dZc, B, N, Din, D, K,
           self.ws_addon, 1, grads["Wa"], grads["ba"], None)
         main.wait_event(ev[6])
+        return self.losses
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Five-launch step (round 2): head_prep -> similarity_fwd -> head_mid -> similarity_bwd2 -> addon_bwd2 on ONE stream
+# ------------------------------------------------------------------------------------------------------------------
+def _ws(fn: str, *dims, zero: bool, device) -> torch.Tensor:
+    import ctypes
+    n = ctypes.c_longlong(0)
+    if getattr(_lib.load(), fn)(*dims, ctypes.byref(n)) != 0:
+        raise RuntimeError(f"{fn} failed: {_lib.load().pph_last_error_string().decode()}")
+    alloc = torch.zeros if zero else torch.empty
+    return alloc(max(int(n.value), 256), dtype=torch.uint8, device=device)
+
+
+def fused_step_supported(B, N, Din, D, K, P, Pg, C, m) -> bool:
+    """Host-side check (no device needed): can the five-launch step run this shape?"""
+    lib = _lib.load()
+    if C > 256 or B < 1 or B > 64 * 74:
+        return False
+    ppc_smem = 4 * (m * D + K * (D + 4) + 2 * m * K + 8 * m + 8)
+    return bool(lib.pph_head_prep_supported(B, N, Din, D, K) and lib.pph_similarity_bwd2_supported(B, K, D, P, Pg)
+                and lib.pph_addon_bwd2_supported(B, N, Din, D, K) and ppc_smem <= 200 * 1024 and D % 4 == 0)
+
+
+class FusedHeadStep:
+    """forward (+ PPC + cross-entropy + backward) of the head for a fixed shape in five launches on the current stream:
+
+      pph_head_prep        selection + gather + add-on + sigmoid + bf16 operands (tokens and both prototype tensors)
+      pph_similarity_fwd   tcgen05 distances, log similarity, min / argmin over tokens (the (B,P,K) map stays in TMEM)
+      pph_head_mid         last layers + cross-entropy + last-layer backward || token bins || PPC loss fwd + bwd
+      pph_similarity_bwd2  dP, dPg, dZs, dZc (+ the PPC gradients)              [training]
+      pph_addon_bwd2       dWa, dba, dtokens                                    [training]
+
+    Same results interface as FusedHeadStepV1: losses (4,) = (total, ce, ppc_cov, ppc_mean), logits, logits_g, logits_l,
+    act_l, dmin_l, argmin, idx32, dtokens; parameter gradients are OVERWRITTEN in the tensors of `grads`
+    (keys Wa, ba, P, Pg -- e.g. views of one flat all-reduce buffer).  Reference: tools/engine_proto.py:49-76."""
+
+    def __init__(self, cfg: HeadConfig, B, N, Din, D, P, Pg, C, m, device, heads: int = 0, ppc_cov_coe: float = 0.1,
+                 ppc_mean_coe: float = 0.5, train: bool = True, use_ppc: bool = True, schedule=None):
+        if not fused_step_supported(B, N, Din, D, cfg.K, P, Pg, C, m):
+            raise ValueError("shape outside the five-launch step: use FusedHeadStepV1")
+        self.cfg, self.train, self.use_ppc = cfg, train, use_ppc
+        self.dims = (B, N, Din, D, P, Pg, C, m, heads)
+        self.cov_coe, self.mean_coe = float(ppc_cov_coe), float(ppc_mean_coe)
+        K = cfg.K
+        f32, bf, i32 = torch.float32, torch.bfloat16, torch.int32
+        e = lambda *s, dt=f32: torch.empty(s, dtype=dt, device=device)  # noqa: E731
+        self.split = cfg.mode_id != _lib.MODE_FP32_FMA
+        self.idx32 = e(B, K, dt=i32)
+        self.Zs, self.Zc, self.z2s, self.z2c = e(B, K, D), e(B, D), e(B, K), e(B)
+        names = ("z2s_ctr", "z2c_ctr", "z2s_hi", "z2c_hi", "Zs_hi", "Zs_lo", "Zc_hi", "Zc_lo", "P_hi", "P_lo", "Pg_hi",
+                 "Pg_lo", "p2_ctr", "p2_hi", "pg2_ctr", "pg2_hi")
+        if self.split:
+            shapes = ((B, K), (B,), (B, K), (B,), (B * K, D), (B * K, D), (B, D), (B, D), (P, D), (P, D), (Pg, D), (Pg, D),
+                      (P,), (P,), (Pg,), (Pg,))
+            for n, sh in zip(names, shapes):
+                setattr(self, n, e(*sh, dt=bf if ("_hi" in n or "_lo" in n) and n[0] in "ZP" else f32))
+        else:
+            for n in names:
+                setattr(self, n, None)
+        self.p2, self.pg2 = e(P), e(Pg)
+        self.dmin_l, self.act_l, self.argmin = e(B, P), e(B, P), e(B, P, dt=i32)
+        self.dmin_g, self.act_g = e(B, Pg), e(B, Pg)
+        self.logits, self.logits_g, self.logits_l = e(B, C), e(B, C), e(B, C)
+        self.losses = torch.zeros(4, dtype=f32, device=device)
+        self.ws_mid = _ws("pph_head_mid_ws_bytes", B, K, D, P, Pg, C, m, zero=True, device=device)
+        self.dlogits = self.g_l = self.g_g = self.pairT = self.ws_bins = None
+        self.dZs_ppc = self.dP_img = None
+        if train:
+            Bp = (B + 63) // 64 * 64
+            self.dlogits, self.g_l, self.g_g = e(B, C), e(B, P), e(B, Pg)
+            self.pairT = e(P + Pg, Bp, 2)
+            self.ws_bins = _ws("pph_similarity_bwd2_ws_bytes", B, K, P, zero=False, device=device)
+            if use_ppc:
+                self.dZs_ppc, self.dP_img = e(B, K, D), e(B, m, D)
+            self.dZs, self.dZc = e(B, K, D), e(B, D)
+            self.dtokens = e(B, 1 + N, Din)
+            self.ws_addon = _ws("pph_addon_bwd2_ws_bytes", B, N, Din, D, K, zero=True, device=device)
+
+    def step(self, tokens, scores, labels, Wa, ba, P, Pg, Wl, Wg, grads=None, upstream: float = 1.0):
+        B, N, Din, D, Pn, Pgn, C, m, H = self.dims
+        cfg, K = self.cfg, self.cfg.K
+        c = _lib.call
+        c("pph_head_prep", scores, tokens, Wa, ba, B, max(H, 1), N, Din, D, K, float(cfg.center), self.idx32, None,
+          self.Zs, self.Zc, self.z2s, self.z2c, self.z2s_ctr, self.z2c_ctr, self.z2s_hi, self.z2c_hi,
+          self.Zs_hi, self.Zs_lo, self.Zc_hi, self.Zc_lo,
+          P, Pn, self.P_hi, self.P_lo, self.p2, self.p2_ctr, self.p2_hi,
+          Pg, Pgn, self.Pg_hi, self.Pg_lo, self.pg2, self.pg2_ctr, self.pg2_hi)
+        mode = cfg.mode_id
+        sel = {_lib.MODE_FP32_FMA: 0, _lib.MODE_BF16X3: 1, _lib.MODE_BF16: 2}[mode]
+        c("pph_similarity_fwd", mode, cfg.act_id, float(cfg.eps), B, K, D, Pn, Pgn, self.Zs, self.Zc,
+          (self.z2s, self.z2s_ctr, self.z2s_hi)[sel], (self.z2c, self.z2c_ctr, self.z2c_hi)[sel],
+          self.Zs_hi, self.Zs_lo, self.Zc_hi, self.Zc_lo, P, Pg,
+          (self.p2, self.p2_ctr, self.p2_hi)[sel], (self.pg2, self.pg2_ctr, self.pg2_hi)[sel],
+          self.P_hi, self.P_lo, self.Pg_hi, self.Pg_lo,
+          self.dmin_l, self.argmin, self.act_l, self.dmin_g, self.act_g, None, None)
+        ppc = self.use_ppc and self.train
+        c("pph_head_mid", self.act_l, self.act_g, self.dmin_l, self.dmin_g, self.argmin, Wl, Wg, labels,
+          B, K, D, Pn, Pgn, C, m, N, float(cfg.global_coe), cfg.act_id, float(cfg.eps), float(upstream),
+          1 if self.train else 0, 1 if ppc else 0, self.Zs, self.z2s, P, self.p2, self.idx32,
+          float(cfg.ppc_cov_thresh), float(cfg.ppc_mean_thresh), self.cov_coe, self.mean_coe,
+          self.ws_mid, self.ws_bins, self.logits, self.logits_g, self.logits_l, self.losses, self.dlogits,
+          self.g_l, self.g_g, self.pairT, self.dZs_ppc if ppc else None, self.dP_img if ppc else None)
+        if not self.train:
+            return self.losses
+        c("pph_similarity_bwd2", self.g_l, self.g_g, self.pairT, self.ws_bins, self.Zs, self.Zc, P, Pg,
+          B, K, D, Pn, Pgn, m, self.dZs_ppc if ppc else None, self.dP_img if ppc else None, labels if ppc else None,
+          self.dZs, self.dZc, grads["P"], grads["Pg"])
+        c("pph_addon_bwd2", tokens, self.idx32, Wa, self.Zs, self.Zc, self.dZs, self.dZc, B, N, Din, D, K,
+          self.ws_addon, grads["Wa"], grads["ba"], self.dtokens)
         return self.losses

@@ -2,7 +2,7 @@
 
 Every tensor is drawn from an explicit ``torch.Generator`` so the same (shape, seed) pair yields the same
 bytes in this container (where the golden fixtures are produced from the real reference) and on the GPU box
-(where only the oracle restatement and the CUDA path run).  Distributions follow SURVEY.md §8(d):
+(where only the CPU restatement and the CUDA path run).  Distributions follow SURVEY.md §8(d):
 
 * tokens  (B, 1+N, Din)  ~ N(0,1)              -- LayerNorm-like backbone output (protopformer.py:155)
 * scores  (B, N)         per-image permutation  -- exactly tie-free CLS-attention rollout (protopformer.py:157)

@@ -1,0 +1,30 @@
+#!/bin/bash
+# Stages run on the GPU box through gpurun (outputs under gpurun_out/):  bash scripts/gpu.sh <stage> [...]
+mkdir -p gpurun_out
+for stage in "$@"; do
+case $stage in
+  step2)      # new kernels, one pytest process per kernel so a device trap in one does not poison the others
+    for k in head_prep head_mid similarity_bwd2 addon_bwd2 "five_launch or benchmarked"; do
+      n=$(echo $k | tr ' ' '_')
+      timeout 600 python -m pytest tests/test_step2_gpu.py -q --tb=short -k "$k" > gpurun_out/t_$n.log 2>&1
+      echo "== $k: rc=$? $(tail -1 gpurun_out/t_$n.log)"
+    done ;;
+  times)
+    timeout 300 python scripts/step_times.py cub_b64 fp32 > gpurun_out/times_b64.json 2> gpurun_out/times_b64.err; tail -c 1500 gpurun_out/times_b64.json
+    timeout 300 python scripts/step_times.py cub_b64 fp32 1024 > gpurun_out/times_b1024.json 2> gpurun_out/times_b1024.err; tail -c 1500 gpurun_out/times_b1024.json ;;
+  sanitize)
+    timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_step2_gpu.py -q --tb=line \
+        -k "tiny or small or cub_b8" > gpurun_out/sanitize.log 2>&1
+    echo "== sanitize rc=$?"; grep -E "ERROR SUMMARY|Invalid|passed|failed" gpurun_out/sanitize.log | head -20 ;;
+  all)
+    timeout 1500 python -m pytest tests -q -m gpu --tb=short > gpurun_out/t_all.log 2>&1; echo "== all: rc=$? $(tail -1 gpurun_out/t_all.log)" ;;
+  bench)
+    timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json ;;
+  smoke)
+    timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3 ;;
+  launches)
+    timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -s 200 -c 60 --csv \
+        --log-file gpurun_out/launches.csv python bench.py --steps 20 --warmup 5 --no-cpu --no-aux > gpurun_out/launches.log 2>&1
+    echo "== launches rc=$?" ;;
+esac
+done

@@ -2,7 +2,7 @@
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import synth
+from protopformer_b200 import synth
 from protopformer_b200 import ops
 
 dev = torch.device("cuda:0")

@@ -3,7 +3,7 @@ import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import torch.nn.functional as F
-from oracle import synth
+from protopformer_b200 import synth
 from protopformer_b200 import ops, _lib
 
 key = sys.argv[1] if len(sys.argv) > 1 else "cub_b64"

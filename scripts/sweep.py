@@ -4,7 +4,7 @@ replays and reports images/s plus the tensor-roofline fraction of the similarity
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import synth
+from protopformer_b200 import synth
 from protopformer_b200 import ops
 from protopformer_b200.graph import GraphedHeadStep
 

@@ -1,7 +1,7 @@
 import os, sys, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from oracle import synth
+from protopformer_b200 import synth
 from protopformer_b200 import ops, _lib
 dev = torch.device("cuda:0")
 s = synth.SHAPES["cub_b64"]

@@ -22,7 +22,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
-from oracle import ref_harness, synth  # noqa: E402
+from oracle import ref_harness  # noqa: E402
+from protopformer_b200 import synth  # noqa: E402
 
 # name, shape key, batch override, seed, proto_mode, activation
 CASES = [

@@ -19,7 +19,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
-from oracle import ref_harness, rollout_oracle as R, synth  # noqa: E402
+from oracle import ref_harness, rollout_oracle as R  # noqa: E402
+from protopformer_b200 import synth  # noqa: E402
 
 # name: (L, B, H, T, seed, head_fusion, K)
 CASES = {

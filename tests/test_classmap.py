@@ -49,7 +49,7 @@ def test_class_maps_match_reference_proto_acts(name):
 
 @pytest.mark.gpu
 def test_class_maps_full_size_against_materialised_map():
-    from oracle import synth
+    from protopformer_b200 import synth
     from protopformer_b200 import ops
     shape = synth.SHAPES["cub_b64"].with_batch(16)
     case = synth.make_case(shape, seed=2)

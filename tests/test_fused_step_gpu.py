@@ -6,7 +6,7 @@ import pytest
 import torch
 
 from oracle import protohead_oracle as O
-from oracle import synth
+from protopformer_b200 import synth
 from tests.util import GOLDEN_CASES, load_golden, norm_rel, rel_close
 
 pytestmark = pytest.mark.gpu

@@ -15,7 +15,7 @@ import torch
 import torch.nn.functional as F
 
 from oracle import protohead_oracle as O
-from oracle import synth
+from protopformer_b200 import synth
 from tests.util import (GOLDEN_CASES, argmax_mismatch_outside_near_ties, load_golden, max_rel, norm_rel, rel_close)
 
 pytestmark = pytest.mark.gpu

@@ -7,7 +7,8 @@ import pytest
 import torch
 
 from oracle import protohead_oracle as O
-from oracle import ref_harness, rollout_oracle as R, synth
+from oracle import ref_harness, rollout_oracle as R
+from protopformer_b200 import synth
 from tests.util import FakeCait, FakeDeit, norm_rel, rel_close
 
 pytestmark = pytest.mark.skipif(not ref_harness.reference_available(), reason="reference tree not present")

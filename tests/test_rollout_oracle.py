@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import rollout_oracle as R
-from oracle import synth
+from protopformer_b200 import synth
 from tests.util import GOLDEN_DIR, rel_close
 
 ROLLOUT_CASES = {

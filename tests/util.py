@@ -4,7 +4,7 @@ import os
 import numpy as np
 import torch
 
-from oracle import synth
+from protopformer_b200 import synth
 
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
