@@ -25,6 +25,7 @@ SIGNATURES = {
     "pph_version": [],
     "pph_last_error_string": [],
     "pph_sm_count": [],
+    "pph_set_option": [C.c_char_p, _i],
     "pph_select_topk": [_p, _i, _i, _i, _i, _p, _p, _p],
     "pph_addon_fwd": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p, _p],
     "pph_split_rows": [_p, _i, _i, _f, _p, _p, _p, _p, _p, _p],
@@ -63,7 +64,11 @@ _RESTYPES = {"pph_last_error_string": C.c_char_p}
 KERNELS_PER_CALL = {
     "pph_select_topk": 1, "pph_addon_fwd": 1, "pph_split_rows": 1, "pph_logits_fwd": 1, "pph_ppc_fwd": 1,
     "pph_ppc_bwd": 1, "pph_logits_bwd": 1, "pph_similarity_bwd": 2, "pph_addon_bwd": 3, "pph_loss_tail": 1, "pph_loss_combine": 1, "pph_rollout_scores": 2, "pph_adamw_step": 1, "pph_class_maps": 1, "pph_rollout_cls_rows": 1,
+    "pph_head_prep": 1, "pph_head_mid": 1, "pph_similarity_bwd2": 1, "pph_addon_bwd2": 1,
 }
+
+_ENV_OPTIONS = {"PPH_PDL": "pdl", "PPH_SIM_LANES": "sim_lanes", "PPH_SIM_SHARED": "sim_shared", "PPH_SIM_EPI": "sim_epi",
+                "PPH_ROLLOUT": "rollout", "PPH_CLASSMAP": "classmap"}
 
 _lib = None
 _launches = 0
@@ -87,6 +92,12 @@ def load() -> C.CDLL:
             fn = getattr(lib, name)      # AttributeError here = header / library mismatch
             fn.argtypes = args
             fn.restype = _RESTYPES.get(name, C.c_int)
+        # variant switches are resolved HERE, once, from the environment (the C side never calls getenv)
+        for env, opt in _ENV_OPTIONS.items():
+            v = os.environ.get(env)
+            if v is not None and v.strip() != "":
+                if lib.pph_set_option(opt.encode(), int(v)) != 0:
+                    raise RuntimeError(f"{env}: {lib.pph_last_error_string().decode()}")
         _lib = lib
     return _lib
 

@@ -492,11 +492,13 @@ extern "C" int pph_split_rows(const float* V, int R, int D, float center, uint16
     return pph::launch_status("pph_split_rows");
 }
 
-// development aid (not part of the drop-in surface): phase timestamps (ns) of CTA 0 of the last tcgemm launch
+#ifdef PPH_DEBUG_STAMPS
+// development aid (only in -DPPH_DEBUG_STAMPS builds): phase timestamps (ns) of CTA 0 of the last tcgemm launch
 extern "C" int pph_debug_read(long long* out32) {
     cudaError_t e = cudaMemcpyFromSymbol(out32, pph::g_dbg_ts, sizeof(long long) * 32);
     return e == cudaSuccess ? 0 : (int)e;
 }
+#endif
 
 extern "C" int pph_addon_bwd_ws_bytes(int B, int N, int Din, int D, int K, long long* bytes) {
     using namespace pph;

@@ -110,7 +110,7 @@ extern "C" int pph_class_maps(const float* Zs, const float* z2s, const float* Pl
                 "pph_class_maps: bad dims B=%d K=%d D=%d P=%d m=%d N=%d", B, K, D, P, m, N);
     PPH_REQUIRE(act_fn == PPH_ACT_LOG || act_fn == PPH_ACT_LINEAR, PPH_EINVAL, "pph_class_maps: act_fn %d", act_fn);
     if (B == 0) return 0;
-    static const bool use_v2 = [] { const char* e = getenv("PPH_CLASSMAP"); return e && e[0] == '2'; }();
+    const bool use_v2 = option(kOptClassmap) == 2;
     const size_t smem2 = (size_t)(K + m) * (D + 4) * sizeof(float);
     if (use_v2 && D % 4 == 0 && smem2 <= 200 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(class_maps2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);

@@ -45,6 +45,11 @@ inline cudaStream_t as_stream(pph_stream_t s) { return reinterpret_cast<cudaStre
 // Under stream capture the attribute becomes a programmatic edge of the CUDA graph.
 bool pdl_enabled();
 
+// Measurement / variant switches, set once by the host binding through pph_set_option() (protopformer_b200/_lib.py reads
+// the PPH_* environment variables at load time); the launchers never read the environment.
+enum Option { kOptPdl = 0, kOptSimLanes, kOptSimShared, kOptSimEpi, kOptRollout, kOptClassmap, kOptCount };
+int option(Option o);
+
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};

@@ -658,20 +658,15 @@ extern "C" int pph_rollout_scores(const float* const* attn_layers, int L, int B,
     const RoWorkspace w = rollout_carve(workspace, L, B, T, k_discard);
     const int n = T * T;
     // PPH_ROLLOUT=1 selects the first version of both kernels (kept for A/B measurements)
-    static const bool use_v1 = [] { const char* e = getenv("PPH_ROLLOUT"); return e && e[0] == '1'; }();
+    const bool use_v1 = option(kOptRollout) == 1;
     // PPH_ROLLOUT=3: v2 kernels with the reciprocal-scale normalisation (unvalidated, see the kernel)
-    static const int norm_mode = [] { const char* e = getenv("PPH_ROLLOUT"); return (e && e[0] == '3') ? 1 : 0; }();
+    const int norm_mode = option(kOptRollout) == 3 ? 1 : 0;
     const size_t smem1 = (size_t)((n + 3) & ~3) * 4 + 256 * 4 + (kRoThreads + 40) * 4;
     const size_t smem2 = (size_t)((n + 3) & ~3) * 4 + kRo2Bins * 4 + (kRoThreads + 40) * 4;
     const bool v1 = use_v1 || smem2 > 220 * 1024;
     const size_t smem = v1 ? smem1 : smem2;
-    static int sms = 0;
-    if (sms <= 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
+    int sms = pph_sm_count();            // per call: the current device may differ between calls
+    if (sms <= 0) sms = 148;
     const int tiles = L * B;
     cudaStream_t st = as_stream(stream);
     const dim3 grid(tiles < sms ? tiles : sms);

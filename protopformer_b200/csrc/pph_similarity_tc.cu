@@ -627,8 +627,38 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-// bf16 matrix [rows, D] row-major -> 2-D tiled map, box {64 elements, box_rows}, 128B swizzle, OOB rows read as 0
+// bf16 matrix [rows, D] row-major -> 2-D tiled map, box {64 elements, box_rows}, 128B swizzle, OOB rows read as 0.
+// A tensor map depends only on (base pointer, rows, D, box_rows): the eager drop-in path calls this entry point every
+// step on the same operand buffers, so the encoded maps are kept in a small per-thread cache ("cached
+// tensor maps"); a hit costs a 64-byte copy instead of a driver call.
+struct MapKey {
+    const void* base;
+    int rows, D, box_rows;
+};
+constexpr int kMapCache = 32;
+static thread_local MapKey g_map_key[kMapCache];
+static thread_local CUtensorMap g_map_val[kMapCache];
+static thread_local int g_map_n = 0, g_map_next = 0;
+
+static int make_map_uncached(CUtensorMap* m, const uint16_t* base, int rows, int D, int box_rows);
+
 static int make_map(CUtensorMap* m, const uint16_t* base, int rows, int D, int box_rows) {
+    for (int i = 0; i < g_map_n; ++i) {
+        const MapKey& k = g_map_key[i];
+        if (k.base == base && k.rows == rows && k.D == D && k.box_rows == box_rows) {
+            *m = g_map_val[i];
+            return 0;
+        }
+    }
+    const int rc = make_map_uncached(m, base, rows, D, box_rows);
+    if (rc) return rc;
+    const int slot = g_map_n < kMapCache ? g_map_n++ : (g_map_next++ % kMapCache);
+    g_map_key[slot] = MapKey{base, rows, D, box_rows};
+    g_map_val[slot] = *m;
+    return 0;
+}
+
+static int make_map_uncached(CUtensorMap* m, const uint16_t* base, int rows, int D, int box_rows) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return PPH_EDRIVER; }
     cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)rows};
@@ -671,8 +701,8 @@ static Tc2Plan plan_tc2(const TcParams& prm, int nterms, int sms) {
     // Measured on B200 (profiles/r1b_sim_plan_ab.txt): giving the local walkers all 148 SMs and dealing the global
     // tiles out as second jobs (9 lanes instead of 8 at the CUB shape) is 1.5-1.7x SLOWER at every batch size, so
     // the dedicated plan stays; PPH_SIM_SHARED=1 / PPH_SIM_LANES=n select the alternatives for measurements.
-    static const int knob_lanes = [] { const char* e = getenv("PPH_SIM_LANES"); return e ? atoi(e) : 0; }();
-    static const bool knob_shared = [] { const char* e = getenv("PPH_SIM_SHARED"); return e && e[0] == '1'; }();
+    const int knob_lanes = option(kOptSimLanes);
+    const bool knob_shared = option(kOptSimShared) != 0;
     int avail = sms;
     if (!knob_shared) avail = sms - (prm.MT_g <= sms / 4 ? prm.MT_g : sms / 4);
     int lanes = avail / prm.MT_l;
@@ -721,11 +751,9 @@ static void tc_shape_plan(bool x3, int B, int K, int D, int P, int Pg, int sms, 
 template <int NTERMS, int KT, int EPI = 1>
 static int launch_tc2(const CUtensorMap* maps, const TcParams& prm, const Tc2Plan& pl, cudaStream_t st) {
     auto kern = similarity_tc2_kernel<NTERMS, KT, EPI>;
-    static int configured = 0;
-    if (configured < pl.smem) {
+    {   // per call, not cached in a static: the attribute is per device and setting it is cheap
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        configured = kTcSmemLimit;
     }
     launch_k(kern, dim3(pl.grid), dim3(kTcThreads), (size_t)(pl.smem), st, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], prm, pl.lanes_l, pl.n_local_ctas, pl.stages, pl.b_tile_bytes);
     return launch_status("pph_similarity_fwd(tcgen05, resident prototypes)");
@@ -734,11 +762,9 @@ static int launch_tc2(const CUtensorMap* maps, const TcParams& prm, const Tc2Pla
 template <int NTERMS, int KT>
 static int launch_tc(const CUtensorMap* maps, const TcParams& prm, int grid, cudaStream_t st) {
     auto kern = similarity_tc_kernel<NTERMS, KT>;
-    static bool configured = false;
-    if (!configured) {
+    {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-        configured = true;
     }
     launch_k(kern, dim3(grid), dim3(kTcThreads), (size_t)(kTcSmemBytes), st, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], prm);
     return launch_status("pph_similarity_fwd(tcgen05)");
@@ -760,13 +786,8 @@ int similarity_fwd_tc(int mode, int act_fn, float eps, int B, int K, int D, int 
     PPH_REQUIRE(Pg == 0 || (Zc_hi && Pg_hi && z2c && p2g && dmin_g && act_g && (!x3 || (Zc_lo && Pg_lo))), PPH_EINVAL,
                 "tcgen05 similarity: null global operand");
 
-    static int sms = 0;
-    if (sms <= 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (sms <= 0) sms = 148;
-    }
+    int sms = pph_sm_count();
+    if (sms <= 0) sms = 148;
     TcParams prm;
     Tc2Plan pl;
     tc_shape_plan(x3, B, K, D, P, Pg, sms, prm, pl);
@@ -797,7 +818,7 @@ int similarity_fwd_tc(int mode, int act_fn, float eps, int B, int K, int D, int 
         return x3 ? launch_tc<3, KT>(maps, prm, grid, st) : launch_tc<1, KT>(maps, prm, grid, st);   \
     } while (0)
     // A/B switch for measurements: PPH_SIM_EPI=0 selects the sequential-scan epilogue (built for K = 81 only)
-    static const bool old_epi = [] { const char* e = getenv("PPH_SIM_EPI"); return e && e[0] == '0'; }();
+    const bool old_epi = option(kOptSimEpi) == 0;
     if (old_epi && K == 81 && pl.ok)
         return x3 ? launch_tc2<3, 81, 0>(maps, prm, pl, st) : launch_tc2<1, 81, 0>(maps, prm, pl, st);
     switch (K) {

@@ -22,7 +22,9 @@
 
 namespace pph {
 
-// phase timestamps (globaltimer ns) of CTA 0 of the most recent tcgemm launch: development aid, read by pph_debug_read
+// phase timestamps (globaltimer ns) of CTA 0 of the most recent tcgemm launch: development aid, compiled in only with
+// -DPPH_DEBUG_STAMPS (then read back through pph_debug_read); the shipped library carries neither
+#ifdef PPH_DEBUG_STAMPS
 static __device__ long long g_dbg_ts[32];   // one copy per translation unit (the add-on kernels live in pph_addon.cu)
 __device__ __forceinline__ void dbg_stamp(int slot) {
     if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && slot < 32) {
@@ -31,6 +33,9 @@ __device__ __forceinline__ void dbg_stamp(int slot) {
         g_dbg_ts[slot] = t;
     }
 }
+#else
+__device__ __forceinline__ void dbg_stamp(int) {}
+#endif
 
 constexpr int kTgThreads = 512;
 constexpr int kTgWarps = kTgThreads / 32;
@@ -261,12 +266,10 @@ inline int launch_tcgemm(int M, int N, int Kd, int BN, int splits, AOp a, BOp b,
                          const char* what) {
     auto kern = tcgemm_kernel<AOp, BOp, Epi>;
     const size_t smem = tcgemm_smem_bytes(BN);
-    static bool configured = false;
-    if (!configured) {
+    {   // per call: the attribute is per device and setting it is cheap
         cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                (int)tcgemm_smem_bytes(kTgMaxBN));
         if (err != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(err)); return (int)err; }
-        configured = true;
     }
     if (splits < 1) splits = 1;
     int k_per_split = ceil_div(ceil_div(Kd, splits), kTgBK) * kTgBK;

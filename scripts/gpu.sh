@@ -16,6 +16,10 @@ case $stage in
     timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_step2_gpu.py -q --tb=line \
         -k "tiny or small or cub_b8" > gpurun_out/sanitize.log 2>&1
     echo "== sanitize rc=$?"; grep -E "ERROR SUMMARY|Invalid|passed|failed" gpurun_out/sanitize.log | head -20 ;;
+  ncu2)       # one --set full capture of each kernel of the five-launch step (second eager step)
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:"head_prep|similarity_tc2|head_mid|sim_grads2|addon_bwd2" \
+        -s 5 -c 5 -o gpurun_out/r2_step2 -f python scripts/run_step.py cub_b64 fp32 v2 3 > gpurun_out/ncu2.log 2>&1
+    echo "== ncu2 rc=$?"; tail -3 gpurun_out/ncu2.log ;;
   all)
     timeout 1500 python -m pytest tests -q -m gpu --tb=short > gpurun_out/t_all.log 2>&1; echo "== all: rc=$? $(tail -1 gpurun_out/t_all.log)" ;;
   bench)
