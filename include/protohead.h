@@ -278,7 +278,7 @@ int pph_head_prep(const float* scores, const float* tokens, const float* Wa, con
  *   dlogits [B,C]; g_l [B,P], g_g [B,Pg] as pph_logits_bwd (no upstream gradient on logits_global/local);
  *   pairT [(P+Pg)][Bp][2] fp32, Bp = B rounded up to 64: (g, bit pattern of the int32 token slot) per (prototype, image),
  *   token slot K (= the CLS row) for global prototypes, zeros for images >= B;
- *   the token bins of pph_similarity_bwd2 in bwd_workspace (pph_similarity_bwd2_ws_bytes);
+ *   the token bins (and, with use_ppc, the images sorted by class) of pph_similarity_bwd2 in bwd_workspace;
  *   with use_ppc: dZs_ppc [B,K,D] = d(cov_coe*cov + mean_coe*mean)*upstream / dZs (OVERWRITTEN) and
  *   dP_img [B,m,D] = the same gradient w.r.t. the m label-class prototype rows, per image (summed over the images of a
  *   class by pph_similarity_bwd2 in image order: deterministic).
@@ -296,24 +296,55 @@ int pph_head_mid(const float* act_l, const float* act_g, const float* dmin_l, co
                  float* g_l, float* g_g, float* pairT, float* dZs_ppc, float* dP_img, pph_stream_t stream);
 
 /* (a8 part 2), second implementation: same results as pph_similarity_bwd(PPH_BWD_GRADS) from operands staged in shared
- * memory by 16-float feature slices (no L2 row gathers), every row summed in a fixed order.  g_l / g_g / pairT and the
- * bins in bwd_workspace come from pph_head_mid.  add_dZs [B,K,D] (or NULL) is added to dZs; dP_img [B,m,D] (or NULL;
- * needs labels [B] int64 and m) is added to the label-class rows of dPl.  D % 16 == 0. */
+ * memory by feature slices (no L2 row gathers), every row summed in a fixed order (no atomics on data).  Three kernels,
+ * selected by `parts`, independent of each other -- meant for concurrent streams:
+ *   PPH_BWD2_TOKENS -> dZs [B,K,D]     PPH_BWD2_PROTOS -> dPl [P,D], dPg [Pg,D]     PPH_BWD2_CLS -> dZc [B,D]
+ * g_l / g_g / pairT and the bins + class lists in bwd_workspace come from pph_head_mid (same launch sequence).
+ * add_dZs [B,K,D] (or NULL) is added to dZs; dP_img [B,m,D] (or NULL) is added to the label-class rows of dPl, summed
+ * over the images of a class in image order.  dpre_out != 0: dZs / dZc are multiplied by Z (1 - Z) while they are
+ * written, i.e. they hold the pre-activation gradient pph_addon_bwd2 consumes.
+ * bwd_workspace: pph_similarity_bwd2_ws_bytes() bytes, ZERO-FILLED once before first use.  D % 16 == 0. */
+#define PPH_BWD2_TOKENS 1
+#define PPH_BWD2_PROTOS 2
+#define PPH_BWD2_CLS    4
 int pph_similarity_bwd2_supported(int B, int K, int D, int P, int Pg);
-int pph_similarity_bwd2_ws_bytes(int B, int K, int P, long long* bytes /* host */);
-int pph_similarity_bwd2(const float* g_l, const float* g_g, const float* pairT, const void* bwd_workspace,
+int pph_similarity_bwd2_ws_bytes(int B, int K, int D, int P, long long* bytes /* host */);
+int pph_similarity_bwd2(int parts, const float* g_l, const float* g_g, const float* pairT, void* bwd_workspace,
                         const float* Zs, const float* Zc, const float* Pl, const float* Pgl,
                         int B, int K, int D, int P, int Pg, int m,
-                        const float* add_dZs, const float* dP_img, const int64_t* labels,
+                        const float* add_dZs, const float* dP_img, int dpre_out,
                         float* dZs, float* dZc, float* dPl, float* dPg, pph_stream_t stream);
 
-/* (a8 part 3), second implementation: pph_addon_bwd(PPH_ADDON_WGRAD | PPH_ADDON_DGRAD) in one launch, exact FP32,
- * deterministic.  dtokens may be NULL (no gradient to the backbone).  workspace: pph_addon_bwd2_ws_bytes() bytes,
- * ZERO-FILLED once before first use.  Din % 8 == 0, D % 4 == 0. */
+/* (a8 part 3), second implementation: backward of pph_addon_fwd from the PRE-ACTIVATION gradient
+ * dpre = dZ * Z * (1 - Z) (dpre_s [B,K,D] for the selected tokens, dpre_c [B,D] for the CLS token), exact FP32,
+ * deterministic.  parts: PPH_ADDON_WGRAD -> dWa [D,Din], dba [D]; PPH_ADDON_DGRAD -> dtokens [B,1+N,Din] (every row
+ * written: zeros for tokens that were not selected).  workspace: pph_addon_bwd2_ws_bytes() bytes, ZERO-FILLED once
+ * before first use.  Din % 8 == 0, D % 4 == 0. */
 int pph_addon_bwd2_supported(int B, int N, int Din, int D, int K);
 int pph_addon_bwd2_ws_bytes(int B, int N, int Din, int D, int K, long long* bytes /* host */);
-int pph_addon_bwd2(const float* tokens, const int32_t* idx32, const float* Wa,
-                   const float* Zs, const float* Zc, const float* dZs, const float* dZc,
+int pph_addon_bwd2(int parts, const float* tokens, const int32_t* idx32, const float* Wa,
+                   const float* dpre_s, const float* dpre_c,
+                   int B, int N, int Din, int D, int K, void* workspace,
+                   float* dWa, float* dba, float* dtokens, pph_stream_t stream);
+
+/* The add-on layer products on the single-shot tcgen05 kernel (one 128 x BN output tile per CTA, its whole k range
+ * resident in shared memory, 3-term bf16 split as pph_addon_fwd):
+ *   pph_addon_fwd2 = pph_addon_fwd (same outputs, same numerics) with the output columns split over CTAs;
+ *   pph_addon_bwd3 = pph_addon_bwd2 (inputs dpre_s / dpre_c) on tensor cores; with PPH_ADDON_DGRAD the rows of dtokens
+ *   that belong to selected tokens (and the CLS rows) are written, every other row must have been ZERO-FILLED by the
+ *   caller; PPH_ADDON_WGRAD reduces its split-k partials in-kernel behind a grid barrier (needs <= SM-count CTAs).
+ * pph_addon_tc2_supported: bit 0 forward, bit 1 DGRAD, bit 2 WGRAD can run this shape.  workspace:
+ * pph_addon_tc2_ws_bytes() bytes, ZERO-FILLED once before first use (shared by the three calls of a step). */
+int pph_addon_tc2_supported(int B, int N, int Din, int D, int K);
+int pph_addon_tc2_ws_bytes(int B, int N, int Din, int D, int K, long long* bytes /* host */);
+int pph_addon_fwd2(const float* tokens, const int32_t* idx32, const float* Wa, const float* ba,
+                   int B, int N, int Din, int D, int K,
+                   float* Zs, float* Zc, float* z2s, float* z2c,
+                   float center, float* z2s_ctr, float* z2c_ctr, float* z2s_hi, float* z2c_hi,
+                   uint16_t* Zs_hi, uint16_t* Zs_lo, uint16_t* Zc_hi, uint16_t* Zc_lo,
+                   void* workspace, pph_stream_t stream);
+int pph_addon_bwd3(int parts, const float* tokens, const int32_t* idx32, const float* Wa,
+                   const float* dpre_s, const float* dpre_c,
                    int B, int N, int Din, int D, int K, void* workspace,
                    float* dWa, float* dba, float* dtokens, pph_stream_t stream);
 

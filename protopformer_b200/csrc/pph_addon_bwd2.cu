@@ -1,5 +1,6 @@
 // (a8, part 3) backward of gather -> add-on layer -> sigmoid (autograd of protopformer.py:159-172) in ONE launch:
-//   dpre = dZ * Z * (1 - Z)                        evaluated on the fly while the operand tiles are staged
+//   dpre = dZ * Z * (1 - Z)                        is the INPUT (pph_similarity_bwd2 writes it with dpre_out = 1), so both
+//                                                  operand tiles are staged with plain cp.async copies
 //   role X (blockIdx < nX)   dtokens[b, 1+idx[b,j], :] = dpre[r,:] Wa   (CLS row 0 likewise) for a tile of TR rows, and
 //                            the zero fill of this CTA's share of the token rows that were not selected
 //   role W (the rest)        dWa = dpre^T X_sel, dba = sum_r dpre: 64 x 64 output tiles x S row splits; every split
@@ -22,7 +23,7 @@ struct AddonBwdArgs {
     int TR, Dp, nchunks, threadsX, nX;     // role X plan
     int tilesO, tilesI, S, RS, nW;         // role W plan: S row splits of RS rows
     int want_dx, want_dw;
-    const float *tokens, *Wa, *Zs, *Zc, *dZs, *dZc;
+    const float *tokens, *Wa, *dpre_s, *dpre_c;
     const int32_t* idx;
     float *dWa, *dba, *dtokens;
     float *part, *partb;                   // [S][D][Din], [S][D]
@@ -34,14 +35,11 @@ __device__ __forceinline__ void row_of(int r, int K, int& b, int& j) {
     j = r - b * (K + 1);
 }
 
-__device__ __forceinline__ float4 dpre4(const AddonBwdArgs& a, int r, int col) {
+// address of dpre(r, col): selected-token rows live in dpre_s [B,K,D], the CLS row of an image in dpre_c [B,D]
+__device__ __forceinline__ const float* dpre_ptr(const AddonBwdArgs& a, int r, int col) {
     int b, j;
     row_of(r, a.K, b, j);
-    const size_t o = (j < a.K ? ((size_t)b * a.K + j) : (size_t)b) * a.D + col;
-    const float4 z = __ldg(reinterpret_cast<const float4*>((j < a.K ? a.Zs : a.Zc) + o));
-    const float4 g = __ldcg(reinterpret_cast<const float4*>((j < a.K ? a.dZs : a.dZc) + o));
-    return make_float4(g.x * z.x * (1.0f - z.x), g.y * z.y * (1.0f - z.y), g.z * z.z * (1.0f - z.z),
-                       g.w * z.w * (1.0f - z.w));
+    return (j < a.K ? a.dpre_s + ((size_t)b * a.K + j) * a.D : a.dpre_c + (size_t)b * a.D) + col;
 }
 
 // ---- role X ----------------------------------------------------------------------------------------------------
@@ -52,20 +50,23 @@ __device__ __forceinline__ void addon_bwd_x(const AddonBwdArgs& a, float* sm) {
     float* Ds = sm;                                   // [TR][Dp]     dpre rows
     float* Wt = Ds + (size_t)TR * Dp;                  // [2][kAbKC][Din]
     const int d4 = Dp >> 2;
-    for (int i = tid; i < TR * d4; i += nthr) {
-        const int rl = i / d4, q = i - rl * d4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rl < nrow && q * 4 < D) v = dpre4(a, r0 + rl, q * 4);
-        *reinterpret_cast<float4*>(Ds + (size_t)rl * Dp + q * 4) = v;
+    for (int rl = warp; rl < TR; rl += nwarp) {                  // one warp per row: no division in the copy loop
+        const float* src = rl < nrow ? dpre_ptr(a, r0 + rl, 0) : nullptr;
+        for (int q = lane; q < d4; q += 32) {
+            float* dst = Ds + (size_t)rl * Dp + q * 4;
+            if (src && q * 4 < D) cp_async16(dst, src + q * 4);
+            else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
     }
     const int i4 = Din >> 2;
     auto issue = [&](int ch, int buf) {
         float* dst = Wt + (size_t)buf * kAbKC * Din;
-        for (int i = tid; i < kAbKC * i4; i += nthr) {
-            const int ol = i / i4, q = i - ol * i4;
+        for (int ol = warp; ol < kAbKC; ol += nwarp) {
             const int o = ch * kAbKC + ol;
-            if (o < D) cp_async16(dst + (size_t)ol * Din + q * 4, a.Wa + (size_t)o * Din + q * 4);
-            else *reinterpret_cast<float4*>(dst + (size_t)ol * Din + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int q = lane; q < i4; q += 32) {
+                if (o < D) cp_async16(dst + (size_t)ol * Din + q * 4, a.Wa + (size_t)o * Din + q * 4);
+                else *reinterpret_cast<float4*>(dst + (size_t)ol * Din + q * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
         }
         cp_async_commit();
     };
@@ -165,47 +166,39 @@ __device__ __forceinline__ void addon_bwd_w(const AddonBwdArgs& a, int vb, float
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
     float bsum[4] = {0.f, 0.f, 0.f, 0.f};
-    // stage chunk ch into buffer buf: X via cp.async, dpre through registers (returned, stored after the barrier)
+    // stage chunk ch into buffer buf: both operand tiles are plain copies (gathered token rows, dpre rows)
     const int lr = tid >> 4, lq = tid & 15;            // (row, float4 column) of this thread's two staging elements
-    auto issue_x = [&](int ch, int buf) {
+    auto issue = [&](int ch, int buf) {
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int rl = lr + 16 * u, r = rA + ch * kAbRC + rl;
-            float* dst = Xs + ((size_t)buf * kAbRC + rl) * kAbWT + lq * 4;
-            if (r < rE && i0 + lq * 4 < Din) {
+            float* dx = Xs + ((size_t)buf * kAbRC + rl) * kAbWT + lq * 4;
+            float* da = As + ((size_t)buf * kAbRC + rl) * kAbWT + lq * 4;
+            if (r < rE) {
                 int b, j;
                 row_of(r, K, b, j);
-                const int tok = j < K ? 1 + __ldg(a.idx + (size_t)b * K + j) : 0;
-                cp_async16(dst, a.tokens + ((size_t)b * (1 + N) + tok) * Din + i0 + lq * 4);
+                if (i0 + lq * 4 < Din) {
+                    const int tok = j < K ? 1 + __ldg(a.idx + (size_t)b * K + j) : 0;
+                    cp_async16(dx, a.tokens + ((size_t)b * (1 + N) + tok) * Din + i0 + lq * 4);
+                } else {
+                    *reinterpret_cast<float4*>(dx) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                if (o0 + lq * 4 < D)
+                    cp_async16(da, (j < K ? a.dpre_s + ((size_t)b * K + j) * D : a.dpre_c + (size_t)b * D) + o0 + lq * 4);
+                else
+                    *reinterpret_cast<float4*>(da) = make_float4(0.f, 0.f, 0.f, 0.f);
             } else {
-                *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(dx) = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(da) = make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
         cp_async_commit();
     };
-    auto load_a = [&](int ch, float4 (&v)[2]) {
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int rl = lr + 16 * u, r = rA + ch * kAbRC + rl;
-            v[u] = (r < rE && o0 + lq * 4 < D) ? dpre4(a, r, o0 + lq * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    };
-    auto store_a = [&](int buf, const float4 (&v)[2]) {
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-            *reinterpret_cast<float4*>(As + ((size_t)buf * kAbRC + lr + 16 * u) * kAbWT + lq * 4) = v[u];
-    };
-    float4 av[2];
-    if (nch > 0) {
-        issue_x(0, 0);
-        load_a(0, av);
-        store_a(0, av);
-    }
+    if (nch > 0) issue(0, 0);
     for (int ch = 0; ch < nch; ++ch) {
         const int buf = ch & 1;
         if (ch + 1 < nch) {
-            issue_x(ch + 1, buf ^ 1);
-            load_a(ch + 1, av);
+            issue(ch + 1, buf ^ 1);
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
@@ -225,8 +218,7 @@ __device__ __forceinline__ void addon_bwd_w(const AddonBwdArgs& a, int vb, float
                 for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], x4[j], acc[i][j]);
             }
         }
-        if (ch + 1 < nch) store_a(buf ^ 1, av);       // buffer buf^1 was last read in iteration ch-1 (barrier below)
-        bar_w();
+        bar_w();                                       // buffer buf is free for the copies of chunk ch + 2
     }
     // partial of this split
     float* part = a.part + (size_t)s * D * Din;
@@ -338,13 +330,15 @@ extern "C" int pph_addon_bwd2_ws_bytes(int B, int N, int Din, int D, int K, long
     return 0;
 }
 
-extern "C" int pph_addon_bwd2(const float* tokens, const int32_t* idx32, const float* Wa,
-                              const float* Zs, const float* Zc, const float* dZs, const float* dZc,
+extern "C" int pph_addon_bwd2(int parts, const float* tokens, const int32_t* idx32, const float* Wa,
+                              const float* dpre_s, const float* dpre_c,
                               int B, int N, int Din, int D, int K, void* workspace,
                               float* dWa, float* dba, float* dtokens, pph_stream_t stream) {
     using namespace pph;
-    PPH_REQUIRE(tokens && idx32 && Wa && Zs && Zc && dZs && dZc && workspace && dWa && dba, PPH_EINVAL,
-                "pph_addon_bwd2: null pointer");
+    PPH_REQUIRE((parts & 3) != 0, PPH_EINVAL, "pph_addon_bwd2: parts must name WGRAD and/or DGRAD");
+    PPH_REQUIRE(tokens && idx32 && Wa && dpre_s && dpre_c && workspace, PPH_EINVAL, "pph_addon_bwd2: null pointer");
+    PPH_REQUIRE(!(parts & PPH_ADDON_WGRAD) || (dWa && dba), PPH_EINVAL, "pph_addon_bwd2(WGRAD): null output");
+    PPH_REQUIRE(!(parts & PPH_ADDON_DGRAD) || dtokens, PPH_EINVAL, "pph_addon_bwd2(DGRAD): null dtokens");
     PPH_REQUIRE(pph_addon_bwd2_supported(B, N, Din, D, K), PPH_EUNSUP, "pph_addon_bwd2: unsupported shape");
     int sms = pph_sm_count();
     if (sms <= 0) sms = 148;
@@ -353,10 +347,11 @@ extern "C" int pph_addon_bwd2(const float* tokens, const int32_t* idx32, const f
     AddonBwdArgs a;
     a.B = B; a.N = N; a.Din = Din; a.D = D; a.K = K; a.R = B * (K + 1);
     a.TR = p.TR; a.Dp = p.Dp; a.nchunks = p.nchunks; a.threadsX = p.threadsX;
-    a.nX = dtokens ? p.nX : 0;
-    a.tilesO = p.tilesO; a.tilesI = p.tilesI; a.S = p.S; a.RS = p.RS; a.nW = p.nW;
-    a.want_dx = dtokens ? 1 : 0; a.want_dw = 1;
-    a.tokens = tokens; a.Wa = Wa; a.Zs = Zs; a.Zc = Zc; a.dZs = dZs; a.dZc = dZc; a.idx = idx32;
+    a.nX = (parts & PPH_ADDON_DGRAD) ? p.nX : 0;
+    a.tilesO = p.tilesO; a.tilesI = p.tilesI; a.S = p.S; a.RS = p.RS;
+    a.nW = (parts & PPH_ADDON_WGRAD) ? p.nW : 0;
+    a.want_dx = a.nX ? 1 : 0; a.want_dw = a.nW ? 1 : 0;
+    a.tokens = tokens; a.Wa = Wa; a.dpre_s = dpre_s; a.dpre_c = dpre_c; a.idx = idx32;
     a.dWa = dWa; a.dba = dba; a.dtokens = dtokens;
     char* w = static_cast<char*>(workspace);
     const int tiles = p.tilesO * p.tilesI;

@@ -14,6 +14,7 @@ namespace pph {
 constexpr int kBinChunk = 32;
 
 // One CTA of 256 threads per image b; smi: 8*K + 2*(K+1) ints of shared memory.
+template <bool kCoherentKeys = false>
 __device__ __forceinline__ void
 bin_tokens_body(int b, const int32_t* __restrict__ argmin_l, int K, int P, int32_t* __restrict__ bin_start,
                 int32_t* __restrict__ item_start, int32_t* __restrict__ bin_list, int* smi) {
@@ -29,7 +30,7 @@ bin_tokens_body(int b, const int32_t* __restrict__ argmin_l, int K, int P, int32
     for (int p0 = pa; p0 < pb; p0 += 32) {               // pass A
         const int p = p0 + lane;
         const bool valid = p < pb;
-        const int a = valid ? min(max(__ldg(am + p), 0), K - 1) : -1 - lane;   // clamped: a bad index must not leave the bins
+        const int a = valid ? min(max(kCoherentKeys ? __ldcg(am + p) : __ldg(am + p), 0), K - 1) : -1 - lane;   // clamped: a bad index must not leave the bins
         const unsigned peers = __match_any_sync(0xffffffffu, a);
         if (valid && lane == __ffs(peers) - 1) hist[warp * K + a] += __popc(peers);
         __syncwarp();
@@ -75,7 +76,7 @@ bin_tokens_body(int b, const int32_t* __restrict__ argmin_l, int K, int P, int32
     for (int p0 = pa; p0 < pb; p0 += 32) {               // pass B
         const int p = p0 + lane;
         const bool valid = p < pb;
-        const int a = valid ? min(max(__ldg(am + p), 0), K - 1) : -1 - lane;   // clamped: a bad index must not leave the bins
+        const int a = valid ? min(max(kCoherentKeys ? __ldcg(am + p) : __ldg(am + p), 0), K - 1) : -1 - lane;   // clamped: a bad index must not leave the bins
         const unsigned peers = __match_any_sync(0xffffffffu, a);
         const int rank = __popc(peers & ((1u << lane) - 1u));
         const int leader = __ffs(peers) - 1;

@@ -47,7 +47,7 @@ bool pdl_enabled();
 
 // Measurement / variant switches, set once by the host binding through pph_set_option() (protopformer_b200/_lib.py reads
 // the PPH_* environment variables at load time); the launchers never read the environment.
-enum Option { kOptPdl = 0, kOptSimLanes, kOptSimShared, kOptSimEpi, kOptRollout, kOptClassmap, kOptCount };
+enum Option { kOptPdl = 0, kOptSimLanes, kOptSimShared, kOptSimEpi, kOptRollout, kOptClassmap, kOptDebug, kOptCount };
 int option(Option o);
 
 template <typename... KArgs, typename... Args>
@@ -82,6 +82,11 @@ __device__ __forceinline__ void pdl_sync() {
 // ---- cp.async (LDGSTS): 16-byte global -> shared copies that bypass the register file ---------------------------
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gmem_src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)),
                  "l"(gmem_src)
                  : "memory");
 }

@@ -33,7 +33,7 @@ constexpr int kMidAST = 68;      // row stride of the [*][64-image] shared tiles
 struct MidArgs {
     int B, Bp, K, D, P, Pg, C, Cp, m, N, side;
     int tiles_b, S_l, S_g, nsl_l, nsl_g;
-    int n_ll, n_bin, n_ppc;
+    int n_ll, n_bin, n_ppc, n_cls_cta;
     float gc, eps, upstream, cov_thresh, mean_thresh, cov_coe, mean_coe;
     int act_fn, train;
     const float *act_l, *act_g, *dmin_l, *dmin_g;
@@ -46,6 +46,7 @@ struct MidArgs {
     float *part, *dlT, *ce_part, *ppc_part, *ppc_losses;
     unsigned int* ctr;      // [0] barrier, [1] done, [2] fin, [3] ppc ticket
     int32_t *bin_start, *item_start, *bin_list;
+    int32_t *cls_id, *cls_start, *cls_item, *cls_order;
     // PPC role
     const float *Zs, *z2s, *Pl, *p2l;
     const int32_t* idx;
@@ -89,6 +90,20 @@ __device__ __forceinline__ void role_finished(const MidArgs& a) {      // one th
 // ---------------------------------------------------------------------------------------------------------------
 // role LL
 // ---------------------------------------------------------------------------------------------------------------
+// W slice, transposed on the way in: Ws[pl][c] = W[c][p0 + pl].  4-byte cp.async copies: a warp reads one 128-byte row
+// segment and scatters it down a column of Ws (odd stride: conflict-free); all C copies of a thread are in flight at once.
+__device__ __forceinline__ void stage_w(float* Ws, const float* __restrict__ W, int np, int p0, int C, int WST) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pp = p0 + lane;
+    float* dst = Ws + lane * WST;
+    if (pp < np) {
+        const float* src = W + pp;
+        for (int c = warp; c < C; c += kMidThreads / 32) cp_async4(dst + c, src + (size_t)c * np);
+    } else {
+        for (int c = warp; c < C; c += kMidThreads / 32) dst[c] = 0.f;
+    }
+}
+
 template <int CJ>
 __device__ __forceinline__ void ll_role(const MidArgs& a, float* sm) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -122,15 +137,19 @@ __device__ __forceinline__ void ll_role(const MidArgs& a, float* sm) {
         for (int sl = sg; sl < nsl; sl += Sg) {
             const int p0 = sl * kMidPS;
             __syncthreads();
-            for (int i = tid; i < C * kMidPS; i += kMidThreads) {
-                const int c = i >> 5, pl = i & 31;
-                Ws[pl * WST + c] = (p0 + pl < np) ? __ldg(W + (size_t)c * np + p0 + pl) : 0.f;
+            stage_w(Ws, W, np, p0, C, WST);
+            {   // act tile, transposed on the way in: As[pl][bi] = act[b0 + bi][p0 + pl]
+                const int pl = lane, pp = p0 + pl;
+                const float* src = act + (size_t)(b0 + warp) * np + pp;
+#pragma unroll
+                for (int u = 0; u < kMidTB / 8; ++u) {
+                    const int bi = warp + 8 * u;
+                    if (b0 + bi < B && pp < np) cp_async4(&As[pl * kMidAST + bi], src + (size_t)(8 * u) * np);
+                    else As[pl * kMidAST + bi] = 0.f;
+                }
             }
-            for (int i = tid; i < kMidTB * kMidPS; i += kMidThreads) {
-                const int bi = i >> 5, pl = i & 31;
-                As[pl * kMidAST + bi] =
-                    (b0 + bi < B && p0 + pl < np) ? __ldg(act + (size_t)(b0 + bi) * np + p0 + pl) : 0.f;
-            }
+            cp_async_commit();
+            cp_async_wait<0>();
             __syncthreads();
 #pragma unroll 2
             for (int pl = 0; pl < kMidPS; ++pl) {
@@ -252,10 +271,13 @@ __device__ __forceinline__ void ll_role(const MidArgs& a, float* sm) {
 
     // ---- phase 3: g[b,p] = coef * (dlogits[b,:] . W[:,p]) * act'(dmin[b,p]) --------------------------------------
     if (a.train) {
-        for (int i = tid; i < C * kMidTB; i += kMidThreads) {
-            const int c = i >> 6, bi = i & 63;
-            dls[c * kMidAST + bi] = (b0 + bi < B) ? __ldcg(a.dlT + (size_t)c * a.Bp + b0 + bi) : 0.f;
+        // dlogits tile of this image tile: rows of dlT are 64 contiguous floats (columns >= B of dlT stay zero: the
+        // workspace starts zeroed and only columns < B are ever written)
+        for (int i = tid; i < C * (kMidTB / 4); i += kMidThreads) {
+            const int c = i >> 4, q = i & 15;
+            cp_async16(&dls[c * kMidAST + q * 4], a.dlT + (size_t)c * a.Bp + b0 + q * 4);
         }
+        cp_async_commit();
         const bool keepW = nsl <= Sg;            // one slice per CTA: Ws still holds it from phase 1
         const float coef = glob ? a.gc : 1.0f - a.gc;
         const float* dmin = glob ? a.dmin_g : a.dmin_l;
@@ -264,11 +286,10 @@ __device__ __forceinline__ void ll_role(const MidArgs& a, float* sm) {
             const int p0 = sl * kMidPS;
             if (!keepW) {
                 __syncthreads();
-                for (int i = tid; i < C * kMidPS; i += kMidThreads) {
-                    const int c = i >> 5, pl = i & 31;
-                    Ws[pl * WST + c] = (p0 + pl < np) ? __ldg(W + (size_t)c * np + p0 + pl) : 0.f;
-                }
+                stage_w(Ws, W, np, p0, C, WST);
+                cp_async_commit();
             }
+            cp_async_wait<0>();
             __syncthreads();
             float g8[8];
 #pragma unroll
@@ -323,16 +344,15 @@ __device__ __forceinline__ void ppc_role(const MidArgs& a, int b, float* sm) {
     if (y < 0) y = 0;
     if (y * m + m > a.P) y = a.P / m - 1;
     const int prow0 = (int)y * m;
-    for (int i = tid; i < m * D / 4; i += kMidThreads)
-        reinterpret_cast<float4*>(Prow)[i] = __ldg(reinterpret_cast<const float4*>(a.Pl + (size_t)prow0 * D) + i);
+    for (int i = tid; i < m * D / 4; i += kMidThreads) cp_async16(Prow + 4 * i, a.Pl + (size_t)prow0 * D + 4 * i);
     const float* Zb = a.Zs + (size_t)b * K * D;
     {
         const int d4 = D >> 2;
-        for (int i = tid; i < K * d4; i += kMidThreads) {
-            const int r = i / d4, c = i - r * d4;
-            *reinterpret_cast<float4*>(Zt + (size_t)r * zs + 4 * c) = __ldg(reinterpret_cast<const float4*>(Zb + (size_t)r * D) + c);
-        }
+        for (int r = warp; r < K; r += nwarp)
+            for (int c = lane; c < d4; c += 32) cp_async16(Zt + (size_t)r * zs + 4 * c, Zb + (size_t)r * D + 4 * c);
     }
+    cp_async_commit();
+    cp_async_wait<0>();
     __syncthreads();
     const int JG = K * 3 <= kMidThreads ? 3 : (K * 2 <= kMidThreads ? 2 : 1);
     for (int t = tid; t < K * JG; t += kMidThreads) {
@@ -443,26 +463,45 @@ __device__ __forceinline__ void ppc_role(const MidArgs& a, int b, float* sm) {
         dsl[j * K + r] = 2.0f * dw * dact_of_dist(d, a.act_fn, a.eps);        // factor 2 of d|z-p|^2 folded in
     }
     __syncthreads();
-    // token rows: dZ[b,k,:] = sum_j dd[j,k] (Z[b,k,:] - P_j), one warp per token
+    // token rows: dZ[b,k,:] = Z[b,k,:] sum_j dd[j,k] - sum_j dd[j,k] P_j; one warp per token, a lane owns 4 features
+    // of a 128-feature group (one broadcast read of dd and one 16-byte read of P_j per 4 FMAs)
+    const int ngrp = (D + 127) >> 7;
     for (int r = warp; r < K; r += nwarp) {
+        float S = 0.f;
+        for (int j = 0; j < m; ++j) S += dsl[j * K + r];
         float* out = a.dZs_ppc + ((size_t)b * K + r) * D;
-        for (int d = lane; d < D; d += 32) {
-            const float z = Zt[(size_t)r * zs + d];
-            float acc = 0.f;
-            for (int j = 0; j < m; ++j) acc = fmaf(dsl[j * K + r], z - Prow[j * D + d], acc);
-            out[d] = acc;
+        for (int g = 0; g < ngrp; ++g) {
+            const int d = g * 128 + lane * 4;
+            if (d >= D) continue;
+            const float4 z = *reinterpret_cast<const float4*>(Zt + (size_t)r * zs + d);
+            float4 acc = make_float4(z.x * S, z.y * S, z.z * S, z.w * S);
+#pragma unroll 2
+            for (int j = 0; j < m; ++j) {
+                const float c = -dsl[j * K + r];
+                const float4 p = *reinterpret_cast<const float4*>(Prow + j * D + d);
+                acc.x = fmaf(c, p.x, acc.x); acc.y = fmaf(c, p.y, acc.y); acc.z = fmaf(c, p.z, acc.z); acc.w = fmaf(c, p.w, acc.w);
+            }
+            *reinterpret_cast<float4*>(out + d) = acc;
         }
     }
     // prototype rows of THIS image (summed over the images of a class by the prototype-gradient kernel, in image
-    // order: deterministic, unlike the atomics of pph_ppc_bwd): dP_img[b,j,:] = sum_k dd[j,k] (P_j - Z[b,k,:])
-    for (int j = warp; j < m; j += nwarp) {
-        float* out = a.dP_img + ((size_t)b * m + j) * D;
-        for (int d = lane; d < D; d += 32) {
-            const float pj = Prow[j * D + d];
-            float acc = 0.f;
-            for (int r = 0; r < K; ++r) acc = fmaf(dsl[j * K + r], pj - Zt[(size_t)r * zs + d], acc);
-            out[d] = acc;
+    // order: deterministic, unlike the atomics of pph_ppc_bwd): dP_img[b,j,:] = P_j sum_k dd[j,k] - sum_k dd[j,k] Z[b,k,:]
+    for (int it = warp; it < m * ngrp; it += nwarp) {       // work item = (prototype, 128-feature group)
+        const int j = it / ngrp, g = it - j * ngrp;
+        const int d = g * 128 + lane * 4;
+        if (d >= D) continue;
+        float S = 0.f;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int r = 0; r < K; ++r) {
+            const float c = dsl[j * K + r];
+            const float4 z = *reinterpret_cast<const float4*>(Zt + (size_t)r * zs + d);
+            S += c;
+            acc.x = fmaf(c, z.x, acc.x); acc.y = fmaf(c, z.y, acc.y); acc.z = fmaf(c, z.z, acc.z); acc.w = fmaf(c, z.w, acc.w);
         }
+        const float4 p = *reinterpret_cast<const float4*>(Prow + j * D + d);
+        *reinterpret_cast<float4*>(a.dP_img + ((size_t)b * m + j) * D + d) =
+            make_float4(p.x * S - acc.x, p.y * S - acc.y, p.z * S - acc.z, p.w * S - acc.w);
     }
 }
 
@@ -475,10 +514,22 @@ head_mid_kernel(const MidArgs a) {
     if (bid < a.n_ll) {
         ll_role<CJ>(a, sm_mid);
     } else if (bid < a.n_ll + a.n_bin) {
-        bin_tokens_body(bid - a.n_ll, a.argmin_l, a.K, a.P, a.bin_start, a.item_start, a.bin_list,
+        bin_tokens_body<false>(bid - a.n_ll, a.argmin_l, a.K, a.P, a.bin_start, a.item_start, a.bin_list,
                         reinterpret_cast<int*>(sm_mid));
-    } else {
+    } else if (bid < a.n_ll + a.n_bin + a.n_ppc) {
         ppc_role(a, bid - a.n_ll - a.n_bin, sm_mid);
+    } else {
+        // role CLS (one CTA): the images sorted by clamped label (stable counting sort: image order inside a class)
+        const int n_cls = a.P / a.m;
+        for (int b = threadIdx.x; b < a.B; b += kMidThreads) {
+            long y = a.labels[b];
+            if (y < 0) y = 0;
+            if (y * a.m + a.m > a.P) y = a.P / a.m - 1;
+            a.cls_id[b] = (int)y;
+        }
+        __threadfence();
+        __syncthreads();
+        bin_tokens_body<true>(0, a.cls_id, n_cls, a.B, a.cls_start, a.cls_item, a.cls_order, reinterpret_cast<int*>(sm_mid));
     }
 }
 
@@ -597,13 +648,18 @@ extern "C" int pph_head_mid(const float* act_l, const float* act_g, const float*
     a.part = w.part; a.dlT = w.dlT; a.ce_part = w.ce_part; a.ppc_part = w.ppc_part; a.ppc_losses = w.ppc_losses;
     a.ctr = w.ctr;
     a.bin_start = a.item_start = a.bin_list = nullptr;
+    a.cls_id = a.cls_start = a.cls_item = a.cls_order = nullptr;
+    a.n_cls_cta = 0;
     if (train) {
         const Step2Bins bw = carve_bins(bwd_workspace, B, K, P);
         a.bin_start = bw.bin_start; a.item_start = bw.item_start; a.bin_list = bw.bin_list;
+        a.cls_id = bw.cls_id; a.cls_start = bw.cls_start; a.cls_item = bw.cls_item; a.cls_order = bw.cls_order;
+        if (use_ppc && bin_tokens_smem_bytes(P / m) <= 200 * 1024) a.n_cls_cta = 1;
     }
     a.Zs = Zs; a.z2s = z2s; a.Pl = Pl; a.p2l = p2l; a.idx = idx32; a.dZs_ppc = dZs_ppc; a.dP_img = dP_img;
     size_t smem = p.smem_ll;
     if (a.n_bin && p.smem_bin > smem) smem = p.smem_bin;
+    if (a.n_cls_cta && bin_tokens_smem_bytes(P / m) > smem) smem = bin_tokens_smem_bytes(P / m);
     if (use_ppc) {
         PPH_REQUIRE(D % 4 == 0 && a.side * a.side == N && P >= m, PPH_EINVAL, "pph_head_mid: bad PPC dims");
         PPH_REQUIRE(p.smem_ppc <= 200 * 1024, PPH_EUNSUP, "pph_head_mid: an image's K x D slice does not fit shared memory");
@@ -614,7 +670,8 @@ extern "C" int pph_head_mid(const float* act_l, const float* act_g, const float*
     PPH_REQUIRE(p.n_ll <= max_ctas, PPH_EUNSUP, "pph_head_mid: B=%d needs %d co-resident CTAs (> %d SMs)", B, p.n_ll,
                 max_ctas);
     const int cj = ceil_div(C, 32);
-    const dim3 grid(a.n_ll + a.n_bin + a.n_ppc), block(kMidThreads);
+    PPH_REQUIRE(!(use_ppc && train) || a.n_cls_cta == 1, PPH_EUNSUP, "pph_head_mid: too many classes");
+    const dim3 grid(a.n_ll + a.n_bin + a.n_ppc + a.n_cls_cta), block(kMidThreads);
     cudaStream_t st = as_stream(stream);
 #define PPH_MID(CJ)                                                                                                   \
     do {                                                                                                              \

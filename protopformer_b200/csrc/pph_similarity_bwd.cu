@@ -18,7 +18,7 @@ bin_tokens_kernel(const int32_t* __restrict__ argmin_l, int K, int P, int32_t* _
                   int32_t* __restrict__ item_start, int32_t* __restrict__ bin_list) {
     pdl_sync();
     extern __shared__ int smi[];
-    bin_tokens_body(blockIdx.x, argmin_l, K, P, bin_start, item_start, bin_list, smi);
+    bin_tokens_body<false>(blockIdx.x, argmin_l, K, P, bin_start, item_start, bin_list, smi);
 }
 
 // ---- gather kernels (templated on DV = ceil(D / 32) register slots per lane) ---------------------------------------

@@ -9,8 +9,11 @@ namespace pph {
 //   bin_start [B][K+1]  offsets into bin_list[b], bin k = entries [bin_start[k], bin_start[k+1])
 //   bin_list  [B][P]    the image's prototypes sorted by argmin token (stable: ascending inside a bin)
 //   item_start[B][K+1]  work-item offsets of the round-1 gradient kernel (unused by the new one)
+//   cls_id [B], cls_start [n_cls+1], cls_item [n_cls+1], cls_order [B]: the images sorted by (clamped) label, stable --
+//   the prototype-gradient kernel adds the per-image PPC rows of a class in image order
 struct Step2Bins {
     int32_t *bin_start, *item_start, *bin_list;
+    int32_t *cls_id, *cls_start, *cls_item, *cls_order;
     size_t bytes;
 };
 
@@ -22,6 +25,10 @@ inline Step2Bins carve_bins(void* base, int B, int K, int P) {
     w.bin_start = reinterpret_cast<int32_t*>(take(sizeof(int) * (size_t)B * (K + 1)));
     w.item_start = reinterpret_cast<int32_t*>(take(sizeof(int) * (size_t)B * (K + 1)));
     w.bin_list = reinterpret_cast<int32_t*>(take(sizeof(int) * (size_t)B * P));
+    w.cls_id = reinterpret_cast<int32_t*>(take(sizeof(int) * (size_t)B));
+    w.cls_start = reinterpret_cast<int32_t*>(take(sizeof(int) * (size_t)(P + 1)));      // n_cls = P / m <= P
+    w.cls_item = reinterpret_cast<int32_t*>(take(sizeof(int) * (size_t)(P + 1)));
+    w.cls_order = reinterpret_cast<int32_t*>(take(sizeof(int) * (size_t)B));
     w.bytes = off + 256;
     return w;
 }

@@ -26,7 +26,7 @@ class GraphedHeadStep:
     def __init__(self, params: dict, cfg: ops.HeadConfig, B: int, N: int, C: int, m: int, n_slots: int = 1,
                  heads: int = 0, ppc_cov_coe: float = 0.1, ppc_mean_coe: float = 0.5, train: bool = True,
                  process_group=None, device=None, fused: bool = True, allreduce_in_graph: bool = False,
-                 schedule: int | None = None, use_ppc: bool = True, impl: str = "auto"):
+                 schedule: int | None = None, use_ppc: bool = True, impl: str = "auto", variants=None):
         """params: dict with Wa (D,Din), ba (D), P (P,D), Pg (Pg,D) [leaf tensors, requires_grad in training] and
         the frozen Wl (C,P), Wg (C,Pg).  ppc_*_coe follow scripts/train_cub.sh:43-44."""
         self.p, self.cfg, self.B, self.N, self.C, self.m = params, cfg, B, N, C, m
@@ -59,8 +59,9 @@ class GraphedHeadStep:
                 impl = "v2" if ops.fused_step_supported(B, N, Din, D, cfg.K, P, Pg, C, m) else "v1"
             self.impl = impl
             cls = ops.FusedHeadStep if impl == "v2" else ops.FusedHeadStepV1
+            kw = dict(variants=variants) if impl == "v2" else {}
             self.fused = cls(cfg, B, N, Din, D, P, Pg, C, m, dev, heads=heads, ppc_cov_coe=ppc_cov_coe,
-                             ppc_mean_coe=ppc_mean_coe, train=train, use_ppc=use_ppc, schedule=schedule)
+                             ppc_mean_coe=ppc_mean_coe, train=train, use_ppc=use_ppc, schedule=schedule, **kw)
             if train:
                 self.grads = dict(zip(("P", "Pg", "Wa", "ba"), self.reducer.views))
 

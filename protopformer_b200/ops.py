@@ -647,7 +647,7 @@ class FusedHeadStep:
       pph_head_prep        selection + gather + add-on + sigmoid + bf16 operands (tokens and both prototype tensors)
       pph_similarity_fwd   tcgen05 distances, log similarity, min / argmin over tokens (the (B,P,K) map stays in TMEM)
       pph_head_mid         last layers + cross-entropy + last-layer backward || token bins || PPC loss fwd + bwd
-      pph_similarity_bwd2  dP, dPg, dZs, dZc (+ the PPC gradients)              [training]
+      pph_similarity_bwd2  x3 concurrent kinds: token rows | prototype rows | CLS rows (+ the PPC gradients)   [training]
       pph_addon_bwd2       dWa, dba, dtokens                                    [training]
 
     Same results interface as FusedHeadStepV1: losses (4,) = (total, ce, ppc_cov, ppc_mean), logits, logits_g, logits_l,
@@ -655,10 +655,21 @@ class FusedHeadStep:
     (keys Wa, ba, P, Pg -- e.g. views of one flat all-reduce buffer).  Reference: tools/engine_proto.py:49-76."""
 
     def __init__(self, cfg: HeadConfig, B, N, Din, D, P, Pg, C, m, device, heads: int = 0, ppc_cov_coe: float = 0.1,
-                 ppc_mean_coe: float = 0.5, train: bool = True, use_ppc: bool = True, schedule=None):
+                 ppc_mean_coe: float = 0.5, train: bool = True, use_ppc: bool = True, schedule=None, variants=None):
         if not fused_step_supported(B, N, Din, D, cfg.K, P, Pg, C, m):
             raise ValueError("shape outside the five-launch step: use FusedHeadStepV1")
         self.cfg, self.train, self.use_ppc = cfg, train, use_ppc
+        # kernel choice per stage: "tc" = single-shot tcgen05 kernels (pph_addon_fwd2 / pph_addon_bwd3) where the shape
+        # allows, "simt" = the exact-FP32 CUDA-core kernels (pph_head_prep / pph_addon_bwd2)
+        tc_bits = _lib.load().pph_addon_tc2_supported(B, N, Din, D, cfg.K)
+        v = {"prep": "tc" if (tc_bits & 1) else "simt",
+             "addon_bwd": "tc" if (tc_bits & 6) == 6 else "simt"}
+        v.update(variants or {})
+        if v["prep"] == "tc" and not (tc_bits & 1):
+            v["prep"] = "simt"
+        if v["addon_bwd"] == "tc" and (tc_bits & 6) != 6:
+            v["addon_bwd"] = "simt"
+        self.variants = v
         self.dims = (B, N, Din, D, P, Pg, C, m, heads)
         self.cov_coe, self.mean_coe = float(ppc_cov_coe), float(ppc_mean_coe)
         K = cfg.K
@@ -683,28 +694,60 @@ class FusedHeadStep:
         self.logits, self.logits_g, self.logits_l = e(B, C), e(B, C), e(B, C)
         self.losses = torch.zeros(4, dtype=f32, device=device)
         self.ws_mid = _ws("pph_head_mid_ws_bytes", B, K, D, P, Pg, C, m, zero=True, device=device)
+        self.ws_tc = _ws("pph_addon_tc2_ws_bytes", B, N, Din, D, K, zero=True, device=device)
+        self.side = torch.cuda.Stream(device=device)
+        self.side2 = torch.cuda.Stream(device=device)
+        self.ev = [torch.cuda.Event() for _ in range(6)]
         self.dlogits = self.g_l = self.g_g = self.pairT = self.ws_bins = None
         self.dZs_ppc = self.dP_img = None
         if train:
             Bp = (B + 63) // 64 * 64
             self.dlogits, self.g_l, self.g_g = e(B, C), e(B, P), e(B, Pg)
             self.pairT = e(P + Pg, Bp, 2)
-            self.ws_bins = _ws("pph_similarity_bwd2_ws_bytes", B, K, P, zero=False, device=device)
+            self.ws_bins = _ws("pph_similarity_bwd2_ws_bytes", B, K, D, P, zero=True, device=device)
             if use_ppc:
                 self.dZs_ppc, self.dP_img = e(B, K, D), e(B, m, D)
             self.dZs, self.dZc = e(B, K, D), e(B, D)
             self.dtokens = e(B, 1 + N, Din)
             self.ws_addon = _ws("pph_addon_bwd2_ws_bytes", B, N, Din, D, K, zero=True, device=device)
+            if self.variants["addon_bwd"] == "tc":
+                self.dtokens.zero_()
+
 
     def step(self, tokens, scores, labels, Wa, ba, P, Pg, Wl, Wg, grads=None, upstream: float = 1.0):
         B, N, Din, D, Pn, Pgn, C, m, H = self.dims
         cfg, K = self.cfg, self.cfg.K
         c = _lib.call
-        c("pph_head_prep", scores, tokens, Wa, ba, B, max(H, 1), N, Din, D, K, float(cfg.center), self.idx32, None,
-          self.Zs, self.Zc, self.z2s, self.z2c, self.z2s_ctr, self.z2c_ctr, self.z2s_hi, self.z2c_hi,
-          self.Zs_hi, self.Zs_lo, self.Zc_hi, self.Zc_lo,
-          P, Pn, self.P_hi, self.P_lo, self.p2, self.p2_ctr, self.p2_hi,
-          Pg, Pgn, self.Pg_hi, self.Pg_lo, self.pg2, self.pg2_ctr, self.pg2_hi)
+        main, side, side2, ev = torch.cuda.current_stream(), self.side, self.side2, self.ev
+        if self.variants["prep"] == "tc":
+            # selection -> single-shot tcgen05 add-on || operand split of both prototype tensors (side branch)
+            ev[3].record(main)
+            side.wait_event(ev[3])
+            with torch.cuda.stream(side):
+                c("pph_split_rows", P, Pn, D, float(cfg.center), self.P_hi, self.P_lo, self.p2, self.p2_ctr, self.p2_hi)
+                c("pph_split_rows", Pg, Pgn, D, float(cfg.center), self.Pg_hi, self.Pg_lo, self.pg2, self.pg2_ctr, self.pg2_hi)
+                if self.train and self.variants["addon_bwd"] == "tc":
+                    self.dtokens.zero_()            # rows of unselected tokens: a memset node off the critical path
+                ev[4].record(side)
+            c("pph_select_topk", scores, B, max(H, 1), N, K, self.idx32, None)
+            c("pph_addon_fwd2", tokens, self.idx32, Wa, ba, B, N, Din, D, K, self.Zs, self.Zc, self.z2s, self.z2c,
+              float(cfg.center), self.z2s_ctr, self.z2c_ctr, self.z2s_hi, self.z2c_hi, self.Zs_hi, self.Zs_lo,
+              self.Zc_hi, self.Zc_lo, self.ws_tc)
+            main.wait_event(ev[4])
+        else:
+            if self.train and self.variants["addon_bwd"] == "tc":
+                ev[3].record(main)
+                side.wait_event(ev[3])
+                with torch.cuda.stream(side):
+                    self.dtokens.zero_()
+                    ev[4].record(side)
+            c("pph_head_prep", scores, tokens, Wa, ba, B, max(H, 1), N, Din, D, K, float(cfg.center), self.idx32, None,
+              self.Zs, self.Zc, self.z2s, self.z2c, self.z2s_ctr, self.z2c_ctr, self.z2s_hi, self.z2c_hi,
+              self.Zs_hi, self.Zs_lo, self.Zc_hi, self.Zc_lo,
+              P, Pn, self.P_hi, self.P_lo, self.p2, self.p2_ctr, self.p2_hi,
+              Pg, Pgn, self.Pg_hi, self.Pg_lo, self.pg2, self.pg2_ctr, self.pg2_hi)
+            if self.train and self.variants["addon_bwd"] == "tc":
+                main.wait_event(ev[4])
         mode = cfg.mode_id
         sel = {_lib.MODE_FP32_FMA: 0, _lib.MODE_BF16X3: 1, _lib.MODE_BF16: 2}[mode]
         c("pph_similarity_fwd", mode, cfg.act_id, float(cfg.eps), B, K, D, Pn, Pgn, self.Zs, self.Zc,
@@ -722,9 +765,34 @@ class FusedHeadStep:
           self.g_l, self.g_g, self.pairT, self.dZs_ppc if ppc else None, self.dP_img if ppc else None)
         if not self.train:
             return self.losses
-        c("pph_similarity_bwd2", self.g_l, self.g_g, self.pairT, self.ws_bins, self.Zs, self.Zc, P, Pg,
-          B, K, D, Pn, Pgn, m, self.dZs_ppc if ppc else None, self.dP_img if ppc else None, labels if ppc else None,
-          self.dZs, self.dZc, grads["P"], grads["Pg"])
-        c("pph_addon_bwd2", tokens, self.idx32, Wa, self.Zs, self.Zc, self.dZs, self.dZc, B, N, Din, D, K,
-          self.ws_addon, grads["Wa"], grads["ba"], self.dtokens)
+        # dZs / dZc leave the backward already multiplied by Z (1 - Z) (dpre_out = 1): what pph_addon_bwd2 consumes
+        bwd = lambda parts: c("pph_similarity_bwd2", parts, self.g_l, self.g_g, self.pairT, self.ws_bins, self.Zs, self.Zc,  # noqa: E731
+                              P, Pg, B, K, D, Pn, Pgn, m, self.dZs_ppc if ppc else None, self.dP_img if ppc else None, 1,
+                              self.dZs, self.dZc, grads["P"], grads["Pg"])
+        ev[0].record(main)
+        side.wait_event(ev[0])
+        side2.wait_event(ev[0])
+        with torch.cuda.stream(side):
+            bwd(2)                      # prototype rows: not needed by the add-on backward, joins at the end
+            ev[1].record(side)
+        with torch.cuda.stream(side2):
+            bwd(4)                      # CLS rows
+            ev[2].record(side2)
+        bwd(1)                          # token rows
+        main.wait_event(ev[2])
+        if self.variants["addon_bwd"] == "tc":
+            # weight gradient (112 CTAs behind a grid barrier) || token gradient (82 CTAs): two graph branches
+            ev[5].record(main)
+            side2.wait_event(ev[5])
+            with torch.cuda.stream(side2):
+                c("pph_addon_bwd3", 2, tokens, self.idx32, Wa, self.dZs, self.dZc, B, N, Din, D, K, self.ws_tc,
+                  None, None, self.dtokens)
+                ev[2].record(side2)
+            c("pph_addon_bwd3", 1, tokens, self.idx32, Wa, self.dZs, self.dZc, B, N, Din, D, K, self.ws_tc,
+              grads["Wa"], grads["ba"], None)
+            main.wait_event(ev[2])
+        else:
+            c("pph_addon_bwd2", 3, tokens, self.idx32, Wa, self.dZs, self.dZc, B, N, Din, D, K,
+              self.ws_addon, grads["Wa"], grads["ba"], self.dtokens)
+        main.wait_event(ev[1])
         return self.losses

@@ -9,6 +9,12 @@ case $stage in
       timeout 600 python -m pytest tests/test_step2_gpu.py -q --tb=short -k "$k" > gpurun_out/t_$n.log 2>&1
       echo "== $k: rc=$? $(tail -1 gpurun_out/t_$n.log)"
     done ;;
+  t_*)        # one pytest -k group of tests/test_step2_gpu.py:  t_similarity_bwd2, t_head_mid, ...
+    k=${stage#t_}
+    timeout 600 python -m pytest tests/test_step2_gpu.py -q --tb=short -k "$k" > gpurun_out/t_$k.log 2>&1
+    echo "== $k: rc=$? $(tail -1 gpurun_out/t_$k.log)" ;;
+  times64)
+    timeout 300 python scripts/step_times.py cub_b64 fp32 > gpurun_out/times_b64.json 2> gpurun_out/times_b64.err; tail -c 1500 gpurun_out/times_b64.json ;;
   times)
     timeout 300 python scripts/step_times.py cub_b64 fp32 > gpurun_out/times_b64.json 2> gpurun_out/times_b64.err; tail -c 1500 gpurun_out/times_b64.json
     timeout 300 python scripts/step_times.py cub_b64 fp32 1024 > gpurun_out/times_b1024.json 2> gpurun_out/times_b1024.err; tail -c 1500 gpurun_out/times_b1024.json ;;
@@ -20,6 +26,15 @@ case $stage in
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:"head_prep|similarity_tc2|head_mid|sim_grads2|addon_bwd2" \
         -s 5 -c 5 -o gpurun_out/r2_step2 -f python scripts/run_step.py cub_b64 fp32 v2 3 > gpurun_out/ncu2.log 2>&1
     echo "== ncu2 rc=$?"; tail -3 gpurun_out/ncu2.log ;;
+  ncuk_*)     # --set full capture of the kernels matching the regex after ncuk_ (five-launch step, second eager step)
+    k=${stage#ncuk_}
+    timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$k" -s 0 -c 6 -o gpurun_out/r2_$k -f \
+        python scripts/run_step.py cub_b64 fp32 v2 3 > gpurun_out/ncuk_$k.log 2>&1
+    echo "== ncuk $k rc=$?"; tail -2 gpurun_out/ncuk_$k.log ;;
+  ncu1)       # same capture of the round-1 launch sequence (reference point for the A/B)
+    timeout 900 ncu --set full --clock-control none --import-source on -s 32 -c 16 -o gpurun_out/r2_step1 -f \
+        python scripts/run_step.py cub_b64 fp32 v1 3 > gpurun_out/ncu1.log 2>&1
+    echo "== ncu1 rc=$?"; tail -3 gpurun_out/ncu1.log ;;
   all)
     timeout 1500 python -m pytest tests -q -m gpu --tb=short > gpurun_out/t_all.log 2>&1; echo "== all: rc=$? $(tail -1 gpurun_out/t_all.log)" ;;
   bench)

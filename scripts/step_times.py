@@ -43,11 +43,11 @@ def timed_graph(fn, rep=REP, outer=10):
     return 1e3 * e0.elapsed_time(e1) / (outer * rep)
 
 
-def make(impl, train=True):
+def make(impl, train=True, variants=None):
     params = {k: case[k].to(dev).clone() for k in ("Wa", "ba", "P", "Pg", "Wl", "Wg")}
     for k in ("Wa", "ba", "P", "Pg"):
         params[k].requires_grad_(train)
-    st = GraphedHeadStep(params, cfg, B=s.B, N=s.N, C=s.C, m=s.m, train=train, impl=impl)
+    st = GraphedHeadStep(params, cfg, B=s.B, N=s.N, C=s.C, m=s.m, train=train, impl=impl, variants=variants)
     st.load(0, case["tokens"], case["scores"], case["labels"])
     torch.cuda.synchronize()
     st.capture()
@@ -55,12 +55,17 @@ def make(impl, train=True):
 
 
 out = {"shape": key, "B": s.B, "mode": mode}
-for impl in ("v1", "v2"):
+ARMS = [("v1", None), ("v2", dict(prep="simt", addon_bwd="simt")), ("v2", dict(prep="tc", addon_bwd="simt")),
+        ("v2", dict(prep="simt", addon_bwd="tc")), ("v2", dict(prep="tc", addon_bwd="tc"))]
+for impl, variants in ARMS:
     for train in (True, False):
+        if not train and variants is not None and variants["addon_bwd"] == "tc":
+            continue
+        tag = impl if variants is None else f"v2[{variants['prep']},{variants['addon_bwd']}]"
         try:
-            st, _ = make(impl, train)
+            st, _ = make(impl, train, variants)
         except Exception as exc:
-            out[f"{impl}_{'train' if train else 'eval'}"] = f"failed: {exc}"
+            out[f"{tag}_{'train' if train else 'eval'}"] = f"failed: {exc}"
             continue
         for _ in range(20):
             st.run(0)
@@ -72,9 +77,8 @@ for impl in ("v1", "v2"):
         e1.record()
         torch.cuda.synchronize()
         us = 1e3 * e0.elapsed_time(e1) / 300
-        out[f"{impl}_{'train' if train else 'eval'}"] = {"us": us, "launches": st.kernel_launches_per_step,
-                                                           "images_per_s": s.B / us * 1e6}
-        if impl == "v2" and train:
+        out[f"{tag}_{'train' if train else 'eval'}"] = {"us": round(us, 2), "launches": st.kernel_launches_per_step}
+        if impl == "v2" and train and variants == dict(prep="simt", addon_bwd="simt"):
             f = st.fused
             p = st.p
             grads = st.grads
@@ -105,13 +109,31 @@ for impl in ("v1", "v2"):
                 per["head_mid"] = timed_graph(lambda: mid(1, 1))
                 per["head_mid(no ppc)"] = timed_graph(lambda: mid(1, 0))
                 per["head_mid(eval)"] = timed_graph(lambda: mid(0, 0))
-                per["similarity_bwd2"] = timed_graph(lambda: c(
-                    "pph_similarity_bwd2", f.g_l, f.g_g, f.pairT, f.ws_bins, f.Zs, f.Zc, p["P"], p["Pg"], B, K, D, Pn, Pgn,
-                    m, f.dZs_ppc, f.dP_img, lab, f.dZs, f.dZc, grads["P"], grads["Pg"]))
-                per["addon_bwd2"] = timed_graph(lambda: c(
-                    "pph_addon_bwd2", tok, f.idx32, p["Wa"], f.Zs, f.Zc, f.dZs, f.dZc, B, N, Din, D, K, f.ws_addon,
-                    grads["Wa"], grads["ba"], f.dtokens))
+                def bwd2(parts):
+                    c("pph_similarity_bwd2", parts, f.g_l, f.g_g, f.pairT, f.ws_bins, f.Zs, f.Zc, p["P"], p["Pg"], B, K, D, Pn,
+                      Pgn, m, f.dZs_ppc, f.dP_img, 1, f.dZs, f.dZc, grads["P"], grads["Pg"])
+                per["similarity_bwd2[all, serial]"] = timed_graph(lambda: bwd2(7))
+                for mask, nm in ((1, "tokens"), (2, "protos"), (4, "cls")):
+                    per[f"similarity_bwd2[{nm}]"] = timed_graph(lambda: bwd2(mask))
+
+                def ab2(parts):
+                    c("pph_addon_bwd2", parts, tok, f.idx32, p["Wa"], f.dZs, f.dZc, B, N, Din, D, K, f.ws_addon,
+                      grads["Wa"], grads["ba"], f.dtokens)
+                per["addon_bwd2"] = timed_graph(lambda: ab2(3))
+                per["addon_bwd2[wgrad]"] = timed_graph(lambda: ab2(1))
+                per["addon_bwd2[dgrad]"] = timed_graph(lambda: ab2(2))
+
+                def ab3(parts):
+                    c("pph_addon_bwd3", parts, tok, f.idx32, p["Wa"], f.dZs, f.dZc, B, N, Din, D, K, f.ws_tc,
+                      grads["Wa"], grads["ba"], f.dtokens)
+                per["addon_bwd3[wgrad]"] = timed_graph(lambda: ab3(1))
+                per["addon_bwd3[dgrad]"] = timed_graph(lambda: ab3(2))
+                per["select_topk"] = timed_graph(lambda: c("pph_select_topk", sc, B, max(H, 1), N, K, f.idx32, None))
+                per["addon_fwd2"] = timed_graph(lambda: c(
+                    "pph_addon_fwd2", tok, f.idx32, p["Wa"], p["ba"], B, N, Din, D, K, f.Zs, f.Zc, f.z2s, f.z2c, 0.5,
+                    f.z2s_ctr, f.z2c_ctr, f.z2s_hi, f.z2c_hi, f.Zs_hi, f.Zs_lo, f.Zc_hi, f.Zc_lo, f.ws_tc))
+                per = {k: round(v, 2) for k, v in per.items()}
             out["v2_per_launch_us"] = per
             out["v2_sum_of_launches_us"] = (per["head_prep"] + per["similarity_fwd"] + per["head_mid"] +
-                                            per["similarity_bwd2"] + per["addon_bwd2"])
+                                            per["similarity_bwd2[all, serial]"] + per["addon_bwd2"])
 print(json.dumps(out))

@@ -144,7 +144,7 @@ def _run_mid(shape, d, cfg, idx, tf, pl, dmin_l, argmin, act_l, dmin_g, act_g, t
     o = dict(logits=_e(B, C), logits_g=_e(B, C), logits_l=_e(B, C), losses=torch.zeros(4, device=DEV), dlogits=_e(B, C),
              g_l=_e(B, P), g_g=_e(B, Pg), pairT=_e(P + Pg, Bp, 2), dZs_ppc=_e(B, K, D), dP_img=_e(B, m, D))
     o["ws"] = ops._ws("pph_head_mid_ws_bytes", B, K, D, P, Pg, C, m, zero=True, device=DEV)
-    o["bins"] = ops._ws("pph_similarity_bwd2_ws_bytes", B, K, P, zero=False, device=DEV)
+    o["bins"] = ops._ws("pph_similarity_bwd2_ws_bytes", B, K, D, P, zero=True, device=DEV)
     for _ in range(2):      # twice: the counters must self-reset
         L.call("pph_head_mid", act_l, act_g, dmin_l, dmin_g, argmin, d["Wl"], d["Wg"], d["labels"],
                B, K, D, P, Pg, C, m, N, float(shape.global_coe), cfg.act_id, float(cfg.eps), float(upstream),
@@ -267,17 +267,29 @@ def test_similarity_bwd2_matches_round1_kernel(key, seed):
     L.call("pph_similarity_bwd", o["g_l"], o["g_g"], argmin, tf.Zs, tf.Zc, Pl2, Pg2, B, K, D, P, Pg, ws, 3,
            o["dZs_ppc"], dP_ppc, r["dZs"], r["dZc"], r["dP"], r["dPg"])
     n = dict(dZs=_e(B, K, D), dZc=_e(B, D), dP=_e(P, D), dPg=_e(Pg, D))
+
+    def bwd2(parts, add, dpi, dpre_out=0):
+        L.call("pph_similarity_bwd2", parts, o["g_l"], o["g_g"], o["pairT"], o["bins"], tf.Zs, tf.Zc, Pl2, Pg2, B, K, D, P,
+               Pg, m, add, dpi, dpre_out, n["dZs"], n["dZc"], n["dP"], n["dPg"])
+
     for _ in range(2):
-        L.call("pph_similarity_bwd2", o["g_l"], o["g_g"], o["pairT"], o["bins"], tf.Zs, tf.Zc, Pl2, Pg2, B, K, D, P, Pg,
-               m, o["dZs_ppc"], o["dP_img"], d["labels"], n["dZs"], n["dZc"], n["dP"], n["dPg"])
+        bwd2(7, o["dZs_ppc"], o["dP_img"])
     torch.cuda.synchronize()
     for k in r:
         assert norm_rel(n[k].cpu(), r[k].cpu()) < 1e-5, (k, norm_rel(n[k].cpu(), r[k].cpu()))
+    # the three kinds one by one (as the step launches them), with the Z (1 - Z) factor folded in
+    for k in n:
+        n[k].fill_(7.0)
+    for parts in (1, 2, 4):
+        bwd2(parts, o["dZs_ppc"], o["dP_img"], 1)
+    torch.cuda.synchronize()
+    assert norm_rel(n["dZs"].cpu(), (r["dZs"] * tf.Zs * (1 - tf.Zs)).cpu()) < 1e-5
+    assert norm_rel(n["dZc"].cpu(), (r["dZc"] * tf.Zc * (1 - tf.Zc)).cpu()) < 1e-5
+    assert norm_rel(n["dP"].cpu(), r["dP"].cpu()) < 1e-5 and norm_rel(n["dPg"].cpu(), r["dPg"].cpu()) < 1e-5
     # without the PPC inputs
     L.call("pph_similarity_bwd", o["g_l"], o["g_g"], argmin, tf.Zs, tf.Zc, Pl2, Pg2, B, K, D, P, Pg, ws, 3,
            None, None, r["dZs"], r["dZc"], r["dP"], r["dPg"])
-    L.call("pph_similarity_bwd2", o["g_l"], o["g_g"], o["pairT"], o["bins"], tf.Zs, tf.Zc, Pl2, Pg2, B, K, D, P, Pg,
-           m, None, None, None, n["dZs"], n["dZc"], n["dP"], n["dPg"])
+    bwd2(7, None, None)
     torch.cuda.synchronize()
     for k in r:
         assert norm_rel(n[k].cpu(), r[k].cpu()) < 1e-5, (k, norm_rel(n[k].cpu(), r[k].cpu()))
@@ -297,9 +309,15 @@ def test_addon_bwd2_matches_float64(key, seed):
     dZs, dZc = torch.randn(B, K, D, generator=g) * 1e-2, torch.randn(B, D, generator=g) * 1e-2
     ws = ops._ws("pph_addon_bwd2_ws_bytes", B, N, Din, D, K, zero=True, device=DEV)
     dWa, dba, dtok = _e(D, Din), _e(D), torch.full((B, 1 + N, Din), 7.0, device=DEV)
-    for _ in range(2):
-        L.call("pph_addon_bwd2", d["tokens"], idx, d["Wa"].reshape(D, Din), tf.Zs, tf.Zc, dZs.to(DEV), dZc.to(DEV), B, N,
-               Din, D, K, ws, dWa, dba, dtok)
+    dpre_s = (dZs.to(DEV) * tf.Zs * (1 - tf.Zs)).contiguous()
+    dpre_c = (dZc.to(DEV) * tf.Zc * (1 - tf.Zc)).contiguous()
+    for parts in ((3,), (3,), (1, 2)):          # both roles in one launch (twice: self-resetting tickets), then separately
+        dWa.fill_(7.0)
+        dba.fill_(7.0)
+        dtok.fill_(7.0)
+        for pt in parts:
+            L.call("pph_addon_bwd2", pt, d["tokens"], idx, d["Wa"].reshape(D, Din), dpre_s, dpre_c, B, N, Din, D, K, ws,
+                   dWa, dba, dtok)
     torch.cuda.synchronize()
     Z = torch.cat([tf.Zs.cpu(), tf.Zc.cpu()[:, None]], 1).double()
     dZ = torch.cat([dZs, dZc[:, None]], 1).double()
@@ -315,16 +333,103 @@ def test_addon_bwd2_matches_float64(key, seed):
     assert bool((dtok.cpu()[ref_dtok == 0] == 0).all())               # unselected token rows are exact zeros
 
 
+TC2_CASES = [("cub_b8", 1), ("cub_b64", 3), ("cars_b64", 4), ("sweep_k49", 2), ("sweep_k196", 1)]
+
+
+@pytest.mark.parametrize("key,seed", TC2_CASES)
+def test_addon_fwd2_single_shot_matches_oracle(key, seed):
+    """pph_addon_fwd2 (single-shot tcgen05, columns split over CTAs, norms completed by the last column tile)."""
+    ops, L = _ops(), _lib()
+    shape = synth.SHAPES[key]
+    case = synth.make_case(shape, seed=seed)
+    d = _d(case)
+    B, N, Din, D, K = shape.B, shape.N, shape.Din, shape.D, shape.K
+    assert L.load().pph_addon_tc2_supported(B, N, Din, D, K) & 1
+    idx = ops.select_topk(d["scores"], K)
+    bf = torch.bfloat16
+    o = dict(Zs=_e(B, K, D), Zc=_e(B, D), z2s=_e(B, K), z2c=_e(B), z2s_ctr=_e(B, K), z2c_ctr=_e(B), z2s_hi=_e(B, K),
+             z2c_hi=_e(B), Zs_hi=_e(B * K, D, dt=bf), Zs_lo=_e(B * K, D, dt=bf), Zc_hi=_e(B, D, dt=bf), Zc_lo=_e(B, D, dt=bf))
+    ws = ops._ws("pph_addon_tc2_ws_bytes", B, N, Din, D, K, zero=True, device=DEV)
+    for _ in range(2):
+        L.call("pph_addon_fwd2", d["tokens"], idx, d["Wa"].reshape(D, Din), d["ba"], B, N, Din, D, K, o["Zs"], o["Zc"],
+               o["z2s"], o["z2c"], 0.5, o["z2s_ctr"], o["z2c_ctr"], o["z2s_hi"], o["z2c_hi"], o["Zs_hi"], o["Zs_lo"],
+               o["Zc_hi"], o["Zc_lo"], ws)
+    torch.cuda.synchronize()
+    Zs, Zc = O.addon(case["tokens"], idx.cpu().long(), case["Wa"], case["ba"])
+    # 3-term bf16 split on the pre-activation (~1e-5) and sigmoid through ex2.approx / rcp.approx: 5e-5 on Z
+    assert rel_close(o["Zs"].cpu(), Zs, 5e-5) and rel_close(o["Zc"].cpu(), Zc, 5e-5), max_rel(o["Zs"].cpu(), Zs)
+    assert rel_close(o["z2s"].cpu(), (Zs * Zs).sum(-1), 2e-5) and rel_close(o["z2c"].cpu(), (Zc * Zc).sum(-1), 2e-5)
+    assert rel_close(o["z2s"].cpu(), (o["Zs"] ** 2).sum(-1).cpu(), 2e-6)          # norms of the kernel's own output
+    assert rel_close(o["z2s_ctr"].cpu(), ((o["Zs"] - 0.5) ** 2).sum(-1).cpu(), 2e-6)
+    assert rel_close(o["z2c_ctr"].cpu(), ((o["Zc"] - 0.5) ** 2).sum(-1).cpu(), 2e-6)
+    rec = (o["Zs_hi"].float() + o["Zs_lo"].float()).cpu().reshape(Zs.shape)
+    assert float((rec - (o["Zs"].cpu() - 0.5)).abs().max()) < 1e-5
+    assert rel_close(o["z2s_hi"].cpu(), (o["Zs_hi"].float() ** 2).sum(-1).reshape(B, K).cpu(), 1e-5)
+    assert rel_close(o["z2c_hi"].cpu(), (o["Zc_hi"].float() ** 2).sum(-1).cpu(), 1e-5)
+
+
+@pytest.mark.parametrize("key,seed", TC2_CASES)
+def test_addon_bwd3_single_shot_matches_float64(key, seed):
+    ops, L = _ops(), _lib()
+    shape = synth.SHAPES[key]
+    case = synth.make_case(shape, seed=seed)
+    d = _d(case)
+    B, N, Din, D, K = shape.B, shape.N, shape.Din, shape.D, shape.K
+    bits = L.load().pph_addon_tc2_supported(B, N, Din, D, K)
+    assert bits & 2
+    idx = ops.select_topk(d["scores"], K)
+    g = torch.Generator().manual_seed(seed)
+    dpre_s = (torch.randn(B, K, D, generator=g) * 1e-3).to(DEV)
+    dpre_c = (torch.randn(B, D, generator=g) * 1e-3).to(DEV)
+    ws = ops._ws("pph_addon_tc2_ws_bytes", B, N, Din, D, K, zero=True, device=DEV)
+    dWa, dba, dtok = _e(D, Din), _e(D), torch.zeros(B, 1 + N, Din, device=DEV)
+    parts = 3 if bits & 4 else 2
+    for _ in range(2):
+        L.call("pph_addon_bwd3", parts, d["tokens"], idx, d["Wa"].reshape(D, Din), dpre_s, dpre_c, B, N, Din, D, K, ws,
+               dWa, dba, dtok)
+    torch.cuda.synchronize()
+    dpre = torch.cat([dpre_s.cpu(), dpre_c.cpu()[:, None]], 1).double()
+    rows = torch.cat([1 + idx.cpu().long(), torch.zeros(B, 1, dtype=torch.long)], 1)
+    X = torch.gather(case["tokens"].double(), 1, rows[:, :, None].expand(B, K + 1, Din))
+    ref_dtok = torch.zeros(B, 1 + N, Din, dtype=torch.float64)
+    ref_dtok.scatter_(1, rows[:, :, None].expand(B, K + 1, Din), dpre @ case["Wa"].reshape(D, Din).double())
+    assert norm_rel(dtok.cpu(), ref_dtok) < 2e-5, norm_rel(dtok.cpu(), ref_dtok)
+    if bits & 4:
+        assert norm_rel(dWa.cpu(), torch.einsum("bkd,bki->di", dpre, X)) < 2e-5
+        assert norm_rel(dba.cpu(), dpre.sum((0, 1))) < 2e-5
+
+
+@pytest.mark.parametrize("variants", [dict(prep="simt", addon_bwd="simt"), dict(prep="tc", addon_bwd="tc"),
+                                      dict(prep="tc", addon_bwd="simt"), dict(prep="simt", addon_bwd="tc")])
+def test_step_variants_agree_with_the_oracle(variants):
+    shape, case, g, fn = load_golden("cub_b8_s1")
+    step, params = _make_step(shape, case, "fp32", variants=variants)
+    assert step.fused.variants == variants
+    step.run(0)
+    step.run(0)
+    torch.cuda.synchronize()
+    f = step.fused
+    assert np.array_equal(f.idx32.cpu().numpy(), g["idx"])
+    assert rel_close(f.logits.cpu(), g["logits_train"], 1e-4)
+    assert rel_close(f.losses.cpu()[0], g["loss"], 1e-4)
+    ref = O.head_train_step(case, shape, fn=fn, route=f.argmin.cpu().long())
+    got = dict(g_tokens=f.dtokens, g_P=params["P"].grad, g_Pg=params["Pg"].grad, g_Wa=params["Wa"].grad,
+               g_ba=params["ba"].grad)
+    for k, v in got.items():
+        e = norm_rel(v.cpu().reshape(ref[k].shape), ref[k])
+        assert e < 2e-4, (variants, k, e)
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # whole step
 # ---------------------------------------------------------------------------------------------------------------
-def _make_step(shape, case, mode, impl="v2", train=True, use_ppc=True):
+def _make_step(shape, case, mode, impl="v2", train=True, use_ppc=True, variants=None):
     from protopformer_b200.graph import GraphedHeadStep
     params = {k: case[k].to(DEV).clone() for k in ("Wa", "ba", "P", "Pg", "Wl", "Wg")}
     for k in ("Wa", "ba", "P", "Pg"):
         params[k].requires_grad_(train)
     step = GraphedHeadStep(params, _cfg(shape, mode), B=shape.B, N=shape.N, C=shape.C, m=shape.m, train=train, impl=impl,
-                           use_ppc=use_ppc)
+                           use_ppc=use_ppc, variants=variants)
     step.load(0, case["tokens"], case["scores"], case["labels"])
     torch.cuda.synchronize()
     step.capture()
@@ -342,7 +447,7 @@ def test_five_launch_step_matches_reference_fixture(name, mode):
         pytest.skip("fixture uses the linear activation: covered by the modular path")
     step, params = _make_step(shape, case, mode)
     v2 = _ops().fused_step_supported(shape.B, shape.N, shape.Din, shape.D, shape.K, shape.P, shape.Pg, shape.C, shape.m)
-    assert step.impl == ("v2" if v2 else "v1") and (not v2 or step.kernel_launches_per_step <= 6)
+    assert step.impl == ("v2" if v2 else "v1") and (not v2 or step.kernel_launches_per_step <= 12)
     step.run(0)
     step.run(0)
     torch.cuda.synchronize()
@@ -425,7 +530,7 @@ def test_five_launch_eval_step_and_no_ppc():
     step, _ = _make_step(shape, case, "fp32", train=False)
     step.run(0)
     torch.cuda.synchronize()
-    assert step.kernel_launches_per_step == 3
+    assert step.kernel_launches_per_step <= 6
     assert rel_close(step.fused.logits.cpu(), g["logits"], 1e-4)
     s_np, p_np = _make_step(shape, case, "fp32", use_ppc=False)
     s_np.run(0)
