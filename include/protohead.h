@@ -277,11 +277,16 @@ int pph_head_prep(const float* scores, const float* tokens, const float* Wa, con
  *   pph_loss_tail + pph_loss_combine (cov = mean = 0 when use_ppc = 0); and, when train != 0:
  *   dlogits [B,C]; g_l [B,P], g_g [B,Pg] as pph_logits_bwd (no upstream gradient on logits_global/local);
  *   pairT [(P+Pg)][Bp][2] fp32, Bp = B rounded up to 64: (g, bit pattern of the int32 token slot) per (prototype, image),
- *   token slot K (= the CLS row) for global prototypes, zeros for images >= B;
+ *   token slot K (= the CLS row) for global prototypes, zeros for images >= B (pairT may be NULL: only
+ *   pph_similarity_bwd2 reads it);
  *   the token bins (and, with use_ppc, the images sorted by class) of pph_similarity_bwd2 in bwd_workspace;
  *   with use_ppc: dZs_ppc [B,K,D] = d(cov_coe*cov + mean_coe*mean)*upstream / dZs (OVERWRITTEN) and
  *   dP_img [B,m,D] = the same gradient w.r.t. the m label-class prototype rows, per image (summed over the images of a
  *   class by pph_similarity_bwd2 in image order: deterministic).
+ * use_ppc: 0 no PPC loss | 1 PPC role inside this launch | 2 this launch runs everything but the PPC role and a second,
+ * concurrent call with use_ppc = 3 (same arguments, another stream) runs only that role: whichever finishes second
+ * writes losses[0] -- lets the PPC loss overlap the last layers instead of lengthening the launch.  Adding 4 to use_ppc
+ * makes dZs_ppc leave as the pre-activation gradient (times Z (1 - Z)): the form pph_addon_bwd3's dpre_add_s takes.
  * workspace: pph_head_mid_ws_bytes() bytes, ZERO-FILLED once before first use (grid-barrier and ticket counters, all
  * self-resetting).  C <= 256; B <= 64 * (SM count / 2).  Out-of-range labels are clamped. */
 int pph_head_mid_ws_bytes(int B, int K, int D, int P, int Pg, int C, int m, long long* bytes /* host */);
@@ -315,6 +320,16 @@ int pph_similarity_bwd2(int parts, const float* g_l, const float* g_g, const flo
                         const float* add_dZs, const float* dP_img, int dpre_out,
                         float* dZs, float* dZc, float* dPl, float* dPg, pph_stream_t stream);
 
+/* pph_similarity_bwd(PPH_BWD_GRADS) inside the fused step: the argmin-routed gather kernel of round 1 fed by the bins
+ * and class lists pph_head_mid left in `step_workspace` (= the bwd_workspace given to it); `workspace` is a
+ * pph_similarity_bwd_ws_bytes() scratch (zero-filled once).  add_dZs / dP_img / dpre_out as pph_similarity_bwd2. */
+int pph_similarity_bwd_fused(int parts /* 1 token-side rows | 2 prototype rows; or 4 alone: dPl += PPC rows of dP_img */,
+                             const float* g_l, const float* g_g, const int32_t* argmin_l,
+                             const float* Zs, const float* Zc, const float* Pl, const float* Pgl,
+                             int B, int K, int D, int P, int Pg, int m, void* workspace, void* step_workspace,
+                             const float* add_dZs, const float* dP_img, int dpre_out,
+                             float* dZs, float* dZc, float* dPl, float* dPg, pph_stream_t stream);
+
 /* (a8 part 3), second implementation: backward of pph_addon_fwd from the PRE-ACTIVATION gradient
  * dpre = dZ * Z * (1 - Z) (dpre_s [B,K,D] for the selected tokens, dpre_c [B,D] for the CLS token), exact FP32,
  * deterministic.  parts: PPH_ADDON_WGRAD -> dWa [D,Din], dba [D]; PPH_ADDON_DGRAD -> dtokens [B,1+N,Din] (every row
@@ -344,7 +359,7 @@ int pph_addon_fwd2(const float* tokens, const int32_t* idx32, const float* Wa, c
                    uint16_t* Zs_hi, uint16_t* Zs_lo, uint16_t* Zc_hi, uint16_t* Zc_lo,
                    void* workspace, pph_stream_t stream);
 int pph_addon_bwd3(int parts, const float* tokens, const int32_t* idx32, const float* Wa,
-                   const float* dpre_s, const float* dpre_c,
+                   const float* dpre_s, const float* dpre_c, const float* dpre_add_s /* [B,K,D] added to dpre_s, or NULL */,
                    int B, int N, int Din, int D, int K, void* workspace,
                    float* dWa, float* dba, float* dtokens, pph_stream_t stream);
 

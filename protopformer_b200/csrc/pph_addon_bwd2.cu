@@ -363,7 +363,7 @@ extern "C" int pph_addon_bwd2(int parts, const float* tokens, const int32_t* idx
     auto k_small = addon_bwd2_kernel<256>;
     auto k_large = addon_bwd2_kernel<640>;
     auto kern = p.threads <= 256 ? k_small : k_large;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    cudaError_t e = opt_in_smem(kern, (int)p.smem);
     if (e != cudaSuccess) { set_error("pph_addon_bwd2: %s", cudaGetErrorString(e)); return (int)e; }
     launch_k(kern, dim3(a.nX + a.nW), dim3(p.threads), p.smem, as_stream(stream), a);
     return launch_status("pph_addon_bwd2");

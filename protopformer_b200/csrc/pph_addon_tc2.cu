@@ -64,30 +64,105 @@ struct FwdEpi2 : FwdEpi {
 };
 
 // ---- backward operands: dpre is an input here ---------------------------------------------------------------------------
-struct PreRowOp {   // (row = r, k = d): dpre rows, contiguous along d
+struct PreRowOp {   // (row = r, k = d): dpre rows (+ the PPC loss's share add_s on the selected-token rows), contiguous along d
     static constexpr bool kContigK = true;
-    const float *dpre_s, *dpre_c;
+    const float *dpre_s, *dpre_c, *add_s;
     int K, D, R;
     __device__ __forceinline__ void load8(int r, int d0, float (&v)[8]) const {
         if (r >= R || d0 >= D) { zero8(v); return; }
         const int b = r / (K + 1), j = r - b * (K + 1);
         ld8((j < K ? dpre_s + ((size_t)b * K + j) * D : dpre_c + (size_t)b * D) + d0, v);
+        if (add_s && j < K) {
+            float w[8];
+            ld8(add_s + ((size_t)b * K + j) * D + d0, w);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += w[i];
+        }
     }
 };
 struct PreColOp {   // (row = d, k = r): the same matrix, transposed access (consecutive lanes = consecutive d)
     static constexpr bool kContigK = false;
-    const float *dpre_s, *dpre_c;
+    const float *dpre_s, *dpre_c, *add_s;
     int K, D, R;
     __device__ __forceinline__ void load8(int d, int r0, float (&v)[8]) const {
         if (d >= D) { zero8(v); return; }
         int b = r0 / (K + 1), j = r0 - b * (K + 1);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            v[i] = r0 + i < R ? __ldg((j < K ? dpre_s + ((size_t)b * K + j) * D : dpre_c + (size_t)b * D) + d) : 0.f;
+            float x = 0.f;
+            if (r0 + i < R) {
+                if (j < K) {
+                    const size_t o = ((size_t)b * K + j) * D + d;
+                    x = __ldg(dpre_s + o);
+                    if (add_s) x += __ldg(add_s + o);
+                } else {
+                    x = __ldg(dpre_c + (size_t)b * D + d);
+                }
+            }
+            v[i] = x;
             if (++j > K) { j = 0; ++b; }
         }
     }
 };
+// quad variants of the transposed operands (see pph_tcshot.cuh): 128-bit loads along the rows
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+struct PreColQOp : PreColOp {       // (rows d..d+3, k = r0..r0+7); D % 4 == 0
+    static constexpr bool kQuad = true;
+    __device__ __forceinline__ void load8x4(int d, int r0, float (&v)[4][8]) const {
+        int b = r0 / (K + 1), j = r0 - b * (K + 1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r0 + i < R && d < D) {
+                if (j < K) {
+                    const size_t o = ((size_t)b * K + j) * D + d;
+                    x = ldg4(dpre_s + o);
+                    if (add_s) {
+                        const float4 y = ldg4(add_s + o);
+                        x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+                    }
+                } else {
+                    x = ldg4(dpre_c + (size_t)b * D + d);
+                }
+            }
+            v[0][i] = x.x; v[1][i] = x.y; v[2][i] = x.z; v[3][i] = x.w;
+            if (++j > K) { j = 0; ++b; }
+        }
+    }
+};
+struct XselColQOp : XselColOp {     // (rows din..din+3, k = r0..r0+7); Din % 4 == 0; row Din = the all-ones column
+    static constexpr bool kQuad = true;
+    __device__ __forceinline__ void load8x4(int din, int r0, float (&v)[4][8]) const {
+        const int K = src.K;
+        int b = r0 / (K + 1), j = r0 - b * (K + 1);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r0 + i < src.R) {
+                if (din < src.Din) {
+                    const int tok = j < K ? 1 + __ldg(src.idx + (size_t)b * K + j) : 0;
+                    x = ldg4(tokens + ((size_t)b * (1 + src.N) + tok) * src.Din + din);
+                } else if (din == src.Din) {
+                    x.x = 1.0f;
+                }
+            }
+            v[0][i] = x.x; v[1][i] = x.y; v[2][i] = x.z; v[3][i] = x.w;
+            if (++j > K) { j = 0; ++b; }
+        }
+    }
+};
+struct WaTQOp : WaTOp {             // (rows din..din+3, k = d0..d0+7): Wa[d, din]; Din % 4 == 0
+    static constexpr bool kQuad = true;
+    __device__ __forceinline__ void load8x4(int din, int d0, float (&v)[4][8]) const {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (din < Din && d0 + i < D) x = ldg4(Wa + (size_t)(d0 + i) * Din + din);
+            v[0][i] = x.x; v[1][i] = x.y; v[2][i] = x.z; v[3][i] = x.w;
+        }
+    }
+};
+
 struct WgradEpi2 {      // split-k partial tiles [split][D][ldn] + in-kernel reduction behind the grid barrier
     static constexpr bool kDirect = false;
     static constexpr bool kGridReduce = true;
@@ -109,11 +184,12 @@ struct WgradEpi2 {      // split-k partial tiles [split][D][ldn] + in-kernel red
             const float* src = part + (size_t)d * ldn + n;
             float s = 0.f;
             int sp = 0;
-            for (; sp + 4 <= splits; sp += 4) {        // four loads in flight, added in split order
-                const float v0 = __ldcg(src + (size_t)(sp + 0) * D * ldn), v1 = __ldcg(src + (size_t)(sp + 1) * D * ldn);
-                const float v2 = __ldcg(src + (size_t)(sp + 2) * D * ldn), v3 = __ldcg(src + (size_t)(sp + 3) * D * ldn);
-                s = ((s + v0) + v1) + v2;
-                s += v3;
+            for (; sp + 8 <= splits; sp += 8) {        // eight loads in flight, added in split order
+                float v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) v[u] = __ldcg(src + (size_t)(sp + u) * D * ldn);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) s += v[u];
             }
             for (; sp < splits; ++sp) s += __ldcg(src + (size_t)sp * D * ldn);
             if (n < Din) dWa[(size_t)d * Din + n] = s; else dba[d] = s;
@@ -210,7 +286,7 @@ extern "C" int pph_addon_fwd2(const float* tokens, const int32_t* idx32, const f
 }
 
 extern "C" int pph_addon_bwd3(int parts, const float* tokens, const int32_t* idx32, const float* Wa,
-                              const float* dpre_s, const float* dpre_c,
+                              const float* dpre_s, const float* dpre_c, const float* dpre_add_s,
                               int B, int N, int Din, int D, int K, void* workspace,
                               float* dWa, float* dba, float* dtokens, pph_stream_t stream) {
     using namespace pph;
@@ -225,8 +301,10 @@ extern "C" int pph_addon_bwd3(int parts, const float* tokens, const int32_t* idx
     if (parts & PPH_ADDON_WGRAD) {
         PPH_REQUIRE(dWa && dba, PPH_EINVAL, "pph_addon_bwd3(WGRAD): null output");
         PPH_REQUIRE(p.w_ok, PPH_EUNSUP, "pph_addon_bwd3(WGRAD): %d CTAs for B=%d K=%d Din=%d D=%d", p.w_ctas, B, K, Din, D);
-        PreColOp a{dpre_s, dpre_c, K, D, R};
-        XselColOp b{tokens, src};
+        PreColQOp a;
+        static_cast<PreColOp&>(a) = PreColOp{dpre_s, dpre_c, dpre_add_s, K, D, R};
+        XselColQOp b;
+        static_cast<XselColOp&>(b) = XselColOp{tokens, src};
         WgradEpi2 e{w.wpart, dWa, dba, D, Din, p.ldn, p.w_splits};
         const int rc = launch_tcshot(D, Din + 1, R, p.bn_w, kTsMaxKB * kTsBK, w.sync_ctr, a, b, e, st,
                                      "pph_addon_bwd3(wgrad tcgen05 single shot)");
@@ -235,8 +313,9 @@ extern "C" int pph_addon_bwd3(int parts, const float* tokens, const int32_t* idx
     if (parts & PPH_ADDON_DGRAD) {
         PPH_REQUIRE(dtokens, PPH_EINVAL, "pph_addon_bwd3(DGRAD): null dtokens");
         PPH_REQUIRE(p.dx_ok, PPH_EUNSUP, "pph_addon_bwd3(DGRAD): D=%d outside the single-shot kernel", D);
-        PreRowOp a{dpre_s, dpre_c, K, D, R};
-        WaTOp b{Wa, D, Din};
+        PreRowOp a{dpre_s, dpre_c, dpre_add_s, K, D, R};
+        WaTQOp b;
+        static_cast<WaTOp&>(b) = WaTOp{Wa, D, Din};
         DxTcEpi e{dtokens, src};
         const int rc = launch_tcshot(R, Din, D, p.bn_dx, ceil_div(D, kTsBK) * kTsBK, w.sync_ctr, a, b, e, st,
                                      "pph_addon_bwd3(dgrad tcgen05 single shot)");

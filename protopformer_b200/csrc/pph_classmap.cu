@@ -113,7 +113,7 @@ extern "C" int pph_class_maps(const float* Zs, const float* z2s, const float* Pl
     const bool use_v2 = option(kOptClassmap) == 2;
     const size_t smem2 = (size_t)(K + m) * (D + 4) * sizeof(float);
     if (use_v2 && D % 4 == 0 && smem2 <= 200 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(class_maps2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = opt_in_smem(class_maps2_kernel, 200 * 1024);
         if (e != cudaSuccess) { set_error("pph_class_maps: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         launch_k(class_maps2_kernel, dim3(B), dim3(kCmThreads), smem2, as_stream(stream), Zs, z2s, Pl, p2l, idx32, labels,
                  K, D, P, m, N, act_fn, eps, maps);

@@ -67,6 +67,18 @@ inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
 
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Opt a kernel into `bytes` of dynamic shared memory AND ask for the maximum shared-memory carve-out: the L1 / shared
+// split of an SM is set by the kernel that arrives first, and a kernel of a concurrent graph branch can only join that
+// SM if its shared memory still fits the carve-out -- with the default (smallest sufficient) carve-out the branches of
+// the step serialised instead of overlapping.
+template <class K>
+inline cudaError_t opt_in_smem(K kern, size_t bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+    return e;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------------------------

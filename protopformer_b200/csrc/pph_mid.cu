@@ -34,6 +34,8 @@ struct MidArgs {
     int B, Bp, K, D, P, Pg, C, Cp, m, N, side;
     int tiles_b, S_l, S_g, nsl_l, nsl_g;
     int n_ll, n_bin, n_ppc, n_cls_cta;
+    int have_ppc;                 // the step has a PPC role (in this launch or in a concurrent one)
+    int ppc_dpre;                 // dZs_ppc is written as the pre-activation gradient dZ * Z * (1 - Z)
     float gc, eps, upstream, cov_thresh, mean_thresh, cov_coe, mean_coe;
     int act_fn, train;
     const float *act_l, *act_g, *dmin_l, *dmin_g;
@@ -53,6 +55,17 @@ struct MidArgs {
     float *dZs_ppc, *dP_img;
 };
 
+__device__ __forceinline__ float block_sum_any(float v, float* red, int nwarp) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float s = 0.f;
+    for (int w = 0; w < nwarp; ++w) s += red[w];
+    return s;
+}
+
 __device__ __forceinline__ float block_sum_mid(float v, float* red) {
     v = warp_sum(v);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -67,15 +80,14 @@ __device__ __forceinline__ float block_sum_mid(float v, float* red) {
 
 // total = ce + cov_coe * cov + mean_coe * mean (engine_proto.py:61-64): written by whichever role finishes second.
 __device__ __forceinline__ void write_total(const MidArgs& a) {
-    const float ce = a.n_ll ? __ldcg(a.losses + 1) : 0.f;
-    if (a.n_ll == 0) a.losses[1] = 0.f;
-    const float cov = a.n_ppc ? __ldcg(a.ppc_losses) : 0.f, mean = a.n_ppc ? __ldcg(a.ppc_losses + 1) : 0.f;
+    const float ce = __ldcg(a.losses + 1);
+    const float cov = a.have_ppc ? __ldcg(a.ppc_losses) : 0.f, mean = a.have_ppc ? __ldcg(a.ppc_losses + 1) : 0.f;
     a.losses[0] = ce + a.cov_coe * cov + a.mean_coe * mean;
     a.losses[2] = cov;
     a.losses[3] = mean;
 }
 __device__ __forceinline__ void role_finished(const MidArgs& a) {      // one thread
-    if (a.n_ppc == 0 || a.n_ll == 0) {
+    if (!a.have_ppc) {
         write_total(a);
         return;
     }
@@ -318,9 +330,11 @@ __device__ __forceinline__ void ll_role(const MidArgs& a, float* sm) {
                     }
                     pr[i] = make_float2(g, __int_as_float(am));
                 }
-                float4* dst = reinterpret_cast<float4*>(a.pairT + (size_t)(glob ? a.P + p : p) * a.Bp + b0 + warp * 8);
+                if (a.pairT) {          // only the staged backward (pph_similarity_bwd2) reads the transposed pairs
+                    float4* dst = reinterpret_cast<float4*>(a.pairT + (size_t)(glob ? a.P + p : p) * a.Bp + b0 + warp * 8);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dst[i] = make_float4(pr[2 * i].x, pr[2 * i].y, pr[2 * i + 1].x, pr[2 * i + 1].y);
+                    for (int i = 0; i < 4; ++i) dst[i] = make_float4(pr[2 * i].x, pr[2 * i].y, pr[2 * i + 1].x, pr[2 * i + 1].y);
+                }
             }
         }
     }
@@ -330,7 +344,10 @@ __device__ __forceinline__ void ll_role(const MidArgs& a, float* sm) {
 // ---------------------------------------------------------------------------------------------------------------
 // role PPC: forward (restatement of SURVEY.md 8(d)(iii), same arithmetic as pph_ppc.cu) + backward in one CTA per image
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void ppc_role(const MidArgs& a, int b, float* sm) {
+// `nsplit` CTAs share an image: each recomputes the (cheap) forward, CTA `part` takes every nsplit-th token row and
+// work item of the backward, part 0 reports the losses.  Block size = blockDim.x (a multiple of 32, <= 1024).
+__device__ __forceinline__ void ppc_role(const MidArgs& a, int b, int part, int nsplit, float* sm) {
+    const int nthr = blockDim.x;
     const int K = a.K, D = a.D, m = a.m, B = a.B, side = a.side;
     const int zs = D + 4;
     float* Prow = sm;                     // [m][D]
@@ -338,13 +355,13 @@ __device__ __forceinline__ void ppc_role(const MidArgs& a, int b, float* sm) {
     float* dsl = Zt + (size_t)K * zs;     // [m][K] distances, later d loss / d distance
     float* wbuf = dsl + m * K;            // [m][K] activations
     float* st = wbuf + m * K;             // [m][8]
-    float* red = st + m * 8;              // [8]
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = kMidThreads / 32;
+    float* red = st + m * 8;              // [32]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = nthr >> 5;
     long y = a.labels[b];
     if (y < 0) y = 0;
     if (y * m + m > a.P) y = a.P / m - 1;
     const int prow0 = (int)y * m;
-    for (int i = tid; i < m * D / 4; i += kMidThreads) cp_async16(Prow + 4 * i, a.Pl + (size_t)prow0 * D + 4 * i);
+    for (int i = tid; i < m * D / 4; i += nthr) cp_async16(Prow + 4 * i, a.Pl + (size_t)prow0 * D + 4 * i);
     const float* Zb = a.Zs + (size_t)b * K * D;
     {
         const int d4 = D >> 2;
@@ -354,8 +371,8 @@ __device__ __forceinline__ void ppc_role(const MidArgs& a, int b, float* sm) {
     cp_async_commit();
     cp_async_wait<0>();
     __syncthreads();
-    const int JG = K * 3 <= kMidThreads ? 3 : (K * 2 <= kMidThreads ? 2 : 1);
-    for (int t = tid; t < K * JG; t += kMidThreads) {
+    const int JG = K * m <= nthr ? m : (K * 5 <= nthr ? 5 : (K * 3 <= nthr ? 3 : (K * 2 <= nthr ? 2 : 1)));
+    for (int t = tid; t < K * JG; t += nthr) {
         const int r = t % K, jg = t / K;
         const float4* zr = reinterpret_cast<const float4*>(Zt + (size_t)r * zs);
         const float zz = __ldg(a.z2s + (size_t)b * K + r);
@@ -404,17 +421,17 @@ __device__ __forceinline__ void ppc_role(const MidArgs& a, int b, float* sm) {
             cov_sum += fmaxf(pre, 0.0f);
         }
     }
-    const float cov_img = block_sum_mid(lane == 0 ? cov_sum : 0.f, red);     // its barriers also publish st[]
+    const float cov_img = block_sum_any(lane == 0 ? cov_sum : 0.f, red, nwarp);     // its barriers also publish st[]
     float mean_sum = 0.f;
-    for (int t = tid; t < m * m; t += kMidThreads) {
+    for (int t = tid; t < m * m; t += nthr) {
         const int i = t / m, j = t - i * m;
         if (i != j) {
             const float dr = st[i * 8 + 1] - st[j * 8 + 1], dc = st[i * 8 + 2] - st[j * 8 + 2];
             mean_sum += fmaxf(a.mean_thresh - sqrtf(dr * dr + dc * dc), 0.0f);
         }
     }
-    const float mean_img = block_sum_mid(mean_sum, red);
-    if (tid == 0) {        // deterministic batch sums: the last image CTA adds the partials in image order
+    const float mean_img = block_sum_any(mean_sum, red, nwarp);
+    if (tid == 0 && part == 0) {        // deterministic batch sums: the last image CTA adds the partials in image order
         a.ppc_part[2 * b] = cov_img;
         a.ppc_part[2 * b + 1] = mean_img;
         __threadfence();
@@ -452,7 +469,7 @@ __device__ __forceinline__ void ppc_role(const MidArgs& a, int b, float* sm) {
         st[i * 8 + 7] = gcn;
     }
     __syncthreads();
-    for (int t = tid; t < m * K; t += kMidThreads) {
+    for (int t = tid; t < m * K; t += nthr) {
         const int j = t / K, r = t - j * K;
         const float S = st[j * 8], mr = st[j * 8 + 1], mc = st[j * 8 + 2], Vr = st[j * 8 + 3], Vc = st[j * 8 + 4];
         const float dV = st[j * 8 + 5] > 0.0f ? 0.5f * g_cov * scale : 0.0f;
@@ -466,7 +483,7 @@ __device__ __forceinline__ void ppc_role(const MidArgs& a, int b, float* sm) {
     // token rows: dZ[b,k,:] = Z[b,k,:] sum_j dd[j,k] - sum_j dd[j,k] P_j; one warp per token, a lane owns 4 features
     // of a 128-feature group (one broadcast read of dd and one 16-byte read of P_j per 4 FMAs)
     const int ngrp = (D + 127) >> 7;
-    for (int r = warp; r < K; r += nwarp) {
+    for (int r = warp * nsplit + part; r < K; r += nwarp * nsplit) {
         float S = 0.f;
         for (int j = 0; j < m; ++j) S += dsl[j * K + r];
         float* out = a.dZs_ppc + ((size_t)b * K + r) * D;
@@ -481,12 +498,15 @@ __device__ __forceinline__ void ppc_role(const MidArgs& a, int b, float* sm) {
                 const float4 p = *reinterpret_cast<const float4*>(Prow + j * D + d);
                 acc.x = fmaf(c, p.x, acc.x); acc.y = fmaf(c, p.y, acc.y); acc.z = fmaf(c, p.z, acc.z); acc.w = fmaf(c, p.w, acc.w);
             }
+            if (a.ppc_dpre) {
+                acc.x *= z.x * (1.0f - z.x); acc.y *= z.y * (1.0f - z.y); acc.z *= z.z * (1.0f - z.z); acc.w *= z.w * (1.0f - z.w);
+            }
             *reinterpret_cast<float4*>(out + d) = acc;
         }
     }
     // prototype rows of THIS image (summed over the images of a class by the prototype-gradient kernel, in image
     // order: deterministic, unlike the atomics of pph_ppc_bwd): dP_img[b,j,:] = P_j sum_k dd[j,k] - sum_k dd[j,k] Z[b,k,:]
-    for (int it = warp; it < m * ngrp; it += nwarp) {       // work item = (prototype, 128-feature group)
+    for (int it = warp * nsplit + part; it < m * ngrp; it += nwarp * nsplit) {       // work item = (prototype, 128-feature group)
         const int j = it / ngrp, g = it - j * ngrp;
         const int d = g * 128 + lane * 4;
         if (d >= D) continue;
@@ -517,7 +537,7 @@ head_mid_kernel(const MidArgs a) {
         bin_tokens_body<false>(bid - a.n_ll, a.argmin_l, a.K, a.P, a.bin_start, a.item_start, a.bin_list,
                         reinterpret_cast<int*>(sm_mid));
     } else if (bid < a.n_ll + a.n_bin + a.n_ppc) {
-        ppc_role(a, bid - a.n_ll - a.n_bin, sm_mid);
+        ppc_role(a, bid - a.n_ll - a.n_bin, 0, 1, sm_mid);
     } else {
         // role CLS (one CTA): the images sorted by clamped label (stable counting sort: image order inside a class)
         const int n_cls = a.P / a.m;
@@ -531,6 +551,15 @@ head_mid_kernel(const MidArgs a) {
         __syncthreads();
         bin_tokens_body<true>(0, a.cls_id, n_cls, a.B, a.cls_start, a.cls_item, a.cls_order, reinterpret_cast<int*>(sm_mid));
     }
+}
+
+// PPC role as its own launch (use_ppc = 3): two 512-thread CTAs per image
+constexpr int kPpcSplit = 2, kPpcThreads = 512;
+__global__ void __launch_bounds__(kPpcThreads)
+head_ppc_kernel(const MidArgs a) {
+    pdl_sync();
+    extern __shared__ __align__(16) float sm_mid[];
+    ppc_role(a, blockIdx.x / kPpcSplit, blockIdx.x % kPpcSplit, kPpcSplit, sm_mid);
 }
 
 struct MidPlan {
@@ -565,7 +594,7 @@ static MidPlan mid_plan(int B, int K, int D, int P, int Pg, int C, int m, int ma
     p.n_ll = p.tiles_b * (p.S_l + p.S_g);
     const int WST = C | 1;
     p.smem_ll = sizeof(float) * ((size_t)kMidPS * WST + (size_t)kMidPS * kMidAST + (size_t)C * kMidAST + 2 * 4 * 64 * 4 + 3 * 256 + 8);
-    p.smem_ppc = sizeof(float) * ((size_t)m * D + (size_t)K * (D + 4) + 2 * (size_t)m * K + 8 * (size_t)m + 8);
+    p.smem_ppc = sizeof(float) * ((size_t)m * D + (size_t)K * (D + 4) + 2 * (size_t)m * K + 8 * (size_t)m + 32);
     p.smem_bin = bin_tokens_smem_bytes(K);
     return p;
 }
@@ -625,7 +654,7 @@ extern "C" int pph_head_mid(const float* act_l, const float* act_g, const float*
     PPH_REQUIRE(B >= 1 && K >= 1 && D >= 4 && P >= 1 && Pg >= 0 && C >= 1 && m >= 1 && N >= 2, PPH_EINVAL,
                 "pph_head_mid: bad dims");
     PPH_REQUIRE(C <= 256, PPH_EUNSUP, "pph_head_mid: C=%d > 256 (use the modular entry points)", C);
-    PPH_REQUIRE(!train || (argmin_l && dlogits && g_l && pairT && bwd_workspace && (Pg == 0 || g_g)), PPH_EINVAL,
+    PPH_REQUIRE(!train || (argmin_l && dlogits && g_l && bwd_workspace && (Pg == 0 || g_g)), PPH_EINVAL,
                 "pph_head_mid: null training pointer");
     PPH_REQUIRE(!use_ppc || (Zs && z2s && Pl && p2l && idx32 && (!train || (dZs_ppc && dP_img))), PPH_EINVAL,
                 "pph_head_mid: null PPC pointer");
@@ -636,9 +665,15 @@ extern "C" int pph_head_mid(const float* act_l, const float* act_g, const float*
     a.B = B; a.Bp = p.Bp; a.K = K; a.D = D; a.P = P; a.Pg = Pg; a.C = C; a.Cp = p.Cp; a.m = m; a.N = N;
     a.side = (int)lrint(sqrt((double)N));
     a.tiles_b = p.tiles_b; a.S_l = p.S_l; a.S_g = p.S_g; a.nsl_l = p.nsl_l; a.nsl_g = p.nsl_g;
-    a.n_ll = p.n_ll;
-    a.n_bin = train ? B : 0;
-    a.n_ppc = use_ppc ? B : 0;
+    // use_ppc: 0 no PPC loss | 1 PPC role in this launch | 2 this launch runs everything BUT the PPC role, which a
+    // concurrent launch (use_ppc = 3) of the same step runs: the second of the two to finish writes losses[0]
+    a.ppc_dpre = (use_ppc & 4) ? 1 : 0;       // bit 2: dZs_ppc leaves as dpre (for pph_addon_bwd3's dpre_add_s)
+    use_ppc &= 3;
+    const bool have_ppc = use_ppc != 0, run_ll = use_ppc != 3, run_ppc = use_ppc == 1 || use_ppc == 3;
+    a.have_ppc = have_ppc ? 1 : 0;
+    a.n_ll = run_ll ? p.n_ll : 0;
+    a.n_bin = (train && run_ll) ? B : 0;
+    a.n_ppc = run_ppc ? B : 0;
     a.gc = global_coe; a.eps = eps; a.upstream = upstream; a.cov_thresh = cov_thresh; a.mean_thresh = mean_thresh;
     a.cov_coe = cov_coe; a.mean_coe = mean_coe; a.act_fn = act_fn; a.train = train;
     a.act_l = act_l; a.act_g = act_g; a.dmin_l = dmin_l; a.dmin_g = dmin_g; a.argmin_l = argmin_l;
@@ -654,28 +689,35 @@ extern "C" int pph_head_mid(const float* act_l, const float* act_g, const float*
         const Step2Bins bw = carve_bins(bwd_workspace, B, K, P);
         a.bin_start = bw.bin_start; a.item_start = bw.item_start; a.bin_list = bw.bin_list;
         a.cls_id = bw.cls_id; a.cls_start = bw.cls_start; a.cls_item = bw.cls_item; a.cls_order = bw.cls_order;
-        if (use_ppc && bin_tokens_smem_bytes(P / m) <= 200 * 1024) a.n_cls_cta = 1;
+        if (have_ppc && run_ll && bin_tokens_smem_bytes(P / m) <= 200 * 1024) a.n_cls_cta = 1;
     }
     a.Zs = Zs; a.z2s = z2s; a.Pl = Pl; a.p2l = p2l; a.idx = idx32; a.dZs_ppc = dZs_ppc; a.dP_img = dP_img;
-    size_t smem = p.smem_ll;
+    size_t smem = run_ll ? p.smem_ll : 0;
     if (a.n_bin && p.smem_bin > smem) smem = p.smem_bin;
     if (a.n_cls_cta && bin_tokens_smem_bytes(P / m) > smem) smem = bin_tokens_smem_bytes(P / m);
-    if (use_ppc) {
-        PPH_REQUIRE(D % 4 == 0 && a.side * a.side == N && P >= m, PPH_EINVAL, "pph_head_mid: bad PPC dims");
+    if (have_ppc) {
+        PPH_REQUIRE(D % 4 == 0 && a.side * a.side == N && P >= m && m <= kMidThreads, PPH_EINVAL, "pph_head_mid: bad PPC dims");
         PPH_REQUIRE(p.smem_ppc <= 200 * 1024, PPH_EUNSUP, "pph_head_mid: an image's K x D slice does not fit shared memory");
-        if (p.smem_ppc > smem) smem = p.smem_ppc;
+        if (run_ppc && p.smem_ppc > smem) smem = p.smem_ppc;
     }
     PPH_REQUIRE(smem <= 220 * 1024, PPH_EUNSUP, "pph_head_mid: shared memory %zu B", smem);
     // all LL CTAs must be co-resident (grid barriers): they come first in the grid and number <= SM count
     PPH_REQUIRE(p.n_ll <= max_ctas, PPH_EUNSUP, "pph_head_mid: B=%d needs %d co-resident CTAs (> %d SMs)", B, p.n_ll,
                 max_ctas);
+    if (use_ppc == 3) {        // PPC role alone: its own kernel, two 512-thread CTAs per image
+        cudaError_t e = opt_in_smem(head_ppc_kernel, (int)p.smem_ppc);
+        if (e != cudaSuccess) { set_error("pph_head_mid: %s", cudaGetErrorString(e)); return (int)e; }
+        launch_k(head_ppc_kernel, dim3(B * kPpcSplit), dim3(kPpcThreads), p.smem_ppc, as_stream(stream), a);
+        return launch_status("pph_head_mid(ppc)");
+    }
     const int cj = ceil_div(C, 32);
-    PPH_REQUIRE(!(use_ppc && train) || a.n_cls_cta == 1, PPH_EUNSUP, "pph_head_mid: too many classes");
+    PPH_REQUIRE(!(have_ppc && train && run_ll) || a.n_cls_cta == 1, PPH_EUNSUP, "pph_head_mid: too many classes");
+
     const dim3 grid(a.n_ll + a.n_bin + a.n_ppc + a.n_cls_cta), block(kMidThreads);
     cudaStream_t st = as_stream(stream);
 #define PPH_MID(CJ)                                                                                                   \
     do {                                                                                                              \
-        cudaError_t e = cudaFuncSetAttribute(head_mid_kernel<CJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        cudaError_t e = opt_in_smem(head_mid_kernel<CJ>, (int)smem); \
         if (e != cudaSuccess) { set_error("pph_head_mid: %s", cudaGetErrorString(e)); return (int)e; }                \
         launch_k(head_mid_kernel<CJ>, grid, block, smem, st, a);                                                      \
     } while (0)

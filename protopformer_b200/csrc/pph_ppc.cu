@@ -301,7 +301,7 @@ static int launch_ppc_bwd(dim3 grid, size_t smem, cudaStream_t st, const float* 
                           const float* g_losses, float gs_cov, float gs_mean, int B, int K, int D, int P, int m, int N,
                           int side, int act_fn, float eps, float mean_thresh, int accumulate, float* dZs, float* dP) {
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(ppc_bwd_kernel<DV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = opt_in_smem(ppc_bwd_kernel<DV>, (int)smem);
         if (e != cudaSuccess) { set_error("pph_ppc_bwd: %s", cudaGetErrorString(e)); return (int)e; }
     }
     launch_k(ppc_bwd_kernel<DV>, dim3(grid), dim3(kPpcBwdThreads), (size_t)(smem), st, Zs, Pl, idx32, labels, dslice, stats, g_losses, gs_cov, gs_mean, B, K, D, P, m, N, side, act_fn, eps, mean_thresh, accumulate, dZs, dP);
@@ -341,7 +341,7 @@ extern "C" int pph_ppc_fwd(const float* Zs, const float* z2s, const float* Pl, c
     if (rc) return rc;
     if (B == 0) return 0;
     if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(ppc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = opt_in_smem(ppc_fwd_kernel, (int)smem);
         if (e != cudaSuccess) { set_error("pph_ppc_fwd: %s", cudaGetErrorString(e)); return (int)e; }
     }
     launch_k(ppc_fwd_kernel, dim3(B), dim3(kPpcThreads), (size_t)(smem), as_stream(stream), Zs, z2s, Pl, p2l, idx32, labels, B, K, D, P, m, N, side, kc, act_fn, eps, cov_thresh, mean_thresh, dslice, stats, partial, counter, losses);

@@ -395,7 +395,7 @@ extern "C" int pph_head_prep(const float* scores, const float* tokens, const flo
     auto k_small = head_prep_kernel<256, 8>;
     auto k_large = head_prep_kernel<640, 6>;
     auto kern = p.threads <= 256 ? k_small : k_large;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem);
+    cudaError_t e = opt_in_smem(kern, (int)p.smem);
     if (e != cudaSuccess) { set_error("pph_head_prep: %s", cudaGetErrorString(e)); return (int)e; }
     launch_k(kern, dim3(p.grid), dim3(p.threads), p.smem, as_stream(stream), a);
     return launch_status("pph_head_prep");

@@ -671,14 +671,14 @@ extern "C" int pph_rollout_scores(const float* const* attn_layers, int L, int B,
     cudaStream_t st = as_stream(stream);
     const dim3 grid(tiles < sms ? tiles : sms);
     auto go = [&](auto kern) -> int {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaError_t e = opt_in_smem(kern, 220 * 1024);
         if (e != cudaSuccess) { set_error("pph_rollout_scores: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         launch_k(kern, grid, dim3(kRoThreads), smem, st, layers, L, B, H, T, k_discard, head_fusion, identity_w, w.cap,
                  w.col_ptr, w.ent_val, w.ent_row);
         return launch_status("pph_rollout_scores(prepare)");
     };
     auto go2 = [&](auto kern) -> int {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        cudaError_t e = opt_in_smem(kern, 220 * 1024);
         if (e != cudaSuccess) { set_error("pph_rollout_scores: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         launch_k(kern, grid, dim3(kRoThreads), smem, st, layers, L, B, H, T, k_discard, head_fusion, identity_w, w.cap,
                  w.col_ptr, w.ent_val, w.ent_row, norm_mode);
@@ -696,8 +696,7 @@ extern "C" int pph_rollout_scores(const float* const* attn_layers, int L, int B,
     // staged chain needs the layer's entry list in shared memory (cap * 6 B): small discard ratios fall back to v1
     const size_t csmem = (size_t)w.cap * 4 + (size_t)(T + 1) * 4 + (size_t)w.cap * 2 + 16;
     if (!use_v1 && csmem <= 160 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(rollout_chain2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             160 * 1024);
+        cudaError_t e = opt_in_smem(rollout_chain2_kernel, 160 * 1024);
         if (e != cudaSuccess) { set_error("pph_rollout_scores: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         launch_k(rollout_chain2_kernel, dim3(B), dim3(kRoChainThreads), csmem, st, L, B, T, w.cap, w.col_ptr, w.ent_val,
                  w.ent_row, v0, drop_first, scores, K, idx32, idx64);

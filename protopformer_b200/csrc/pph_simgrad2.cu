@@ -82,6 +82,14 @@ __device__ __forceinline__ float4 token_out(float4 z, float gs, float4 acc, cons
 // ---------------------------------------------------------------------------------------------------------------
 // TOKENS
 // ---------------------------------------------------------------------------------------------------------------
+// The CTA's 16 warps form kG2TokGroups independent groups; each group walks its own images with private staging
+// buffers and its own named barrier, so the exposed latencies of one group's phases (list gather -> barrier -> walk ->
+// barrier -> final loads / stores) are covered by the other groups' work.
+constexpr int kG2TokGroups = 2;
+constexpr int kG2TokGT = kG2TokThreads / kG2TokGroups;        // threads per group
+
+__device__ __forceinline__ void group_bar(int g) { asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(kG2TokGT) : "memory"); }
+
 __global__ void __launch_bounds__(kG2TokThreads, 1)
 grad2_tokens_kernel(const Grad2Args a) {
     pdl_sync();
@@ -89,43 +97,49 @@ grad2_tokens_kernel(const Grad2Args a) {
     const int K = a.K, P = a.P, D = a.D;
     const int NC = (P + kG2CH - 1) / kG2CH;                 // chunks per image
     const int NSEG = NC + K;                                // partial slots: chunk + bin
-    float* Psl = sm_g2;                                      // [P][16]
-    float2* sp = reinterpret_cast<float2*>(Psl + (size_t)P * kG2DS);          // [P]   (row offset bits, g), bin order
-    float* seg = reinterpret_cast<float*>(sp + ((P + 1) & ~1));               // [NSEG][20]  float4 x 4 lanes + gs
-    int* bst = reinterpret_cast<int*>(seg + (size_t)NSEG * 20);               // [K+1]
-    int* kc = bst + (K + 1);                                 // [NC]  bin of the first entry of each chunk
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, grp = lane >> 2, dq = lane & 3;
+    const int Pe = (P + 1) & ~1;
+    // shared memory: Psl [P][16] | per group: sp [Pe] float2, seg [NSEG][20], bst [K+1], kc [NC]
+    float* Psl = sm_g2;
+    const size_t grp_floats = 2 * (size_t)Pe + (size_t)NSEG * 20 + (size_t)((K + 1 + NC + 3) & ~3);
+    const int tid = threadIdx.x, g = tid / kG2TokGT, gt = tid - g * kG2TokGT;
+    const int lane = tid & 31, gw = gt >> 5, grp = lane >> 2, dq = lane & 3;
+    float* gbase = Psl + (size_t)P * kG2DS + (size_t)g * grp_floats;
+    float2* sp = reinterpret_cast<float2*>(gbase);           // (row offset bits, g), bin order
+    float* seg = gbase + 2 * (size_t)Pe;                     // float4 x 4 lanes + gs per slot
+    int* bst = reinterpret_cast<int*>(seg + (size_t)NSEG * 20);
+    int* kc = bst + (K + 1);                                 // bin of the first entry of each chunk
     const int sa = blockIdx.x % a.NS, ig = blockIdx.x / a.NS;
     const int c0 = sa * kG2DS;
     const int bA = ig * a.IA, bE = min(a.B, bA + a.IA);
     for (int i = tid; i < P * 4; i += kG2TokThreads)
         cp_async16(Psl + (i >> 2) * kG2DS + (i & 3) * 4, a.Pl + (size_t)(i >> 2) * D + c0 + (i & 3) * 4);
     cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
     const uint32_t psl_u = (uint32_t)__cvta_generic_to_shared(Psl) + dq * 16;
     const uint32_t sp_u = (uint32_t)__cvta_generic_to_shared(sp);
     const uint32_t seg_u = (uint32_t)__cvta_generic_to_shared(seg);
     constexpr int EPT = 4;                                   // list entries staged per thread and pass
-    for (int b = bA; b < bE; ++b) {
+    for (int b = bA + g; b < bE; b += kG2TokGroups) {
         // ---- stage this image's list: (prototype -> row offset, g) in bin order, and the bin offsets -------------
         {
             const int32_t* list = a.bin_list + (size_t)b * P;
             const float* gb = a.g_l + (size_t)b * P;
-            for (int e0 = tid; e0 < P; e0 += EPT * kG2TokThreads) {
+            for (int e0 = gt; e0 < P; e0 += EPT * kG2TokGT) {
                 int p[EPT];
-                float g[EPT];
+                float gv[EPT];
 #pragma unroll
-                for (int u = 0; u < EPT; ++u) p[u] = e0 + u * kG2TokThreads < P ? __ldg(list + e0 + u * kG2TokThreads) : 0;
+                for (int u = 0; u < EPT; ++u) p[u] = e0 + u * kG2TokGT < P ? __ldg(list + e0 + u * kG2TokGT) : 0;
 #pragma unroll
-                for (int u = 0; u < EPT; ++u) g[u] = __ldg(gb + p[u]);
+                for (int u = 0; u < EPT; ++u) gv[u] = __ldg(gb + p[u]);
 #pragma unroll
                 for (int u = 0; u < EPT; ++u)
-                    if (e0 + u * kG2TokThreads < P) sp[e0 + u * kG2TokThreads] = make_float2(__int_as_float(p[u] * (kG2DS * 4)), g[u]);
+                    if (e0 + u * kG2TokGT < P) sp[e0 + u * kG2TokGT] = make_float2(__int_as_float(p[u] * (kG2DS * 4)), gv[u]);
             }
-            for (int k = tid; k <= K; k += kG2TokThreads) bst[k] = __ldg(a.bin_start + (size_t)b * (K + 1) + k);
+            for (int k = gt; k <= K; k += kG2TokGT) bst[k] = __ldg(a.bin_start + (size_t)b * (K + 1) + k);
         }
-        cp_async_wait<0>();
-        __syncthreads();
-        for (int c = tid; c < NC; c += kG2TokThreads) {      // bin of entry c * CH: the last k with bst[k] <= e
+        group_bar(g);
+        for (int c = gt; c < NC; c += kG2TokGT) {           // bin of entry c * CH: the last k with bst[k] <= e
             const int e = c * kG2CH;
             int lo = 0, hi = K - 1;
             while (lo < hi) {
@@ -134,9 +148,9 @@ grad2_tokens_kernel(const Grad2Args a) {
             }
             kc[c] = lo;
         }
-        __syncthreads();
-        // ---- walk: one chunk per 4-lane group ---------------------------------------------------------------------
-        for (int c = warp * 8 + grp; c < NC; c += (kG2TokThreads / 32) * 8) {
+        group_bar(g);
+        // ---- walk: one chunk per 4-lane sub-group -------------------------------------------------------------------
+        for (int c = gw * 8 + grp; c < NC; c += (kG2TokGT / 32) * 8) {
             int e = c * kG2CH;
             const int e1 = min(P, e + kG2CH);
             int k = kc[c];
@@ -162,9 +176,9 @@ grad2_tokens_kernel(const Grad2Args a) {
                     gs += q0.y;
                 }
                 acc.x += acc2.x; acc.y += acc2.y; acc.z += acc2.z; acc.w += acc2.w;
-                float* s = seg + (size_t)(c + k) * 20;
-                *reinterpret_cast<float4*>(s + dq * 4) = acc;
-                if (dq == 0) s[16] = gs + gs2;
+                float* sg = seg + (size_t)(c + k) * 20;
+                *reinterpret_cast<float4*>(sg + dq * 4) = acc;
+                if (dq == 0) sg[16] = gs + gs2;
                 e = send;
                 if (e < e1) {
                     ++k;
@@ -172,29 +186,28 @@ grad2_tokens_kernel(const Grad2Args a) {
                 }
             }
         }
-        __syncthreads();
+        group_bar(g);
         // ---- second pass: bin totals in slot order, final combine, store ----------------------------------------------
-        for (int t = tid; t < K * 4; t += kG2TokThreads) {
+        for (int t = gt; t < K * 4; t += kG2TokGT) {
             const int k = t >> 2, q = t & 3;
+            const size_t o = ((size_t)b * K + k) * D + c0 + q * 4;
+            const float4 z = __ldg(reinterpret_cast<const float4*>(a.Zs + o));      // in flight during the slot sums
+            float4 ad;
+            if (a.add_dZs) ad = __ldg(reinterpret_cast<const float4*>(a.add_dZs + o));
             const int e0 = bst[k], e1 = bst[k + 1];
             float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
             float gs = 0.f;
             if (e0 < e1) {
                 const int clo = e0 / kG2CH, chi = (e1 - 1) / kG2CH;
                 for (int c = clo; c <= chi; ++c) {
-                    const uint32_t sa_u = seg_u + (uint32_t)(c + k) * 80u;
-                    const float4 v = lds128(sa_u + q * 16);
+                    const float4 v = lds128(seg_u + (uint32_t)(c + k) * 80u + q * 16);
                     acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
                     gs += seg[(c + k) * 20 + 16];
                 }
             }
-            const size_t o = ((size_t)b * K + k) * D + c0 + q * 4;
-            const float4 z = __ldg(reinterpret_cast<const float4*>(a.Zs + o));
-            float4 ad;
-            if (a.add_dZs) ad = __ldg(reinterpret_cast<const float4*>(a.add_dZs + o));
             *reinterpret_cast<float4*>(a.dZs + o) = token_out(z, gs, acc, a.add_dZs ? &ad : nullptr, a.dpre_out != 0);
         }
-        __syncthreads();
+        group_bar(g);
     }
 }
 
@@ -376,7 +389,8 @@ grad2_cls_kernel(const Grad2Args a) {
 
 static size_t g2_tok_smem(int K, int P) {
     const int NC = (P + kG2CH - 1) / kG2CH;
-    return sizeof(float) * ((size_t)P * kG2DS + 2 * (size_t)((P + 1) & ~1) + (size_t)(NC + K) * 20) + sizeof(int) * ((size_t)K + 1 + NC);
+    const size_t grp = 2 * (size_t)((P + 1) & ~1) + (size_t)(NC + K) * 20 + (size_t)((K + 1 + NC + 3) & ~3);
+    return sizeof(float) * ((size_t)P * kG2DS + kG2TokGroups * grp);
 }
 static size_t g2_pro_smem(int K) { return sizeof(float) * (size_t)kG2ProIB * (K + 1) * 4; }
 static int g2_cls_psplit(int Pg) { return (Pg + kG2ClsSplit - 1) / kG2ClsSplit; }
@@ -439,7 +453,7 @@ extern "C" int pph_similarity_bwd2(int parts, const float* g_l, const float* g_g
     if (parts & PPH_BWD2_TOKENS) {
         PPH_REQUIRE(dZs, PPH_EINVAL, "pph_similarity_bwd2(TOKENS): null dZs");
         const size_t smem = g2_tok_smem(K, P);
-        cudaError_t e = cudaFuncSetAttribute(grad2_tokens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = opt_in_smem(grad2_tokens_kernel, (int)smem);
         if (e != cudaSuccess) { set_error("pph_similarity_bwd2: %s", cudaGetErrorString(e)); return (int)e; }
         launch_k(grad2_tokens_kernel, dim3(a.NS * a.nIG), dim3(kG2TokThreads), smem, st, a);
         const int rc = launch_status("pph_similarity_bwd2(tokens)");
@@ -448,7 +462,7 @@ extern "C" int pph_similarity_bwd2(int parts, const float* g_l, const float* g_g
     if (parts & PPH_BWD2_PROTOS) {
         PPH_REQUIRE(dPl && (Pg == 0 || dPg), PPH_EINVAL, "pph_similarity_bwd2(PROTOS): null output");
         const size_t smem = g2_pro_smem(K);
-        cudaError_t e = cudaFuncSetAttribute(grad2_protos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = opt_in_smem(grad2_protos_kernel, (int)smem);
         if (e != cudaSuccess) { set_error("pph_similarity_bwd2: %s", cudaGetErrorString(e)); return (int)e; }
         launch_k(grad2_protos_kernel, dim3(a.NS4 * a.nPT), dim3(kG2ProThreads), smem, st, a);
         const int rc = launch_status("pph_similarity_bwd2(protos)");
@@ -457,7 +471,7 @@ extern "C" int pph_similarity_bwd2(int parts, const float* g_l, const float* g_g
     if ((parts & PPH_BWD2_CLS) && Pg > 0) {
         PPH_REQUIRE(dZc, PPH_EINVAL, "pph_similarity_bwd2(CLS): null dZc");
         const size_t smem = g2_cls_smem(Pg);
-        cudaError_t e = cudaFuncSetAttribute(grad2_cls_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = opt_in_smem(grad2_cls_kernel, (int)smem);
         if (e != cudaSuccess) { set_error("pph_similarity_bwd2: %s", cudaGetErrorString(e)); return (int)e; }
         launch_k(grad2_cls_kernel, dim3(a.NS * kG2ClsSplit), dim3(kG2ClsThreads), smem, st, a);
         const int rc = launch_status("pph_similarity_bwd2(cls)");

@@ -10,6 +10,7 @@
 //                       deterministic bins, so every gradient row is summed in a fixed order (bit-reproducible).
 #include "pph_common.cuh"
 #include "pph_bins.cuh"
+#include "pph_step2.cuh"
 
 namespace pph {
 
@@ -21,13 +22,22 @@ bin_tokens_kernel(const int32_t* __restrict__ argmin_l, int K, int P, int32_t* _
     bin_tokens_body<false>(blockIdx.x, argmin_l, K, P, bin_start, item_start, bin_list, smi);
 }
 
+// Extras of the fused training step (pph_similarity_bwd_fused): per-image PPC prototype rows summed over the images of
+// a class in image order (class lists from pph_head_mid), and token-side outputs written as the pre-activation gradient
+// dpre = dZ * Z * (1 - Z) that pph_addon_bwd3 consumes.
+struct BwdExtras {
+    const float* dP_img;            // [B][m][D] or nullptr
+    const int32_t *cls_start, *cls_order;
+    int m, dpre_out;
+};
+
 // ---- gather kernels (templated on DV = ceil(D / 32) register slots per lane) ---------------------------------------
 template <int DV, bool FULL>
 __device__ __forceinline__ void
 proto_grad_body(int vb, const float* __restrict__ g_l, const float* __restrict__ g_g, const int32_t* __restrict__ argmin_l,
                 const float* __restrict__ Zs, const float* __restrict__ Zc, const float* __restrict__ Pl,
                 const float* __restrict__ Pgl, int B, int K, int D, int P, int Pg, const float* __restrict__ add_dPl,
-                float* __restrict__ dPl, float* __restrict__ dPg) {
+                float* __restrict__ dPl, float* __restrict__ dPg, const BwdExtras& ex) {
     const int row = vb * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (row >= P + Pg) return;
     const bool global = row >= P;
@@ -71,10 +81,21 @@ proto_grad_body(int vb, const float* __restrict__ g_l, const float* __restrict__
     const float* pr = (global ? Pgl : Pl) + (size_t)p * D;
     float* out = (global ? dPg : dPl) + (size_t)p * D;
     const float* add = (!global && add_dPl) ? add_dPl + (size_t)p * D : nullptr;      // e.g. the PPC-loss contribution
+    int c0 = 0, c1 = 0, jj = 0;
+    if (!global && ex.dP_img) {
+        const int cls = p / ex.m;
+        jj = p - cls * ex.m;
+        c0 = __ldg(ex.cls_start + cls);
+        c1 = __ldg(ex.cls_start + cls + 1);
+    }
 #pragma unroll
     for (int i = 0; i < DV; ++i)
-        if (FULL || i * 32 + lane < D)
-            out[i * 32 + lane] = 2.0f * (__ldg(pr + i * 32 + lane) * gsum - acc[i]) + (add ? __ldg(add + i * 32 + lane) : 0.f);
+        if (FULL || i * 32 + lane < D) {
+            float r = 2.0f * (__ldg(pr + i * 32 + lane) * gsum - acc[i]) + (add ? __ldg(add + i * 32 + lane) : 0.f);
+            for (int c = c0; c < c1; ++c)          // PPC rows of this prototype's class, image order: deterministic
+                r += __ldg(ex.dP_img + ((size_t)__ldg(ex.cls_order + c) * ex.m + jj) * D + i * 32 + lane);
+            out[i * 32 + lane] = r;
+        }
 }
 
 // One warp per work item = (image, token, chunk of <= kBinChunk bin entries).  Single-chunk bins write their row
@@ -86,7 +107,7 @@ token_grad_body(int vb, const float* __restrict__ g_l, const int32_t* __restrict
                 const int32_t* __restrict__ item_start, const int32_t* __restrict__ bin_list,
                 const float* __restrict__ Zs, const float* __restrict__ Pl, int B, int K, int D, int P,
                 int items_per_image, float* part, float* part_gsum, unsigned int* counters,
-                const float* __restrict__ add_dZs, float* __restrict__ dZs) {
+                const float* __restrict__ add_dZs, float* __restrict__ dZs, const BwdExtras& ex) {
     const int gw = vb * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int b = gw / items_per_image, item = gw - b * items_per_image;
     if (b >= B) return;
@@ -147,8 +168,12 @@ token_grad_body(int vb, const float* __restrict__ g_l, const int32_t* __restrict
     if (nchunks == 1) {
 #pragma unroll
         for (int i = 0; i < DV; ++i)
-            if (FULL || i * 32 + lane < D)
-                out[i * 32 + lane] = 2.0f * (__ldg(zr + i * 32 + lane) * gsum - acc[i]) + (add ? __ldg(add + i * 32 + lane) : 0.f);
+            if (FULL || i * 32 + lane < D) {
+                const float z = __ldg(zr + i * 32 + lane);
+                float r = 2.0f * (z * gsum - acc[i]) + (add ? __ldg(add + i * 32 + lane) : 0.f);
+                if (ex.dpre_out) r *= z * (1.0f - z);
+                out[i * 32 + lane] = r;
+            }
         return;
     }
     const size_t slot = (size_t)b * items_per_image + item;                 // partial slot of this chunk
@@ -176,8 +201,12 @@ token_grad_body(int vb, const float* __restrict__ g_l, const int32_t* __restrict
     }
 #pragma unroll
     for (int i = 0; i < DV; ++i)
-        if (FULL || i * 32 + lane < D)
-            out[i * 32 + lane] = 2.0f * (__ldg(zr + i * 32 + lane) * gt - tot[i]) + (add ? __ldg(add + i * 32 + lane) : 0.f);
+        if (FULL || i * 32 + lane < D) {
+            const float z = __ldg(zr + i * 32 + lane);
+            float r = 2.0f * (z * gt - tot[i]) + (add ? __ldg(add + i * 32 + lane) : 0.f);
+            if (ex.dpre_out) r *= z * (1.0f - z);
+            out[i * 32 + lane] = r;
+        }
     if (lane == 0) counters[row] = 0u;                                       // self-resetting (graph replay)
 }
 
@@ -189,7 +218,7 @@ constexpr int kClsTB = 8, kClsThreads = 256;
 __device__ __forceinline__ void
 cls_grad_body(int slice, int bgroup, int nslices, const float* __restrict__ g_g, const float* __restrict__ Zc,
               const float* __restrict__ Pgl, int B, int D, int Pg, int p_per_slice, float* part,
-              unsigned int* counters, float* __restrict__ dZc) {
+              unsigned int* counters, float* __restrict__ dZc, int dpre_out) {
     __shared__ __align__(16) float gs[64][kClsTB];      // [prototype][image]: two 128-bit broadcast reads per prototype
     __shared__ unsigned int s_ticket;
     const int tid = threadIdx.x, b0 = bgroup * kClsTB;
@@ -244,10 +273,32 @@ cls_grad_body(int slice, int bgroup, int nslices, const float* __restrict__ g_g,
             for (int d = tid; d < D; d += kClsThreads) {
                 float s = 0.f;
                 for (int sl = 0; sl < nslices; ++sl) s += __ldcg(part + ((size_t)sl * B + b) * D + d);
+                if (dpre_out) {
+                    const float z = __ldg(Zc + (size_t)b * D + d);
+                    s *= z * (1.0f - z);
+                }
                 dZc[(size_t)b * D + d] = s;
             }
         }
         if (tid == 0) counters[bgroup] = 0u;       // self-resetting (graph replay)
+    }
+}
+
+// dPl[p,:] += sum over the images b of p's class (image order) of dP_img[b, p % m, :]: the PPC loss's prototype
+// gradient, added after the similarity gradients were written (PPH_BWDF_PPCROWS).  One warp per prototype row.
+__global__ void __launch_bounds__(256)
+ppc_rows_add_kernel(const float* __restrict__ dP_img, const int32_t* __restrict__ cls_start,
+                    const int32_t* __restrict__ cls_order, int P, int D, int m, float* __restrict__ dPl) {
+    pdl_sync();
+    const int p = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (p >= P) return;
+    const int cls = p / m, jj = p - cls * m;
+    const int c0 = __ldg(cls_start + cls), c1 = __ldg(cls_start + cls + 1);
+    if (c0 >= c1) return;
+    for (int d = lane; d < D; d += 32) {
+        float r = dPl[(size_t)p * D + d];
+        for (int c = c0; c < c1; ++c) r += __ldg(dP_img + ((size_t)__ldg(cls_order + c) * m + jj) * D + d);
+        dPl[(size_t)p * D + d] = r;
     }
 }
 
@@ -289,35 +340,39 @@ sim_grads_kernel(const float* __restrict__ g_l, const float* __restrict__ g_g, c
                  int items_per_image, int n_cls, int n_slices, int p_per_slice, int n_proto,
                  float* tok_part, float* tok_gsum, unsigned int* tok_counters, float* cls_part,
                  unsigned int* cls_counters, const float* __restrict__ add_dZs, const float* __restrict__ add_dPl,
-                 float* __restrict__ dZs, float* __restrict__ dZc, float* __restrict__ dPl, float* __restrict__ dPg) {
+                 float* __restrict__ dZs, float* __restrict__ dZc, float* __restrict__ dPl, float* __restrict__ dPg,
+                 const BwdExtras ex) {
     pdl_sync();
     int vb = blockIdx.x;
     if (vb < n_cls) {
-        cls_grad_body(vb % n_slices, vb / n_slices, n_slices, g_g, Zc, Pgl, B, D, Pg, p_per_slice, cls_part, cls_counters, dZc);
+        cls_grad_body(vb % n_slices, vb / n_slices, n_slices, g_g, Zc, Pgl, B, D, Pg, p_per_slice, cls_part, cls_counters, dZc,
+                      ex.dpre_out);
         return;
     }
     vb -= n_cls;
     if (vb < n_proto) {
-        proto_grad_body<DV, FULL>(vb, g_l, g_g, argmin_l, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, add_dPl, dPl, dPg);
+        proto_grad_body<DV, FULL>(vb, g_l, g_g, argmin_l, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, add_dPl, dPl, dPg, ex);
         return;
     }
     vb -= n_proto;
     token_grad_body<DV, FULL>(vb, g_l, bin_start, item_start, bin_list, Zs, Pl, B, K, D, P, items_per_image, tok_part,
-                              tok_gsum, tok_counters, add_dZs, dZs);
+                              tok_gsum, tok_counters, add_dZs, dZs, ex);
 }
 
 template <int DV, bool FULL>
 static int launch_bwd(const float* g_l, const float* g_g, const int32_t* argmin_l, const BwdWorkspace& w,
                       const float* Zs, const float* Zc, const float* Pl, const float* Pgl,
                       int B, int K, int D, int P, int Pg, const float* add_dZs, const float* add_dPl,
-                      float* dZs, float* dZc, float* dPl, float* dPg, cudaStream_t st) {
+                      float* dZs, float* dZc, float* dPl, float* dPg, cudaStream_t st, const BwdExtras& ex,
+                      int roles = 3) {
     const int slices = 16;
     const int p_per_slice = Pg > 0 ? ceil_div(ceil_div(Pg, slices), 64) * 64 : 64;
     const int nsl = Pg > 0 ? ceil_div(Pg, p_per_slice) : 0;
-    const int n_cls = nsl * ceil_div(B, kClsTB);
-    const int n_proto = ceil_div(P + Pg, 8);
-    const int n_tok = ceil_div(B * w.items_per_image, 8);
-    launch_k(sim_grads_kernel<DV, FULL>, dim3(n_cls + n_proto + n_tok), dim3(256), (size_t)(0), st, g_l, g_g, argmin_l, w.bin_start, w.item_start, w.bin_list, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, w.items_per_image, n_cls, nsl, p_per_slice, n_proto, w.tok_part, w.tok_gsum, w.tok_counters, w.cls_part, w.cls_counters, add_dZs, add_dPl, dZs, dZc, dPl, dPg);
+    // roles: bit 0 token-side rows (dZs, dZc), bit 1 prototype rows (dPl, dPg) -- independent, may run as two launches
+    const int n_cls = (roles & 1) ? nsl * ceil_div(B, kClsTB) : 0;
+    const int n_proto = (roles & 2) ? ceil_div(P + Pg, 8) : 0;
+    const int n_tok = (roles & 1) ? ceil_div(B * w.items_per_image, 8) : 0;
+    launch_k(sim_grads_kernel<DV, FULL>, dim3(n_cls + n_proto + n_tok), dim3(256), (size_t)(0), st, g_l, g_g, argmin_l, w.bin_start, w.item_start, w.bin_list, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, w.items_per_image, n_cls, nsl, p_per_slice, n_proto, w.tok_part, w.tok_gsum, w.tok_counters, w.cls_part, w.cls_counters, add_dZs, add_dPl, dZs, dZc, dPl, dPg, ex);
     return launch_status("pph_similarity_bwd(grads)");
 }
 
@@ -367,7 +422,8 @@ extern "C" int pph_similarity_bwd(const float* g_l, const float* g_g, const int3
     }
     const int dv = ceil_div(D, 32);
     const bool full = (D % 32 == 0);
-#define PPH_BWD(DV, FULL) launch_bwd<DV, FULL>(g_l, g_g, argmin_l, w, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, add_dZs, add_dPl, dZs, dZc, dPl, dPg, st)
+    const BwdExtras ex{nullptr, nullptr, nullptr, 1, 0};
+#define PPH_BWD(DV, FULL) launch_bwd<DV, FULL>(g_l, g_g, argmin_l, w, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, add_dZs, add_dPl, dZs, dZc, dPl, dPg, st, ex)
     if (full && dv == 2) rc = PPH_BWD(2, true);
     else if (full && dv == 6) rc = PPH_BWD(6, true);
     else if (full && dv == 12) rc = PPH_BWD(12, true);
@@ -377,4 +433,44 @@ extern "C" int pph_similarity_bwd(const float* g_l, const float* g_g, const int3
     else rc = PPH_BWD(16, false);
 #undef PPH_BWD
     return rc;
+}
+
+// Same gradient kernel inside the fused training step: the token bins and class lists come from pph_head_mid
+// (step_workspace = the bwd_workspace given to it), `workspace` only provides this kernel's partial slots and counters.
+extern "C" int pph_similarity_bwd_fused(int parts, const float* g_l, const float* g_g, const int32_t* argmin_l,
+                                        const float* Zs, const float* Zc, const float* Pl, const float* Pgl,
+                                        int B, int K, int D, int P, int Pg, int m, void* workspace, void* step_workspace,
+                                        const float* add_dZs, const float* dP_img, int dpre_out,
+                                        float* dZs, float* dZc, float* dPl, float* dPg, pph_stream_t stream) {
+    using namespace pph;
+    PPH_REQUIRE((parts & 7) != 0, PPH_EINVAL, "pph_similarity_bwd_fused: parts must name TOKENS (1), PROTOS (2), PPCROWS (4)");
+    if (parts == 4) {          // only the PPC prototype rows, added onto dPl (after the launch that wrote dPl)
+        PPH_REQUIRE(dP_img && dPl && step_workspace && m >= 1, PPH_EINVAL, "pph_similarity_bwd_fused(PPCROWS): null pointer");
+        const Step2Bins bins4 = carve_bins(step_workspace, B, K, P);
+        launch_k(ppc_rows_add_kernel, dim3(ceil_div(P, 8)), dim3(256), (size_t)0, as_stream(stream), dP_img, bins4.cls_start,
+                 bins4.cls_order, P, D, m, dPl);
+        return launch_status("pph_similarity_bwd_fused(ppc rows)");
+    }
+    PPH_REQUIRE(g_l && argmin_l && Zs && Pl && dZs && dPl && workspace && step_workspace, PPH_EINVAL,
+                "pph_similarity_bwd_fused: null pointer");
+    PPH_REQUIRE(Pg == 0 || (g_g && Zc && Pgl && dZc && dPg), PPH_EINVAL, "pph_similarity_bwd_fused: null global pointer");
+    PPH_REQUIRE(B >= 1 && K >= 1 && D >= 1 && D <= 512 && P >= 1 && Pg >= 0 && m >= 1, PPH_EINVAL,
+                "pph_similarity_bwd_fused: bad dims");
+    BwdWorkspace w = carve_ws(workspace, B, K, D, P, Pg);
+    const Step2Bins bins = carve_bins(step_workspace, B, K, P);
+    w.bin_start = bins.bin_start; w.item_start = bins.item_start; w.bin_list = bins.bin_list;
+    const BwdExtras ex{dP_img, bins.cls_start, bins.cls_order, m, dpre_out};
+    cudaStream_t st = as_stream(stream);
+    const float* add_dPl = nullptr;
+    const int dv = ceil_div(D, 32);
+    const bool full = (D % 32 == 0);
+#define PPH_BWD(DV, FULL) launch_bwd<DV, FULL>(g_l, g_g, argmin_l, w, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, add_dZs, add_dPl, dZs, dZc, dPl, dPg, st, ex, parts & 3)
+    if (full && dv == 2) return PPH_BWD(2, true);
+    if (full && dv == 6) return PPH_BWD(6, true);
+    if (full && dv == 12) return PPH_BWD(12, true);
+    if (dv <= 2) return PPH_BWD(2, false);
+    if (dv <= 6) return PPH_BWD(6, false);
+    if (dv <= 12) return PPH_BWD(12, false);
+    return PPH_BWD(16, false);
+#undef PPH_BWD
 }

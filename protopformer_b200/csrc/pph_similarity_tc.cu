@@ -752,7 +752,7 @@ template <int NTERMS, int KT, int EPI = 1>
 static int launch_tc2(const CUtensorMap* maps, const TcParams& prm, const Tc2Plan& pl, cudaStream_t st) {
     auto kern = similarity_tc2_kernel<NTERMS, KT, EPI>;
     {   // per call, not cached in a static: the attribute is per device and setting it is cheap
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemLimit);
+        cudaError_t e = opt_in_smem(kern, kTcSmemLimit);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     }
     launch_k(kern, dim3(pl.grid), dim3(kTcThreads), (size_t)(pl.smem), st, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], prm, pl.lanes_l, pl.n_local_ctas, pl.stages, pl.b_tile_bytes);
@@ -763,7 +763,7 @@ template <int NTERMS, int KT>
 static int launch_tc(const CUtensorMap* maps, const TcParams& prm, int grid, cudaStream_t st) {
     auto kern = similarity_tc_kernel<NTERMS, KT>;
     {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes);
+        cudaError_t e = opt_in_smem(kern, kTcSmemBytes);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
     }
     launch_k(kern, dim3(grid), dim3(kTcThreads), (size_t)(kTcSmemBytes), st, maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], maps[6], maps[7], prm);

@@ -267,8 +267,7 @@ inline int launch_tcgemm(int M, int N, int Kd, int BN, int splits, AOp a, BOp b,
     auto kern = tcgemm_kernel<AOp, BOp, Epi>;
     const size_t smem = tcgemm_smem_bytes(BN);
     {   // per call: the attribute is per device and setting it is cheap
-        cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                               (int)tcgemm_smem_bytes(kTgMaxBN));
+        cudaError_t err = opt_in_smem(kern, (int)tcgemm_smem_bytes(kTgMaxBN));
         if (err != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(err)); return (int)err; }
     }
     if (splits < 1) splits = 1;

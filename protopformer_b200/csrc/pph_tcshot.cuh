@@ -35,6 +35,16 @@ inline size_t tcshot_smem_bytes(int BN, int KB) {
     return 1024 + tcshot_operand_bytes(BN, KB) + 128 * 16 * 4 + 128 * 3 * 8 + 256;
 }
 
+// Optional operand contract (row-contiguous operands, kContigK == false):
+//   static constexpr bool kQuad = true;
+//   __device__ void load8x4(int row0, int k0, float (&v)[4][8]) const;     // rows row0..row0+3 (row0 % 4 == 0) x k0..k0+7
+// lets a thread fetch its values with 128-bit loads along the rows (4x fewer load instructions and index look-ups
+// than eight scalar loads per row) -- the transposed operands of the weight gradient are what this is for.
+template <class Op, class = void>
+struct op_is_quad { static constexpr bool value = false; };
+template <class Op>
+struct op_is_quad<Op, decltype((void)Op::kQuad)> { static constexpr bool value = Op::kQuad; };
+
 // Extra epilogue contract on top of pph_tcgemm.cuh's:
 //   static constexpr bool kGridReduce;                       // run reduce() on every CTA after a grid-wide barrier
 //   __device__ void reduce(int cta, int n_ctas, int tid, int nthreads) const;
@@ -72,50 +82,99 @@ tcshot_kernel(int M, int N, int Kd, int BN, int k_per_split, unsigned int* sync_
     }
 
     // ---- fill: k-block kb+1's global loads are in flight while k-block kb is converted and stored -------------------
+    constexpr bool kAQ = op_is_quad<AOp>::value, kBQ = op_is_quad<BOp>::value;
     const int nbg = BN * 8;                                  // B groups of 8 k per k-block (<= 1024: two per thread)
-    float va[2][2][8], vb[2][2][8];
+    // quad items: (4 adjacent rows, one 8-wide k chunk).  A has 32 x 8 = 256 of them, B (BN / 4) x 8 <= 256; when both
+    // operands are quad the first half of the CTA serves A and the second half B
+    const int a_item = tid, b_item = kAQ ? tid - 256 : tid;
+    const int nbq = (BN >> 2) * 8;
+    float va[2][4][8], vb_own[2][4][8];                      // [set][group or quad row][k]
+    // both operands quad: a thread serves ONE of them, so the two roles share one register array
+    float (&vb)[2][4][8] = *((kAQ && kBQ) ? &va : &vb_own);
+    auto zero8v = [](float (&v)[8]) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.f;
+    };
     auto load_kb = [&](int kb, int set) {
         const int k0 = kz0 + kb * kTsBK;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int g = tid + i * kTsThreads;
-            const int row = AOp::kContigK ? (g >> 3) : (g & (kTsBM - 1));
-            const int c = AOp::kContigK ? (g & 7) : (g >> 7);
-            if (k0 + c * 8 < kz1) a_op.load8(m0 + row, k0 + c * 8, va[set][i]);
-            else {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) va[set][i][e] = 0.f;
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int g = tid + i * kTsThreads;
-            if (g < nbg) {
-                const int row = BOp::kContigK ? (g >> 3) : (g % BN);
-                const int c = BOp::kContigK ? (g & 7) : (g / BN);
-                if (k0 + c * 8 < kz1) b_op.load8(n0 + row, k0 + c * 8, vb[set][i]);
+        if constexpr (kAQ) {
+            if (a_item < 256) {
+                const int rq = a_item & 31, c = a_item >> 5;
+                if (k0 + c * 8 < kz1) a_op.load8x4(m0 + 4 * rq, k0 + c * 8, va[set]);
                 else {
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) vb[set][i][e] = 0.f;
+                    for (int i = 0; i < 4; ++i) zero8v(va[set][i]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int g = tid + i * kTsThreads;
+                const int row = AOp::kContigK ? (g >> 3) : (g & (kTsBM - 1));
+                const int c = AOp::kContigK ? (g & 7) : (g >> 7);
+                if (k0 + c * 8 < kz1) a_op.load8(m0 + row, k0 + c * 8, va[set][i]);
+                else zero8v(va[set][i]);
+            }
+        }
+        if constexpr (kBQ) {
+            if (b_item >= 0 && b_item < nbq) {
+                const int nq = BN >> 2;
+                const int rq = b_item % nq, c = b_item / nq;
+                if (k0 + c * 8 < kz1) b_op.load8x4(n0 + 4 * rq, k0 + c * 8, vb[set]);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) zero8v(vb[set][i]);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int g = tid + i * kTsThreads;
+                if (g < nbg) {
+                    const int row = BOp::kContigK ? (g >> 3) : (g % BN);
+                    const int c = BOp::kContigK ? (g & 7) : (g / BN);
+                    if (k0 + c * 8 < kz1) b_op.load8(n0 + row, k0 + c * 8, vb[set][i]);
+                    else zero8v(vb[set][i]);
                 }
             }
         }
     };
     auto store_kb = [&](int kb, int set) {
+        uint8_t* ah = sA_hi + (size_t)kb * a_bytes;
+        uint8_t* al = sA_lo + (size_t)kb * a_bytes;
+        uint8_t* bh = sB_hi + (size_t)kb * b_bytes;
+        uint8_t* bl = sB_lo + (size_t)kb * b_bytes;
+        if constexpr (kAQ) {
+            if (a_item < 256) {
+                const int rq = a_item & 31, c = a_item >> 5;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int g = tid + i * kTsThreads;
-            const int row = AOp::kContigK ? (g >> 3) : (g & (kTsBM - 1));
-            const int c = AOp::kContigK ? (g & 7) : (g >> 7);
-            tg_store_split8(sA_hi + (size_t)kb * a_bytes, sA_lo + (size_t)kb * a_bytes, row, c, va[set][i]);
+                for (int i = 0; i < 4; ++i) tg_store_split8(ah, al, 4 * rq + i, c, va[set][i]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int g = tid + i * kTsThreads;
+                const int row = AOp::kContigK ? (g >> 3) : (g & (kTsBM - 1));
+                const int c = AOp::kContigK ? (g & 7) : (g >> 7);
+                tg_store_split8(ah, al, row, c, va[set][i]);
+            }
         }
+        if constexpr (kBQ) {
+            if (b_item >= 0 && b_item < nbq) {
+                const int nq = BN >> 2;
+                const int rq = b_item % nq, c = b_item / nq;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int g = tid + i * kTsThreads;
-            if (g < nbg) {
-                const int row = BOp::kContigK ? (g >> 3) : (g % BN);
-                const int c = BOp::kContigK ? (g & 7) : (g / BN);
-                tg_store_split8(sB_hi + (size_t)kb * b_bytes, sB_lo + (size_t)kb * b_bytes, row, c, vb[set][i]);
+                for (int i = 0; i < 4; ++i) tg_store_split8(bh, bl, 4 * rq + i, c, vb[set][i]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int g = tid + i * kTsThreads;
+                if (g < nbg) {
+                    const int row = BOp::kContigK ? (g >> 3) : (g % BN);
+                    const int c = BOp::kContigK ? (g & 7) : (g / BN);
+                    tg_store_split8(bh, bl, row, c, vb[set][i]);
+                }
             }
         }
     };
@@ -211,7 +270,7 @@ inline int launch_tcshot(int M, int N, int Kd, int BN, int k_per_split, unsigned
         return PPH_EUNSUP;
     }
     const size_t smem = tcshot_smem_bytes(BN, KB);
-    cudaError_t err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t err = opt_in_smem(kern, (int)smem);
     if (err != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", what, cudaGetErrorString(err)); return (int)err; }
     dim3 grid(ceil_div(M, kTsBM), ceil_div(N, BN), ceil_div(Kd, k_per_split));
     if (Epi::kGridReduce) {

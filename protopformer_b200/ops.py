@@ -636,7 +636,7 @@ def fused_step_supported(B, N, Din, D, K, P, Pg, C, m) -> bool:
     lib = _lib.load()
     if C > 256 or B < 1 or B > 64 * 74:
         return False
-    ppc_smem = 4 * (m * D + K * (D + 4) + 2 * m * K + 8 * m + 8)
+    ppc_smem = 4 * (m * D + K * (D + 4) + 2 * m * K + 8 * m + 32)
     return bool(lib.pph_head_prep_supported(B, N, Din, D, K) and lib.pph_similarity_bwd2_supported(B, K, D, P, Pg)
                 and lib.pph_addon_bwd2_supported(B, N, Din, D, K) and ppc_smem <= 200 * 1024 and D % 4 == 0)
 
@@ -662,14 +662,20 @@ class FusedHeadStep:
         # kernel choice per stage: "tc" = single-shot tcgen05 kernels (pph_addon_fwd2 / pph_addon_bwd3) where the shape
         # allows, "simt" = the exact-FP32 CUDA-core kernels (pph_head_prep / pph_addon_bwd2)
         tc_bits = _lib.load().pph_addon_tc2_supported(B, N, Din, D, cfg.K)
+        # "bwd": "gather" = round-1 argmin-routed L2 gather kernel fed by pph_head_mid's bins, "staged" = the three
+        # shared-memory-staged kinds of pph_similarity_bwd2;  "ppc": "inline" = PPC role inside the pph_head_mid launch,
+        # "split" = its own concurrent launch joined before the backward, "late" = concurrent launch that overlaps the
+        # last layers AND the token-side gradients (its token gradient enters through the add-on backward's operand,
+        # its prototype rows through the prototype-row launch on the same side branch)
         v = {"prep": "tc" if (tc_bits & 1) else "simt",
-             "addon_bwd": "tc" if (tc_bits & 6) == 6 else "simt"}
+             "addon_bwd": "tc" if (tc_bits & 6) == 6 else "simt", "bwd": "gather", "ppc": "late"}
         v.update(variants or {})
         if v["prep"] == "tc" and not (tc_bits & 1):
             v["prep"] = "simt"
         if v["addon_bwd"] == "tc" and (tc_bits & 6) != 6:
             v["addon_bwd"] = "simt"
         self.variants = v
+        self.stop_after = 0             # measurement aid (scripts/step_times.py): truncate the step after stage n
         self.dims = (B, N, Din, D, P, Pg, C, m, heads)
         self.cov_coe, self.mean_coe = float(ppc_cov_coe), float(ppc_mean_coe)
         K = cfg.K
@@ -697,7 +703,7 @@ class FusedHeadStep:
         self.ws_tc = _ws("pph_addon_tc2_ws_bytes", B, N, Din, D, K, zero=True, device=device)
         self.side = torch.cuda.Stream(device=device)
         self.side2 = torch.cuda.Stream(device=device)
-        self.ev = [torch.cuda.Event() for _ in range(6)]
+        self.ev = [torch.cuda.Event() for _ in range(8)]
         self.dlogits = self.g_l = self.g_g = self.pairT = self.ws_bins = None
         self.dZs_ppc = self.dP_img = None
         if train:
@@ -705,6 +711,7 @@ class FusedHeadStep:
             self.dlogits, self.g_l, self.g_g = e(B, C), e(B, P), e(B, Pg)
             self.pairT = e(P + Pg, Bp, 2)
             self.ws_bins = _ws("pph_similarity_bwd2_ws_bytes", B, K, D, P, zero=True, device=device)
+            self.ws_gather = bwd_workspace(B, K, D, P, Pg, device)
             if use_ppc:
                 self.dZs_ppc, self.dP_img = e(B, K, D), e(B, m, D)
             self.dZs, self.dZc = e(B, K, D), e(B, D)
@@ -748,6 +755,8 @@ class FusedHeadStep:
               Pg, Pgn, self.Pg_hi, self.Pg_lo, self.pg2, self.pg2_ctr, self.pg2_hi)
             if self.train and self.variants["addon_bwd"] == "tc":
                 main.wait_event(ev[4])
+        if self.stop_after == 1:
+            return self.losses
         mode = cfg.mode_id
         sel = {_lib.MODE_FP32_FMA: 0, _lib.MODE_BF16X3: 1, _lib.MODE_BF16: 2}[mode]
         c("pph_similarity_fwd", mode, cfg.act_id, float(cfg.eps), B, K, D, Pn, Pgn, self.Zs, self.Zc,
@@ -756,41 +765,84 @@ class FusedHeadStep:
           (self.p2, self.p2_ctr, self.p2_hi)[sel], (self.pg2, self.pg2_ctr, self.pg2_hi)[sel],
           self.P_hi, self.P_lo, self.Pg_hi, self.Pg_lo,
           self.dmin_l, self.argmin, self.act_l, self.dmin_g, self.act_g, None, None)
-        ppc = self.use_ppc and self.train
-        c("pph_head_mid", self.act_l, self.act_g, self.dmin_l, self.dmin_g, self.argmin, Wl, Wg, labels,
-          B, K, D, Pn, Pgn, C, m, N, float(cfg.global_coe), cfg.act_id, float(cfg.eps), float(upstream),
-          1 if self.train else 0, 1 if ppc else 0, self.Zs, self.z2s, P, self.p2, self.idx32,
-          float(cfg.ppc_cov_thresh), float(cfg.ppc_mean_thresh), self.cov_coe, self.mean_coe,
-          self.ws_mid, self.ws_bins, self.logits, self.logits_g, self.logits_l, self.losses, self.dlogits,
-          self.g_l, self.g_g, self.pairT, self.dZs_ppc if ppc else None, self.dP_img if ppc else None)
-        if not self.train:
+        if self.stop_after == 2:
             return self.losses
-        # dZs / dZc leave the backward already multiplied by Z (1 - Z) (dpre_out = 1): what pph_addon_bwd2 consumes
-        bwd = lambda parts: c("pph_similarity_bwd2", parts, self.g_l, self.g_g, self.pairT, self.ws_bins, self.Zs, self.Zc,  # noqa: E731
-                              P, Pg, B, K, D, Pn, Pgn, m, self.dZs_ppc if ppc else None, self.dP_img if ppc else None, 1,
-                              self.dZs, self.dZc, grads["P"], grads["Pg"])
-        ev[0].record(main)
-        side.wait_event(ev[0])
-        side2.wait_event(ev[0])
-        with torch.cuda.stream(side):
-            bwd(2)                      # prototype rows: not needed by the add-on backward, joins at the end
-            ev[1].record(side)
-        with torch.cuda.stream(side2):
-            bwd(4)                      # CLS rows
-            ev[2].record(side2)
-        bwd(1)                          # token rows
-        main.wait_event(ev[2])
-        if self.variants["addon_bwd"] == "tc":
-            # weight gradient (112 CTAs behind a grid barrier) || token gradient (82 CTAs): two graph branches
-            ev[5].record(main)
-            side2.wait_event(ev[5])
+        ppc = self.use_ppc and self.train
+        vr = self.variants
+        late = ppc and vr["ppc"] == "late" and vr["bwd"] == "gather" and vr["addon_bwd"] == "tc"
+        split_ppc = ppc and (vr["ppc"] == "split" or late)
+
+        def mid(use_ppc):
+            c("pph_head_mid", self.act_l, self.act_g, self.dmin_l, self.dmin_g, self.argmin, Wl, Wg, labels,
+              B, K, D, Pn, Pgn, C, m, N, float(cfg.global_coe), cfg.act_id, float(cfg.eps), float(upstream),
+              1 if self.train else 0, use_ppc, self.Zs, self.z2s, P, self.p2, self.idx32,
+              float(cfg.ppc_cov_thresh), float(cfg.ppc_mean_thresh), self.cov_coe, self.mean_coe,
+              self.ws_mid, self.ws_bins, self.logits, self.logits_g, self.logits_l, self.losses, self.dlogits,
+              self.g_l, self.g_g, self.pairT if vr["bwd"] == "staged" else None, self.dZs_ppc if ppc else None,
+              self.dP_img if ppc else None)
+
+        if split_ppc:        # PPC loss forward + backward as a concurrent branch beside the last layers
+            ev[0].record(main)
+            side.wait_event(ev[0])
+            with torch.cuda.stream(side):
+                mid(3 + (4 if late else 0))     # late: dZs_ppc leaves as dpre, consumed by the add-on backward
+                ev[6 if late else 1].record(side)
+            mid(2)
+            if not late:
+                main.wait_event(ev[1])
+        else:
+            mid(1 if ppc else 0)
+        if not self.train or self.stop_after == 3:
+            if late:
+                main.wait_event(ev[6])
+            return self.losses
+
+        def gather(parts, add, dpi):
+            c("pph_similarity_bwd_fused", parts, self.g_l, self.g_g, self.argmin, self.Zs, self.Zc, P, Pg, B, K, D, Pn, Pgn,
+              m, self.ws_gather, self.ws_bins, add, dpi, 1, self.dZs, self.dZc, grads["P"], grads["Pg"])
+
+        dpre_add = None
+        if late:
+            # main: both gradient parts in one launch (as round 1) -> add-on backward.  The PPC branch (side) overlaps
+            # the last layers and this launch; its token gradient joins inside the add-on backward's operand
+            # (dpre_add_s), its prototype rows are added onto dP by a small launch beside the add-on backward.
+            gather(3, None, None)                   # one launch for both parts: split in two they only slow each other
+            ev[2].record(main)
+            with torch.cuda.stream(side):           # after the PPC branch and this launch: the PPC prototype rows onto dP
+                side.wait_event(ev[2])
+                gather(4, None, self.dP_img)
+                ev[1].record(side)
+            dpre_add = self.dZs_ppc
+        elif vr["bwd"] == "gather":
+            gather(3, self.dZs_ppc if ppc else None, self.dP_img if ppc else None)
+            ev[1].record(main)          # (joined at the end like the staged prototype branch)
+        else:
+            bwd = lambda parts: c("pph_similarity_bwd2", parts, self.g_l, self.g_g, self.pairT, self.ws_bins, self.Zs,  # noqa: E731
+                                  self.Zc, P, Pg, B, K, D, Pn, Pgn, m, self.dZs_ppc if ppc else None,
+                                  self.dP_img if ppc else None, 1, self.dZs, self.dZc, grads["P"], grads["Pg"])
+            ev[0].record(main)
+            side.wait_event(ev[0])
+            side2.wait_event(ev[0])
+            with torch.cuda.stream(side):
+                bwd(2)                      # prototype rows: not needed by the add-on backward, joins at the end
+                ev[1].record(side)
             with torch.cuda.stream(side2):
-                c("pph_addon_bwd3", 2, tokens, self.idx32, Wa, self.dZs, self.dZc, B, N, Din, D, K, self.ws_tc,
-                  None, None, self.dtokens)
+                bwd(4)                      # CLS rows
                 ev[2].record(side2)
-            c("pph_addon_bwd3", 1, tokens, self.idx32, Wa, self.dZs, self.dZc, B, N, Din, D, K, self.ws_tc,
-              grads["Wa"], grads["ba"], None)
+            bwd(1)                          # token rows
             main.wait_event(ev[2])
+        if self.stop_after == 4:
+            main.wait_event(ev[1])
+            return self.losses
+        if vr["addon_bwd"] == "tc":
+            if late:
+                main.wait_event(ev[6])              # dZs_ppc (as dpre) from the PPC branch
+            # token gradient (82 CTAs) then weight gradient (112 CTAs behind a grid barrier): both want one CTA per SM, as
+            # graph branches they only time-slice the machine (measured), so they run back to back
+            c("pph_addon_bwd3", 2, tokens, self.idx32, Wa, self.dZs, self.dZc, dpre_add, B, N, Din, D, K, self.ws_tc,
+              None, None, self.dtokens)
+            c("pph_addon_bwd3", 1, tokens, self.idx32, Wa, self.dZs, self.dZc, dpre_add, B, N, Din, D, K, self.ws_tc,
+              grads["Wa"], grads["ba"], None)
         else:
             c("pph_addon_bwd2", 3, tokens, self.idx32, Wa, self.dZs, self.dZc, B, N, Din, D, K,
               self.ws_addon, grads["Wa"], grads["ba"], self.dtokens)

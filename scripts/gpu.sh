@@ -15,6 +15,11 @@ case $stage in
     echo "== $k: rc=$? $(tail -1 gpurun_out/t_$k.log)" ;;
   times64)
     timeout 300 python scripts/step_times.py cub_b64 fp32 > gpurun_out/times_b64.json 2> gpurun_out/times_b64.err; tail -c 1500 gpurun_out/times_b64.json ;;
+  times64pdl)
+    PPH_PDL=1 timeout 300 python scripts/step_times.py cub_b64 fp32 > gpurun_out/times_b64_pdl.json 2> gpurun_out/times_b64_pdl.err; tail -c 1500 gpurun_out/times_b64_pdl.json ;;
+  timeline)
+    timeout 300 python scripts/timeline.py cub_b64 fp32 v2 > gpurun_out/timeline_v2.txt 2> gpurun_out/timeline_v2.err; tail -40 gpurun_out/timeline_v2.txt; tail -3 gpurun_out/timeline_v2.err
+    timeout 300 python scripts/timeline.py cub_b64 fp32 v1 > gpurun_out/timeline_v1.txt 2> gpurun_out/timeline_v1.err ;;
   times)
     timeout 300 python scripts/step_times.py cub_b64 fp32 > gpurun_out/times_b64.json 2> gpurun_out/times_b64.err; tail -c 1500 gpurun_out/times_b64.json
     timeout 300 python scripts/step_times.py cub_b64 fp32 1024 > gpurun_out/times_b1024.json 2> gpurun_out/times_b1024.err; tail -c 1500 gpurun_out/times_b1024.json ;;

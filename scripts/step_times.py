@@ -43,25 +43,29 @@ def timed_graph(fn, rep=REP, outer=10):
     return 1e3 * e0.elapsed_time(e1) / (outer * rep)
 
 
-def make(impl, train=True, variants=None):
+def make(impl, train=True, variants=None, stop_after=0):
     params = {k: case[k].to(dev).clone() for k in ("Wa", "ba", "P", "Pg", "Wl", "Wg")}
     for k in ("Wa", "ba", "P", "Pg"):
         params[k].requires_grad_(train)
     st = GraphedHeadStep(params, cfg, B=s.B, N=s.N, C=s.C, m=s.m, train=train, impl=impl, variants=variants)
     st.load(0, case["tokens"], case["scores"], case["labels"])
+    if stop_after:
+        st.fused.stop_after = stop_after
     torch.cuda.synchronize()
     st.capture()
     return st, params
 
 
 out = {"shape": key, "B": s.B, "mode": mode}
-ARMS = [("v1", None), ("v2", dict(prep="simt", addon_bwd="simt")), ("v2", dict(prep="tc", addon_bwd="simt")),
-        ("v2", dict(prep="simt", addon_bwd="tc")), ("v2", dict(prep="tc", addon_bwd="tc"))]
+S = dict(prep="simt", addon_bwd="simt", bwd="staged", ppc="inline")
+T = dict(prep="tc", addon_bwd="tc", bwd="gather", ppc="late")
+ARMS = [("v1", None), ("v2", S), ("v2", T), ("v2", dict(T, ppc="inline")), ("v2", dict(T, ppc="split")), ("v2", dict(T, bwd="staged", ppc="split")),
+        ("v2", dict(T, prep="simt")), ("v2", dict(T, addon_bwd="simt"))]
 for impl, variants in ARMS:
     for train in (True, False):
-        if not train and variants is not None and variants["addon_bwd"] == "tc":
+        if not train and variants is not None and variants not in (S, T):
             continue
-        tag = impl if variants is None else f"v2[{variants['prep']},{variants['addon_bwd']}]"
+        tag = impl if variants is None else "v2[" + ",".join(f"{k}={v}" for k, v in variants.items()) + "]"
         try:
             st, _ = make(impl, train, variants)
         except Exception as exc:
@@ -78,7 +82,7 @@ for impl, variants in ARMS:
         torch.cuda.synchronize()
         us = 1e3 * e0.elapsed_time(e1) / 300
         out[f"{tag}_{'train' if train else 'eval'}"] = {"us": round(us, 2), "launches": st.kernel_launches_per_step}
-        if impl == "v2" and train and variants == dict(prep="simt", addon_bwd="simt"):
+        if impl == "v2" and train and variants == S:
             f = st.fused
             p = st.p
             grads = st.grads
@@ -109,6 +113,20 @@ for impl, variants in ARMS:
                 per["head_mid"] = timed_graph(lambda: mid(1, 1))
                 per["head_mid(no ppc)"] = timed_graph(lambda: mid(1, 0))
                 per["head_mid(eval)"] = timed_graph(lambda: mid(0, 0))
+                per["head_mid(LL+bins+cls only, mode 2)"] = timed_graph(lambda: mid(1, 2))
+                per["head_mid(PPC only, mode 3)"] = timed_graph(lambda: mid(1, 3))
+                sd, e_a, e_b = torch.cuda.Stream(), torch.cuda.Event(), torch.cuda.Event()
+
+                def mid_split():
+                    cur = torch.cuda.current_stream()
+                    e_a.record(cur)
+                    sd.wait_event(e_a)
+                    with torch.cuda.stream(sd):
+                        mid(1, 3)
+                        e_b.record(sd)
+                    mid(1, 2)
+                    cur.wait_event(e_b)
+                per["head_mid(mode 2 || mode 3)"] = timed_graph(mid_split)
                 def bwd2(parts):
                     c("pph_similarity_bwd2", parts, f.g_l, f.g_g, f.pairT, f.ws_bins, f.Zs, f.Zc, p["P"], p["Pg"], B, K, D, Pn,
                       Pgn, m, f.dZs_ppc, f.dP_img, 1, f.dZs, f.dZc, grads["P"], grads["Pg"])
@@ -124,7 +142,7 @@ for impl, variants in ARMS:
                 per["addon_bwd2[dgrad]"] = timed_graph(lambda: ab2(2))
 
                 def ab3(parts):
-                    c("pph_addon_bwd3", parts, tok, f.idx32, p["Wa"], f.dZs, f.dZc, B, N, Din, D, K, f.ws_tc,
+                    c("pph_addon_bwd3", parts, tok, f.idx32, p["Wa"], f.dZs, f.dZc, None, B, N, Din, D, K, f.ws_tc,
                       grads["Wa"], grads["ba"], f.dtokens)
                 per["addon_bwd3[wgrad]"] = timed_graph(lambda: ab3(1))
                 per["addon_bwd3[dgrad]"] = timed_graph(lambda: ab3(2))
@@ -136,4 +154,22 @@ for impl, variants in ARMS:
             out["v2_per_launch_us"] = per
             out["v2_sum_of_launches_us"] = (per["head_prep"] + per["similarity_fwd"] + per["head_mid"] +
                                             per["similarity_bwd2[all, serial]"] + per["addon_bwd2"])
+def time_step(st, n=300):
+    for _ in range(20):
+        st.run(0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        st.run(0)
+    e1.record()
+    torch.cuda.synchronize()
+    return 1e3 * e0.elapsed_time(e1) / n
+
+
+cum = {}
+for k, name in ((1, "prep"), (2, "+similarity"), (3, "+mid"), (4, "+bwd"), (0, "+addon_bwd = step")):
+    st, _ = make("v2", True, T, stop_after=k)
+    cum[name] = round(time_step(st), 2)
+out["v2[T] cumulative graph time by stage"] = cum
 print(json.dumps(out))

@@ -384,9 +384,10 @@ def test_addon_bwd3_single_shot_matches_float64(key, seed):
     ws = ops._ws("pph_addon_tc2_ws_bytes", B, N, Din, D, K, zero=True, device=DEV)
     dWa, dba, dtok = _e(D, Din), _e(D), torch.zeros(B, 1 + N, Din, device=DEV)
     parts = 3 if bits & 4 else 2
-    for _ in range(2):
-        L.call("pph_addon_bwd3", parts, d["tokens"], idx, d["Wa"].reshape(D, Din), dpre_s, dpre_c, B, N, Din, D, K, ws,
-               dWa, dba, dtok)
+    half = (0.5 * dpre_s).contiguous()          # dpre_s = half + half through the dpre_add_s operand
+    for add in (None, half):
+        L.call("pph_addon_bwd3", parts, d["tokens"], idx, d["Wa"].reshape(D, Din), dpre_s if add is None else half, dpre_c,
+               add, B, N, Din, D, K, ws, dWa, dba, dtok)
     torch.cuda.synchronize()
     dpre = torch.cat([dpre_s.cpu(), dpre_c.cpu()[:, None]], 1).double()
     rows = torch.cat([1 + idx.cpu().long(), torch.zeros(B, 1, dtype=torch.long)], 1)
@@ -399,8 +400,12 @@ def test_addon_bwd3_single_shot_matches_float64(key, seed):
         assert norm_rel(dba.cpu(), dpre.sum((0, 1))) < 2e-5
 
 
-@pytest.mark.parametrize("variants", [dict(prep="simt", addon_bwd="simt"), dict(prep="tc", addon_bwd="tc"),
-                                      dict(prep="tc", addon_bwd="simt"), dict(prep="simt", addon_bwd="tc")])
+_S = dict(prep="simt", addon_bwd="simt", bwd="staged", ppc="inline")
+_T = dict(prep="tc", addon_bwd="tc", bwd="gather", ppc="late")
+
+
+@pytest.mark.parametrize("variants", [_S, _T, dict(_T, ppc="inline"), dict(_T, ppc="split"), dict(_T, bwd="staged", ppc="split"), dict(_S, bwd="gather"),
+                                      dict(_S, ppc="split"), dict(_T, prep="simt"), dict(_T, addon_bwd="simt")])
 def test_step_variants_agree_with_the_oracle(variants):
     shape, case, g, fn = load_golden("cub_b8_s1")
     step, params = _make_step(shape, case, "fp32", variants=variants)
