@@ -33,7 +33,7 @@ constexpr int kG2CH = 16;            // entries per chunk (TOKENS)
 constexpr int kG2TokThreads = 512;
 constexpr int kG2ProThreads = 256;
 constexpr int kG2ProPT = 512;        // prototypes per PROTOS CTA (8 warps x 32 lanes x 2)
-constexpr int kG2ProIB = 64;         // images resident per PROTOS chunk
+constexpr int kG2ProMaxIB = 64;      // images resident per PROTOS chunk (fewer when K is large)
 constexpr int kG2ClsThreads = 256;
 constexpr int kG2ClsSplit = 8;       // prototype splits (CLS)
 constexpr int kG2ClsIB = 64;         // images per CLS chunk (a lane owns two)
@@ -41,7 +41,7 @@ constexpr int kG2ClsIB = 64;         // images per CLS chunk (a lane owns two)
 struct Grad2Args {
     int B, Bp, K, D, P, Pg, m;
     int NS, IA, nIG;                  // TOKENS: slices of 16, images per CTA, image groups
-    int NS4, nPT;                     // PROTOS: slices of 4, prototype tiles over [0, P + Pg)
+    int NS4, nPT, IB;                 // PROTOS: slices of 4, prototype tiles over [0, P + Pg), images per chunk (even)
     int psplit;                       // CLS: global prototypes per split
     int dpre_out;
     const float *g_l, *g_g;
@@ -234,8 +234,8 @@ grad2_protos_kernel(const Grad2Args a) {
     float4 acc0 = make_float4(0.f, 0.f, 0.f, 0.f), acc1 = acc0;
     float gs0 = 0.f, gs1 = 0.f;
     const int last_pair = (a.Bp >> 1) - 1;
-    for (int b0 = 0; b0 < B; b0 += kG2ProIB) {
-        const int n = min(kG2ProIB, B - b0);
+    for (int b0 = 0; b0 < B; b0 += a.IB) {
+        const int n = min(a.IB, B - b0);
         __syncthreads();                                     // previous chunk's readers are done
         {
             const float* zs = a.Zs + (size_t)b0 * K * D + c0;
@@ -392,7 +392,11 @@ static size_t g2_tok_smem(int K, int P) {
     const size_t grp = 2 * (size_t)((P + 1) & ~1) + (size_t)(NC + K) * 20 + (size_t)((K + 1 + NC + 3) & ~3);
     return sizeof(float) * ((size_t)P * kG2DS + kG2TokGroups * grp);
 }
-static size_t g2_pro_smem(int K) { return sizeof(float) * (size_t)kG2ProIB * (K + 1) * 4; }
+static int g2_pro_ib(int K) {
+    int ib = (int)((size_t)100 * 1024 / ((size_t)(K + 1) * 16)) & ~1;
+    return ib > kG2ProMaxIB ? kG2ProMaxIB : ib;
+}
+static size_t g2_pro_smem(int K) { return sizeof(float) * (size_t)g2_pro_ib(K) * (K + 1) * 4; }
 static int g2_cls_psplit(int Pg) { return (Pg + kG2ClsSplit - 1) / kG2ClsSplit; }
 static size_t g2_cls_smem(int Pg) {
     return sizeof(float) * ((size_t)g2_cls_psplit(Pg) * kG2DS + (size_t)(kG2ClsThreads / 32) * kG2ClsIB * 17);
@@ -407,7 +411,7 @@ static size_t g2_ws_bytes(int B, int K, int D, int P) {
 extern "C" int pph_similarity_bwd2_supported(int B, int K, int D, int P, int Pg) {
     using namespace pph;
     if (B < 1 || K < 1 || P < 1 || Pg < 0 || D < kG2DS || D % kG2DS != 0) return 0;
-    return (g2_tok_smem(K, P) <= 220 * 1024 && g2_pro_smem(K) <= 110 * 1024 && g2_cls_smem(Pg) <= 110 * 1024) ? 1 : 0;
+    return (g2_tok_smem(K, P) <= 220 * 1024 && g2_pro_ib(K) >= 2 && g2_cls_smem(Pg) <= 110 * 1024) ? 1 : 0;
 }
 
 extern "C" int pph_similarity_bwd2_ws_bytes(int B, int K, int D, int P, long long* bytes) {
@@ -440,6 +444,7 @@ extern "C" int pph_similarity_bwd2(int parts, const float* g_l, const float* g_g
     if (a.IA < 1) a.IA = 1;
     a.nIG = ceil_div(B, a.IA);
     a.nPT = ceil_div(P + Pg, kG2ProPT);
+    a.IB = g2_pro_ib(K);
     a.psplit = g2_cls_psplit(Pg);
     a.dpre_out = dpre_out;
     a.g_l = g_l; a.g_g = g_g; a.pairT = reinterpret_cast<const float2*>(pairT);

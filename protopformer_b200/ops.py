@@ -637,8 +637,8 @@ def fused_step_supported(B, N, Din, D, K, P, Pg, C, m) -> bool:
     if C > 256 or B < 1 or B > 64 * 74:
         return False
     ppc_smem = 4 * (m * D + K * (D + 4) + 2 * m * K + 8 * m + 32)
-    return bool(lib.pph_head_prep_supported(B, N, Din, D, K) and lib.pph_similarity_bwd2_supported(B, K, D, P, Pg)
-                and lib.pph_addon_bwd2_supported(B, N, Din, D, K) and ppc_smem <= 200 * 1024 and D % 4 == 0)
+    return bool(lib.pph_head_prep_supported(B, N, Din, D, K) and lib.pph_addon_bwd2_supported(B, N, Din, D, K)
+                and ppc_smem <= 200 * 1024 and D % 4 == 0 and D <= 512)
 
 
 class FusedHeadStep:
@@ -674,6 +674,8 @@ class FusedHeadStep:
             v["prep"] = "simt"
         if v["addon_bwd"] == "tc" and (tc_bits & 6) != 6:
             v["addon_bwd"] = "simt"
+        if v["bwd"] == "staged" and not _lib.load().pph_similarity_bwd2_supported(B, cfg.K, D, P, Pg):
+            v["bwd"] = "gather"
         self.variants = v
         self.stop_after = 0             # measurement aid (scripts/step_times.py): truncate the step after stage n
         self.dims = (B, N, Din, D, P, Pg, C, m, heads)

@@ -64,8 +64,6 @@ def test_cait_backbone_loop_matches_reference_method():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("PPH_UNVALIDATED") != "1",
-                    reason="written after round 1's GPU budget was spent: run once with PPH_UNVALIDATED=1, then un-gate")
 @pytest.mark.parametrize("name", list(CASES))
 def test_backbone_loop_with_cuda_rollout(name):
     """Same loop, same GPU-resident fake blocks, CUDA rollout vs the oracle's rollout injected (maps copied to the host):

@@ -65,15 +65,11 @@ def test_class_maps_full_size_against_materialised_map():
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(__import__("os").environ.get("PPH_UNVALIDATED") != "1",
-                    reason="PPH_CLASSMAP=2 (operands staged in shared memory) was written after round 1's GPU budget was "
-                           "spent: run once with PPH_UNVALIDATED=1, then make it the default if green and faster")
-def test_unvalidated_class_maps_variant_2_in_subprocess():
+def test_class_maps_variant_2_in_subprocess():
     import os
     import subprocess
     import sys
     env = dict(os.environ, PPH_CLASSMAP="2")
-    env.pop("PPH_UNVALIDATED", None)
-    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-x"], env=env, capture_output=True,
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-x", "-k", "not subprocess"], env=env, capture_output=True,
                        text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:]

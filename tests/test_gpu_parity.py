@@ -300,12 +300,9 @@ def test_empty_batch():
     assert out.logits.shape == (0, shape.C)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("PPH_UNVALIDATED") != "1",
-                    reason="sweep-corner reference fixtures were added after round 1's GPU budget was spent: run once "
-                           "with PPH_UNVALIDATED=1, then move the cases into GOLDEN_CASES")
 @pytest.mark.parametrize("name", ["sweep_k49_s1", "sweep_k196_s1", "sweep_k144_d384_s1"])
 @pytest.mark.parametrize("mode", ["fp32", "fp32_fma"])
-def test_unvalidated_sweep_corner_fixtures(name, mode):
+def test_sweep_corner_fixtures(name, mode):
     """BASELINE config 5 corners against the REFERENCE's own outputs (not only against the FP32-FMA kernel)."""
     shape, case, g, fn = load_golden(name)
     out, _, _ = _forward(shape, case, mode)

@@ -251,6 +251,7 @@ def test_similarity_bwd2_matches_round1_kernel(key, seed):
     shape = synth.SHAPES[key]
     if key == "dogs_b256":
         shape = shape.with_batch(11)
+    assert L.load().pph_similarity_bwd2_supported(shape.B, shape.K, shape.D, shape.P, shape.Pg)
     case = synth.make_case(shape, seed=seed)
     d = _d(case)
     B, K, D, P, Pg, m = shape.B, shape.K, shape.D, shape.P, shape.Pg, shape.m
@@ -428,12 +429,12 @@ def test_step_variants_agree_with_the_oracle(variants):
 # ---------------------------------------------------------------------------------------------------------------
 # whole step
 # ---------------------------------------------------------------------------------------------------------------
-def _make_step(shape, case, mode, impl="v2", train=True, use_ppc=True, variants=None):
+def _make_step(shape, case, mode, impl="auto", train=True, use_ppc=True, variants=None, fn="log"):
     from protopformer_b200.graph import GraphedHeadStep
     params = {k: case[k].to(DEV).clone() for k in ("Wa", "ba", "P", "Pg", "Wl", "Wg")}
     for k in ("Wa", "ba", "P", "Pg"):
         params[k].requires_grad_(train)
-    step = GraphedHeadStep(params, _cfg(shape, mode), B=shape.B, N=shape.N, C=shape.C, m=shape.m, train=train, impl=impl,
+    step = GraphedHeadStep(params, _cfg(shape, mode, fn), B=shape.B, N=shape.N, C=shape.C, m=shape.m, train=train, impl=impl,
                            use_ppc=use_ppc, variants=variants)
     step.load(0, case["tokens"], case["scores"], case["labels"])
     torch.cuda.synchronize()
@@ -442,15 +443,14 @@ def _make_step(shape, case, mode, impl="v2", train=True, use_ppc=True, variants=
 
 
 ALL_GOLDEN = [(n, "fp32") for n in GOLDEN_CASES if n not in ("tiny_s1", "tiny_s2_linear", "small_s1", "small_s3_matched")] + \
-    [("cub_b8_s1", "bf16"), ("small_s1", "fp32_fma"), ("tiny_s1", "fp32_fma"), ("small_s3_matched", "fp32_fma")]
+    [("cub_b8_s1", "bf16"), ("small_s1", "fp32_fma"), ("tiny_s1", "fp32_fma"), ("small_s3_matched", "fp32_fma"),
+     ("tiny_s2_linear", "fp32_fma")]
 
 
 @pytest.mark.parametrize("name,mode", ALL_GOLDEN)
 def test_five_launch_step_matches_reference_fixture(name, mode):
     shape, case, g, fn = load_golden(name)
-    if fn != "log":
-        pytest.skip("fixture uses the linear activation: covered by the modular path")
-    step, params = _make_step(shape, case, mode)
+    step, params = _make_step(shape, case, mode, fn=fn)
     v2 = _ops().fused_step_supported(shape.B, shape.N, shape.Din, shape.D, shape.K, shape.P, shape.Pg, shape.C, shape.m)
     assert step.impl == ("v2" if v2 else "v1") and (not v2 or step.kernel_launches_per_step <= 12)
     step.run(0)
