@@ -1,18 +1,23 @@
 #!/usr/bin/env python
 """Benchmark of the prototype-head path (BASELINE.json metric: prototype-head images/sec fwd+bwd).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--mode fp32|bf16] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload W] [--mode fp32|bf16] [--impl ours|reference]
 
 A step = one training pass of the head over one per-GPU batch of BASELINE.json configs[1] (CUB / DeiT-Ti shape,
 batch 64 per GPU): selection -> add-on -> similarity/pool -> last layers -> PPC loss -> cross-entropy -> backward
-(token, prototype and add-on gradients) [-> gradient all-reduce when N > 1].  Synthetic inputs, random-init
-parameters (oracle/synth.py).  Prints ONE JSON line (rank 0).
+(token, prototype and add-on gradients) [-> gradient all-reduce when N > 1, recorded inside the CUDA graph and
+overlapped with the add-on backward].  Other workloads (--workload): dogs_b256_eval (configs[2], forward only),
+cars_b64_bf16 (configs[3]), sweep:K=..,D=..,P=..,B=.. (one point of configs[4]).  Synthetic inputs, random-init
+parameters (protopformer_b200/synth.py).  Prints ONE JSON line (rank 0).
 
   value        device-resident throughput: inputs already in HBM, CUDA-graph replays, CUDA events, max over ranks.
                The step rotates over NBUF distinct input batches whose total size exceeds L2 (config.l2).
   e2e          same metric through the public API with HOST (pinned) inputs: H2D copy of every step's batch and a
                D2H read of the loss inside the timed region, double-buffered on a copy stream.
-  roofline     the dominant kernel (tcgen05 similarity), timed alone with CUDA events on its launch stream.
+  roofline     the kernel with the largest share of the step, timed alone with CUDA events on its launch stream,
+               plus roofline.step = the whole step's algorithmic flops against the sustained bf16 peak.
+  forward_only the eval path (no PPC / CE / backward) on the same inputs; dropin_module_path = PPNet.forward +
+               get_PPC_loss + autograd backward launched eagerly from Python.
   cpu_baseline the oracle's ATen-call-faithful port of the reference head (oracle/protohead_oracle.RefStyleHead)
                timed on this box's host cores on a bounded sample (rank 0, N=1 only).
   --impl reference : that CPU port as its own arm (the reference is pure Python over ATen; /root/reference does not
@@ -35,8 +40,88 @@ if ROOT not in sys.path:
 import torch  # noqa: E402
 
 METRIC = "prototype_head_train_images_per_sec"
+METRIC_EVAL = "prototype_head_forward_images_per_sec"
 UNIT = "images/s"
-WORKLOAD = "cub_b64"            # BASELINE.json configs[1]: deit_tiny CUB shape, training step, batch 64 per GPU
+DEFAULT_WORKLOAD = "cub_b64"    # BASELINE.json configs[1]: deit_tiny CUB shape, training step, batch 64 per GPU
+
+
+def parse_workload(name: str, mode_flag: str | None):
+    """-> (canonical name, HeadShape, mode, train).  Named workloads are BASELINE.json's configs[1], [2], [3]; a
+    "sweep:" spec is one point of configs[4] (tokens 49-196, prototypes 1000-8000, dim 192/384, batch 32-1024):
+        sweep:K=81,D=192,P=2000,B=1024[,Pg=2000][,C=200][,mode=bf16][,eval=1]"""
+    from protopformer_b200 import synth
+    if name == "cub_b64":
+        return name, synth.SHAPES["cub_b64"], mode_flag or "fp32", True
+    if name == "dogs_b256_eval":
+        return name, synth.SHAPES["dogs_b256"], mode_flag or "fp32", False
+    if name == "cars_b64_bf16":
+        return name, synth.SHAPES["cars_b64"], "bf16", True
+    if name.startswith("sweep:"):
+        kv = dict(item.split("=") for item in name[6:].split(",") if item)
+        K, D, P, B = int(kv.get("K", 81)), int(kv.get("D", 192)), int(kv.get("P", 2000)), int(kv.get("B", 64))
+        C = int(kv.get("C", P // 10))
+        Pg = int(kv.get("Pg", 10 * C))
+        shape = synth.HeadShape(name, B, 196, D, D, K, P, Pg, C, 0.5, 1.0, 2.0)
+        return name, shape, kv.get("mode", mode_flag or "fp32"), kv.get("eval", "0") in ("0", "", "false")
+    raise SystemExit(f"unknown workload {name!r}: cub_b64 | dogs_b256_eval | cars_b64_bf16 | sweep:K=..,D=..,P=..,B=..")
+
+
+def make_config(workload, shape, mode, train, world, nbuf, in_graph):
+    """The `config` object of the JSON line: built by this one function for BOTH arms so that they are equal."""
+    in_bytes = 4 * shape.B * ((1 + shape.N) * shape.Din + shape.N) + 8 * shape.B
+    step = ("head fwd + PPC + CE + bwd (dtokens, dP, dPg, dWa, dba)" if train
+            else "head forward (selection -> add-on -> similarity/pool -> last layers)")
+    if world > 1 and train:
+        step += " + NCCL grad all-reduce (" + ("in graph, overlapped" if in_graph else "after each replay") + ")"
+    return {"workload": workload, "per_gpu_batch": shape.B, "tokens": shape.K, "dim": shape.D,
+            "prototypes": shape.P, "global_prototypes": shape.Pg, "classes": shape.C, "mode": mode, "step": step,
+            "l2": f"inputs rotate over {nbuf} batches = {nbuf * in_bytes / 1e6:.0f} MB > 126 MB L2; parameters stay "
+                  "L2-resident",
+            "parallelism": f"dp{world}", "cuda_graph": True}
+
+
+def step_flops(shape, train: bool) -> float:
+    """Algorithmic flops of one step: add-on, similarity, last layers; backward = 2x the two GEMMs of
+    each forward GEMM that has a trainable / differentiated operand (the similarity backward is argmin-routed, i.e.
+    sparse: B*(P+Pg) rows of D, not a GEMM)."""
+    s = shape
+    rows = s.B * (s.K + 1)
+    f_addon = 2.0 * rows * s.Din * s.D
+    f_sim = s.B * (2.0 * s.K * s.D * s.P + 2.0 * s.D * s.Pg)
+    f_ll = 2.0 * s.B * s.C * (s.P + s.Pg)
+    fwd = f_addon + f_sim + f_ll
+    if not train:
+        return fwd
+    f_bwd = 2.0 * f_addon + f_ll + 6.0 * s.B * (s.P + s.Pg) * s.D
+    return fwd + f_bwd
+
+
+def bind_to_gpu_numa(index: int):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned staging buffers are
+    allocated (first touch then places them on that node): eight ranks each pushing ~10 MB per step over PCIe should
+    not all read one socket's memory.  Best effort; returns a description for the JSON line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = (bus.decode() if isinstance(bus, bytes) else bus).lower()
+        if len(bus.split(":")[0]) == 8:
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return "numa_node=-1 (single node): not bound"
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & os.sched_getaffinity(0))
+        if not allowed:
+            return f"node {node}: none of its CPUs are in this process's affinity mask"
+        os.sched_setaffinity(0, allowed)
+        return f"bound to NUMA node {node} ({len(allowed)} CPUs) of GPU {index}"
+    except Exception as exc:
+        return f"not bound ({type(exc).__name__}: {exc})"
 
 
 def _peaks():
@@ -46,6 +131,37 @@ def _peaks():
         return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]),
                     tf_sust=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), src="measured")
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+def _measured_traffic(workload, mode, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this
+    workload (profiles/r2_kernel_traffic.json, written by scripts/ncu_traffic.py from the .ncu-rep) or None."""
+    path = os.path.join(ROOT, "profiles", "r2_kernel_traffic.json")
+    try:
+        return json.load(open(path)).get(f"{workload}/{mode}", {}).get(kernel)
+    except Exception:
+        return None
+
+
+def graph_time_us(fn, per_graph: int, replays: int = 10) -> float:
+    """Average device time of one `fn()` call: `per_graph` calls recorded in a CUDA graph (no host launch gaps),
+    replayed `replays` times between two events on the current stream."""
+    for _ in range(3):
+        fn(0)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(per_graph):
+            fn(i)
+    g.replay()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(replays):
+        g.replay()
+    b.record()
+    torch.cuda.synchronize()
+    return 1e3 * a.elapsed_time(b) / (replays * per_graph)
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -105,52 +221,63 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 # CPU arm: the reference head's ATen call sequence on the host cores
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_port_rate(shape, budget_s: float, sample_B: int, iters_min: int = 3):
-    """images/s of RefStyleHead.train_step on a `sample_B`-image slice of the workload, within ~budget_s."""
+def _cpu_step_fn(shape, sample_B, train):
     from oracle import protohead_oracle as O
     from protopformer_b200 import synth
     s = shape.with_batch(sample_B)
     case = synth.make_case(s, seed=1)
     head = O.RefStyleHead(case, s)
-    head.train_step(case["tokens"], case["scores"], case["labels"])          # warm-up
+    if train:
+        return lambda: head.train_step(case["tokens"], case["scores"], case["labels"])
+
+    def fwd():
+        with torch.no_grad():
+            return head.forward(case["tokens"], case["scores"])
+    return fwd
+
+
+def cpu_port_rate(shape, budget_s: float, sample_B: int, iters_min: int = 3, train: bool = True):
+    """images/s of the port's training step (or forward) on a `sample_B`-image slice of the workload, ~budget_s."""
+    fn = _cpu_step_fn(shape, sample_B, train)
+    fn()                                                                      # warm-up
     times = []
     t_end = time.perf_counter() + budget_s
     while len(times) < iters_min or (time.perf_counter() < t_end and len(times) < 50):
         t = time.perf_counter()
-        head.train_step(case["tokens"], case["scores"], case["labels"])
+        fn()
         times.append(time.perf_counter() - t)
     return sample_B / statistics.median(times), len(times)
 
 
 def run_reference_arm(args):
-    from oracle import protohead_oracle as O
-    from protopformer_b200 import synth
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    shape = synth.SHAPES[WORKLOAD]
-    # bounded sample: a per-step slice of the 64-image batch sized so that (K + W) steps end within ~150 s
-    probe, _ = cpu_port_rate(shape, 2.0, 8)
+    workload, shape, mode, train = parse_workload(args.workload, args.mode)
+    # bounded sample: a per-step slice of the per-GPU batch sized so that (K + W) steps end within ~150 s
+    probe, _ = cpu_port_rate(shape, 2.0, min(8, shape.B), train=train)
     per_step = 150.0 / max(1, args.steps + args.warmup)
     sample_B = max(1, min(shape.B, int(probe * per_step)))
-    s = shape.with_batch(sample_B)
-    case = synth.make_case(s, seed=1)
-    head = O.RefStyleHead(case, s)
+    fn = _cpu_step_fn(shape, sample_B, train)
     for _ in range(args.warmup):
-        head.train_step(case["tokens"], case["scores"], case["labels"])
+        fn()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        head.train_step(case["tokens"], case["scores"], case["labels"])
+        fn()
     dt = time.perf_counter() - t0
     value = sample_B * args.steps / dt
-    sample = f"{sample_B} of {shape.B} images per step ({WORKLOAD}), fp32, torch {torch.__version__} CPU"
+    sample = (f"{sample_B} of {shape.B} images per step ({workload}), fp32, torch {torch.__version__} CPU, ONE process "
+              f"on rank 0's host cores" + (f" (the GPU arm at n_gpus={world} processes {world}x{shape.B} images per step: "
+                                           "the driver's ratio is N GPUs vs this one CPU process)" if world > 1 else ""))
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": METRIC if train else METRIC_EVAL, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "per_gpu_batch": shape.B, "sample": sample},
+        "config": make_config(workload, shape, mode, train, world, args.nbuf, not args.eager_allreduce),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -167,7 +294,7 @@ def measure_next_rows(shape, params, dev, peaks):
     from protopformer_b200.optim import FusedHeadAdamW
     out = {}
     with torch.no_grad():
-        L, H, T, B = 11, 3, shape.N + 1, shape.B
+        L, H, T, B = 11, 3, shape.N + 1, min(shape.B, 64)
         g = torch.Generator(device=dev).manual_seed(0)
         attn = [torch.softmax(2.0 * torch.randn(B, H, T, T, device=dev, generator=g), dim=-1) for _ in range(L)]
         for _ in range(3):
@@ -191,22 +318,7 @@ def measure_next_rows(shape, params, dev, peaks):
         gs = [torch.randn_like(p) * 0.01 for p in ps]
         opt = FusedHeadAdamW([{"params": ps[:2], "lr": 3e-3, "weight_decay": 1e-3},
                               {"params": ps[2:], "lr": 3e-3, "weight_decay": 0.05}], grads=gs)
-        for _ in range(3):
-            opt.step()
-        torch.cuda.synchronize()
-        gr = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gr):
-            for _ in range(20):
-                opt.step()
-        gr.replay()
-        torch.cuda.synchronize()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for _ in range(10):
-            gr.replay()
-        a1.record()
-        torch.cuda.synchronize()
-        us = 1e3 * a0.elapsed_time(a1) / 200
+        us = graph_time_us(lambda i: opt.step(), 20)
         nbytes = 28.0 * sum(p.numel() for p in ps)
         out["adamw"] = {"kernel": "adamw_kernel (4 tensors, one launch)", "bound": "hbm",
                         "achieved": nbytes / us / 1e3, "peak": peaks["hbm"], "unit": "GB/s",
@@ -214,6 +326,75 @@ def measure_next_rows(shape, params, dev, peaks):
                         "algorithmic_bytes_per_call": nbytes,
                         "note": "22.5 MB working set is L2-resident between replays: an upper bound on the HBM rate"}
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the drop-in module path: PPNet.forward + get_PPC_loss + autograd backward, eager (what a user of the reference's
+# training loop gets without adopting the graphed step), tools/engine_proto.py:49-76
+# ---------------------------------------------------------------------------------------------------------------
+class _TokenFeed(torch.nn.Module):
+    """Stands in for the backbone (out of this path's scope): hands the preloaded tokens / CLS-attention scores to the
+    head through the two backbone methods PPNet calls (protopformer.py:149, 155)."""
+
+    def __init__(self, Din, N):
+        super().__init__()
+        self.proj = torch.nn.Linear(Din, Din)           # PPNet reads the last nn.Linear's out_features
+        self.patch_embed = type("PE", (), {"num_patches": N})()
+        self.cur = None
+
+    def __repr__(self):
+        return "MYVISIONTRANSFORMER(token feed)"
+
+    def forward_feature_patch_embed_all(self, x):
+        return None, None
+
+    def forward_feature_mask_train_direct(self, cls_embed, x_embed, mask, reserve_layer_nums):
+        tokens, scores = self.cur
+        return tokens, (scores, None)
+
+
+def measure_dropin(shape, mode, params, step, nbuf, steps):
+    from protopformer_b200.head import PPNet
+    dev = params["P"].device
+    net = PPNet(_TokenFeed(shape.Din, shape.N), 224, (shape.P, shape.D, 1, 1), None, shape.C, reserve_layers=[11],
+                reserve_token_nums=[shape.K], use_global=True, use_ppc_loss=True, ppc_cov_thresh=shape.ppc_cov_thresh,
+                ppc_mean_thresh=shape.ppc_mean_thresh, global_coe=shape.global_coe,
+                global_proto_per_class=shape.Pg // shape.C, add_on_layers_type="regular", precision=mode).to(dev)
+    with torch.no_grad():
+        net.add_on_layers[0].weight.copy_(params["Wa"].reshape(net.add_on_layers[0].weight.shape))
+        net.add_on_layers[0].bias.copy_(params["ba"])
+        net.prototype_vectors.copy_(params["P"].reshape(net.prototype_vectors.shape))
+        net.prototype_vectors_global.copy_(params["Pg"].reshape(net.prototype_vectors_global.shape))
+        net.last_layer.weight.copy_(params["Wl"])
+        net.last_layer_global.weight.copy_(params["Wg"])
+    net.train()
+    feed = net.features
+    ce = torch.nn.CrossEntropyLoss()
+
+    def one(i):
+        tok = step.tokens[i % nbuf].detach().requires_grad_(True)
+        feed.cur = (tok, step.scores[i % nbuf])
+        for p in net.parameters():
+            p.grad = None
+        logits, aux = net(None)
+        cov, mean = net.get_PPC_loss(aux[2], aux[3], aux[4], step.labels[i % nbuf])
+        loss = ce(logits, step.labels[i % nbuf]) + 0.1 * cov + 0.5 * mean
+        loss.backward()
+        return loss
+
+    for i in range(5):
+        one(i)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        loss = one(i)
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    return {"value": shape.B / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "loss": float(loss.item()),
+            "path": "PPNet.forward + get_PPC_loss + CrossEntropyLoss + autograd backward, eager launches from Python "
+                    "(device-resident inputs)"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -225,13 +406,15 @@ def main():
     ap.add_argument("--steps", type=int, default=2000)
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="fp32", choices=["fp32", "bf16"],
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD,
+                    help="cub_b64 (default, BASELINE configs[1]) | dogs_b256_eval | cars_b64_bf16 | sweep:K=..,D=..,P=..,B=..")
+    ap.add_argument("--mode", default=None, choices=["fp32", "bf16"],
                     help="similarity precision: fp32 = 3-term bf16 split (1e-4 parity), bf16 = single pass")
     ap.add_argument("--nbuf", type=int, default=16, help="distinct input batches the step rotates over")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--graph-allreduce", action="store_true",
-                    help="N>1 (experimental, unverified): record the NCCL gradient all-reduce inside the CUDA graph "
-                         "instead of issuing it after each replay")
+    ap.add_argument("--no-extras", action="store_true", help="headline numbers only (no roofline / next rows / drop-in legs)")
+    ap.add_argument("--eager-allreduce", action="store_true",
+                    help="N>1: issue the NCCL gradient all-reduce after each graph replay instead of inside the graph")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -249,20 +432,23 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device: the prototype head has no CPU path"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa(local) if world > 1 else "single process: not bound"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
 
-    shape = synth.SHAPES[WORKLOAD]
+    workload, shape, mode, train = parse_workload(args.workload, args.mode)
+    in_graph = world > 1 and train and not args.eager_allreduce
     case = synth.make_case(shape, seed=1)
     params = {k: case[k].to(dev) for k in ("Wa", "ba", "P", "Pg", "Wl", "Wg")}
-    for k in ("Wa", "ba", "P", "Pg"):
-        params[k].requires_grad_(True)
-    cfg = ops.HeadConfig(K=shape.K, global_coe=shape.global_coe, mode=args.mode,
+    if train:
+        for k in ("Wa", "ba", "P", "Pg"):
+            params[k].requires_grad_(True)
+    cfg = ops.HeadConfig(K=shape.K, global_coe=shape.global_coe, mode=mode,
                          ppc_cov_thresh=shape.ppc_cov_thresh, ppc_mean_thresh=shape.ppc_mean_thresh)
     nbuf = args.nbuf
-    step = GraphedHeadStep(params, cfg, B=shape.B, N=shape.N, C=shape.C, m=shape.m, n_slots=nbuf,
-                           allreduce_in_graph=(world > 1 and args.graph_allreduce))
+    step = GraphedHeadStep(params, cfg, B=shape.B, N=shape.N, C=shape.C, m=shape.m, n_slots=nbuf, train=train,
+                           allreduce_in_graph=in_graph)
     # distinct synthetic batches per slot and per rank (weak scaling: fixed per-GPU batch)
     host = []
     for i in range(nbuf):
@@ -272,27 +458,48 @@ def main():
             perm = torch.randperm(shape.B, generator=torch.Generator().manual_seed(i))
             c = dict(tokens=b["tokens"][perm].contiguous(), scores=b["scores"][perm].contiguous(),
                      labels=b["labels"][perm].contiguous())
+        if i == 0:
+            first = {k: c[k].clone() for k in ("tokens", "scores", "labels")}
         host.append({k: c[k].pin_memory() for k in ("tokens", "scores", "labels")})
         step.load(i, host[i]["tokens"], host[i]["scores"], host[i]["labels"])
     torch.cuda.synchronize()
     step.capture()
     in_bytes = sum(host[0][k].numel() * host[0][k].element_size() for k in host[0])
-    l2_note = f"inputs rotate over {nbuf} batches = {nbuf * in_bytes / 1e6:.0f} MB > 126 MB L2; parameters stay L2-resident"
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def one(i):
+        step.run(i % nbuf)
+        if world > 1 and train:
+            step.allreduce_grads()            # no-op when the all-reduce is part of the graph
+
+    # ---- the result of slot 0 against the CPU oracle, once (rank 0 compares; every rank runs the step) -----------
+    one(0)
+    torch.cuda.synchronize()
+    oracle_check = None
+    if rank == 0 and not args.no_cpu and shape.B * shape.P * shape.K <= 64 * 2000 * 121:
+        from oracle import protohead_oracle as O               # the checker, never the thing measured
+        ocase = dict(case)
+        ocase.update(first)
+        tol = 1e-4 if mode == "fp32" else 5e-4
+        if train and world == 1:
+            ref = O.head_train_step(ocase, shape)
+            got, want = float(step.loss[0].item()), float(ref["loss"].item())
+        else:                                  # forward-only workloads (and N>1, whose graph averages gradients only)
+            ref = O.head_forward(ocase, shape.K, shape.global_coe)
+            got, want = float(step.logits[0].abs().sum().item()), float(ref["logits"].abs().sum().item())
+        rel = abs(got - want) / abs(want)
+        oracle_check = {"what": "loss of the first batch" if (train and world == 1) else "sum |logits| of the first batch",
+                        "gpu": got, "oracle": want, "rel_err": rel, "tol": tol}
+        assert rel <= tol, f"bench result differs from the CPU oracle: {oracle_check}"
+
     sampler = ClockSampler(local)
     sampler.start()
 
     # ---- device-resident timing ------------------------------------------------------------------------------
-    def one(i):
-        step.run(i % nbuf)
-        if world > 1:
-            step.allreduce_grads()
-
     for i in range(args.warmup):
         one(i)
     barrier()
@@ -314,7 +521,9 @@ def main():
 
     # ---- end to end through the public API with host buffers ---------------------------------------------------
     copy_stream = torch.cuda.Stream()
-    loss_host = torch.zeros(1).pin_memory()
+    # the result a caller reads back every step: the loss in training, the logits in inference
+    result_of = (lambda s: step.loss[s].reshape(1)) if train else (lambda s: step.logits[s])
+    out_host = torch.zeros(1 if train else shape.B * shape.C).reshape(-1 if train else shape.B, *(() if train else (shape.C,))).pin_memory()
     ready = [torch.cuda.Event() for _ in range(2)]
     done = [torch.cuda.Event() for _ in range(2)]
 
@@ -329,12 +538,12 @@ def main():
                 ready[s].record(copy_stream)
             cur.wait_event(ready[s])
             step.run(s)
-            if world > 1:
+            if world > 1 and train:
                 step.allreduce_grads()
-            loss_host.copy_(step.loss[s].reshape(1), non_blocking=True)
+            out_host.copy_(result_of(s), non_blocking=True)
             done[s].record(cur)
         torch.cuda.synchronize()
-        return float(loss_host.item())
+        return float(out_host.reshape(-1)[0].item())
 
     for s in range(2):
         done[s].record(torch.cuda.current_stream())
@@ -352,115 +561,75 @@ def main():
         ms_e2e = float(t.item())
     e2e_value = world * shape.B * args.steps / (ms_e2e * 1e-3)
     sampler.stop()
+    # restore the rotation the device-resident legs below read
+    for i in range(2):
+        step.load(i, host[i]["tokens"], host[i]["scores"], host[i]["labels"])
+    torch.cuda.synchronize()
 
-    # ---- roofline of the dominant kernel (tcgen05 similarity), timed alone on its stream ---------------------------
     peaks = _peaks()
-    roof = None
-    dominant = None
-    if rank == 0:
-        with torch.no_grad():
-            tfs = []
-            for i in range(nbuf):
-                idx = ops.select_topk(step.scores[i], shape.K)
-                tfs.append(ops.addon(step.tokens[i].detach(), idx, params["Wa"].detach(), params["ba"].detach(), True))
-            pl = ops.prepare_prototypes(params["P"].detach(), True)
-            pg = ops.prepare_prototypes(params["Pg"].detach(), True)
-            for i in range(20):
-                ops._similarity_raw(cfg, tfs[i % nbuf], pl, pg)
-            torch.cuda.synchronize()
-            reps = 200
-            k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            k0.record()
-            for i in range(reps):
-                ops._similarity_raw(cfg, tfs[i % nbuf], pl, pg)
-            k1.record()
-            torch.cuda.synchronize()
-            # launches are back to back on one stream (Python launch overhead < kernel time is NOT guaranteed for a
-            # ~10 us kernel), so also time a CUDA-graph of the same launches and keep the smaller per-launch time
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                for i in range(nbuf):
-                    ops._similarity_raw(cfg, tfs[i], pl, pg)
-            g.replay()
-            torch.cuda.synchronize()
-            g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            g0.record()
-            for _ in range(10):
-                g.replay()
-            g1.record()
-            torch.cuda.synchronize()
-            us_eager = 1e3 * k0.elapsed_time(k1) / reps
-            us_graph = 1e3 * g0.elapsed_time(g1) / (10 * nbuf)
-            us = min(us_eager, us_graph)
-        flops = shape.B * (2.0 * shape.K * shape.D * shape.P + 2.0 * shape.D * shape.Pg)   # F_sim, SURVEY.md 8(d)
-        achieved = flops / (us * 1e-6) / 1e12
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at this shape from the committed ncu --set full
-        # capture (profiles/r1_ncu_full_step_kernels.txt, cold caches); its operands total 7.1 MB, i.e. no re-reads
-        traffic = 7.22e6 if (WORKLOAD == "cub_b64" and args.mode == "fp32") else None
-        roof = {"kernel": "similarity_tc2_kernel (tcgen05 + TMA, resident prototype tile, mode %s)" % args.mode,
-                "bound": "tensor", "achieved": achieved, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["tf_burst"], "traffic": traffic, "us_per_launch": us,
-                "algorithmic_flops_per_launch": flops,
-                "peak_source": peaks["src"] + " bf16 burst (kernel timed alone)",
-                "note": ("fp32 mode issues 3 bf16 MMA passes per algorithmic flop: tensor-pipe work is 3x the algorithmic "
-                         "figure" if args.mode == "fp32" else "")}
-        # the kernel with the largest share of the step (profiles/r1_launches_final_warm.txt): the argmin-routed sparse
-        # backward, a byte/latency-bound gather.  Timed alone the same way; roofline = HBM with its compulsory bytes.
-        try:
-            with torch.no_grad():
-                f = step.fused
-                B_, K_, D_, P_, Pg_ = shape.B, shape.K, shape.D, shape.P, shape.Pg
-                args_b = (f.g_l, f.g_g, f.argmin, f.Zs, f.Zc, params["P"].detach(), params["Pg"].detach(), B_, K_, D_, P_,
-                          Pg_, f.ws, 2, None, None, f.dZs, f.dZc, torch.empty_like(params["P"]),
-                          torch.empty_like(params["Pg"]))
-                for _ in range(3):
-                    _lib.call("pph_similarity_bwd", *args_b)
-                torch.cuda.synchronize()
-                gb = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gb):
-                    for _ in range(20):
-                        _lib.call("pph_similarity_bwd", *args_b)
-                gb.replay()
-                torch.cuda.synchronize()
-                b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                b0.record()
-                for _ in range(10):
-                    gb.replay()
-                b1.record()
-                torch.cuda.synchronize()
-                us_b = 1e3 * b0.elapsed_time(b1) / 200
-            # compulsory bytes: Zs, Zc, P, Pg, g_l, g_g, argmin, bins read once; dZs, dZc, dP, dPg written once
-            byts = 4.0 * (2 * B_ * K_ * D_ + 2 * B_ * D_ + 2 * (P_ + Pg_) * D_ + B_ * (P_ + Pg_) + 2 * B_ * P_)
-            ach = byts / (us_b * 1e-6) / 1e9
-            dominant = {"kernel": "sim_grads_kernel (argmin-routed sparse backward: dP, dPg, dZs, dZc)", "bound": "hbm",
-                        "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
-                        "us_per_launch": us_b, "algorithmic_bytes_per_launch": byts,
-                        "note": "gathers 2*B*P rows of D floats from L2-resident operands (197 MB of L2 traffic): "
-                                "latency/L2-bound, far from the HBM roofline by construction"}
-        except Exception as exc:      # the headline numbers must not depend on this auxiliary measurement
-            dominant = {"error": str(exc)}
+    extras = rank == 0 and not args.no_extras
+    us_step = 1e3 * ms / args.steps
 
-    # ---- rows either side of the head: rollout -> score (HBM bound), fused AdamW (HBM bound) --------
-    next_rows = None
-    if rank == 0:
+    # ---- forward-only rate (eval path, tools/engine_proto.py:156-162 -> protopformer.py:292-301) ---------------------
+    forward_only = None
+    if extras and train:
+        try:
+            ev_params = {k: v.detach() for k, v in params.items()}
+            fstep = GraphedHeadStep(ev_params, cfg, B=shape.B, N=shape.N, C=shape.C, m=shape.m, n_slots=nbuf, train=False)
+            for i in range(nbuf):
+                fstep.load(i, step.tokens[i].detach(), step.scores[i], step.labels[i])
+            fstep.capture()
+            for i in range(20):
+                fstep.run(i % nbuf)
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            nf = max(200, args.steps // 2)
+            f0.record()
+            for i in range(nf):
+                fstep.run(i % nbuf)
+            f1.record()
+            torch.cuda.synchronize()
+            fms = f0.elapsed_time(f1) / nf
+            ff = step_flops(shape, False)
+            forward_only = {"metric": METRIC_EVAL, "value": shape.B / (fms * 1e-3), "unit": UNIT, "ms_per_step": fms,
+                            "gpu_launches_per_step": fstep.kernel_launches_per_step,
+                            "tensor_frac_sustained": ff / (fms * 1e-3) / 1e12 / peaks["tf_sust"]}
+            del fstep
+        except Exception as exc:
+            forward_only = {"error": str(exc)}
+
+    # ---- roofline: the kernel with the largest share of the step + the step itself ---------------------------------
+    roof = None
+    if extras:
+        roof = measure_roofline(step, shape, cfg, mode, params, train, peaks, us_step, workload, nbuf)
+
+    next_rows = dropin = None
+    if extras:
         try:
             next_rows = measure_next_rows(shape, params, dev, peaks)
         except Exception as exc:      # auxiliary: the headline line must print regardless
             next_rows = {"error": str(exc)}
+        if train:
+            try:
+                dropin = measure_dropin(shape, mode, params, step, nbuf, 200)
+            except Exception as exc:
+                dropin = {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---- CPU baseline (rank 0, N = 1 only) ---------------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        rate, n = cpu_port_rate(shape, 12.0, shape.B)
+        sb = min(shape.B, 64)
+        rate, n = cpu_port_rate(shape, 12.0, sb, train=train)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n} training steps of the full {shape.B}-image batch ({WORKLOAD}), fp32, torch CPU"}
+               "sample": f"{n} {'training steps' if train else 'forward passes'} of a {sb}-image batch ({workload}), "
+                         "fp32, torch CPU"}
         try:                              # per-core figure: same port on ONE thread, small sample
             torch.set_num_threads(1)
-            rate1, n1 = cpu_port_rate(shape, 4.0, 8, iters_min=2)
+            rate1, n1 = cpu_port_rate(shape, 4.0, 8, iters_min=2, train=train)
             cpu["value_1_core"] = rate1
-            cpu["sample_1_core"] = f"{n1} training steps of an 8-image slice, 1 thread"
+            cpu["sample_1_core"] = f"{n1} steps of an 8-image slice, 1 thread"
         except Exception as exc:
             cpu["value_1_core"] = None
             cpu["sample_1_core"] = f"failed: {exc}"
@@ -469,23 +638,22 @@ def main():
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC if train else METRIC_EVAL, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16x3 split, fp32 accumulate (fp32-grade)" if args.mode == "fp32" else "bf16, fp32 accumulate",
+            "dtype": "bf16x3 split, fp32 accumulate (fp32-grade)" if mode == "fp32" else "bf16, fp32 accumulate",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "per_gpu_batch": shape.B, "tokens": shape.K, "dim": shape.D,
-                       "prototypes": shape.P, "global_prototypes": shape.Pg, "classes": shape.C, "mode": args.mode,
-                       "step": "head fwd + PPC + CE + bwd (dtokens, dP, dPg, dWa, dba)"
-                               + ((" + NCCL grad all-reduce (" + ("in graph" if args.graph_allreduce else "after each replay") + ")")
-                                  if world > 1 else ""),
-                       "l2": l2_note, "parallelism": f"dp{world}", "cuda_graph": True},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": 4,
-                    "ms_per_step": ms_e2e / args.steps, "last_loss": last_loss},
+            "config": make_config(workload, shape, mode, train, world, nbuf, not args.eager_allreduce),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_host.numel() * 4,
+                    "ms_per_step": ms_e2e / args.steps, "last_loss" if train else "last_logit": last_loss, "host_buffers": numa},
             "gpu_launches": step.kernel_launches_per_step * args.steps,
             "gpu_launches_per_step": step.kernel_launches_per_step,
+            "step_impl": step.impl,
             "clocks": sampler.summary(),
             "roofline": roof,
-            "largest_share_kernel": dominant if rank == 0 else None,
+            "oracle_check": oracle_check,
+            "forward_only": forward_only,
+            "dropin_module_path": dropin,
             "next_rows": next_rows,
             "cpu_baseline": cpu,
         }
@@ -493,6 +661,68 @@ def main():
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def measure_roofline(step, shape, cfg, mode, params, train, peaks, us_step, workload, nbuf):
+    """`roofline` of the JSON line: the kernel with the largest share of the step (timed alone, CUDA graph of back-to-back
+    launches on the current stream, events around the replays), the tensor-core similarity kernel the same way, and the
+    step-level fraction (algorithmic flops of the whole step / step time / sustained bf16 peak)."""
+    from protopformer_b200 import _lib, ops
+    f = step.fused
+    B, K, D, P, Pg = shape.B, shape.K, shape.D, shape.P, shape.Pg
+    cands = {}
+    with torch.no_grad():
+        try:
+            tfs = []
+            for i in range(min(nbuf, 4)):
+                idx = ops.select_topk(step.scores[i], K)
+                tfs.append(ops.addon(step.tokens[i].detach(), idx, params["Wa"].detach(), params["ba"].detach(), True))
+            pl = ops.prepare_prototypes(params["P"].detach(), True)
+            pg = ops.prepare_prototypes(params["Pg"].detach(), True)
+            us = graph_time_us(lambda i: ops._similarity_raw(cfg, tfs[i % len(tfs)], pl, pg), 16)
+            flops = B * (2.0 * K * D * P + 2.0 * D * Pg)                   # F_sim, SURVEY.md 8(d)
+            ach = flops / (us * 1e-6) / 1e12
+            cands["similarity"] = {
+                "kernel": "similarity_tc2_kernel (tcgen05 + TMA, resident prototype tile, mode %s)" % mode,
+                "bound": "tensor", "achieved": ach, "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                "frac": ach / peaks["tf_burst"], "traffic": _measured_traffic(workload, mode, "similarity_tc2_kernel"),
+                "us_per_launch": us, "algorithmic_flops_per_launch": flops,
+                "note": ("fp32 mode issues 3 bf16 MMA passes per algorithmic flop: tensor-pipe work is 3x the "
+                         "algorithmic figure" if mode == "fp32" else "")}
+            del tfs
+        except Exception as exc:
+            cands["similarity"] = {"error": str(exc), "us_per_launch": 0.0}
+        if train and step.impl == "v2":
+            try:
+                gP, gPg = torch.empty_like(params["P"]), torch.empty_like(params["Pg"])
+                us = graph_time_us(lambda i: _lib.call(
+                    "pph_similarity_bwd_fused", 3, f.g_l, f.g_g, f.argmin, f.Zs, f.Zc, params["P"].detach(),
+                    params["Pg"].detach(), B, K, D, P, Pg, shape.m, f.ws_gather, f.ws_bins, None, None, 1, f.dZs, f.dZc,
+                    gP, gPg), 16)
+                # compulsory bytes: Zs, Zc, P, Pg, g_l, g_g, argmin, bins read once; dZs, dZc, dP, dPg written once
+                byts = 4.0 * (2 * B * K * D + 2 * B * D + 2 * (P + Pg) * D + B * (P + Pg) + 2 * B * P)
+                ach = byts / (us * 1e-6) / 1e9
+                cands["sim_grads"] = {
+                    "kernel": "sim_grads_kernel (argmin-routed sparse backward: dP, dPg, dZs as dpre, dZc)", "bound": "hbm",
+                    "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"],
+                    "traffic": _measured_traffic(workload, mode, "sim_grads_kernel"), "us_per_launch": us,
+                    "algorithmic_bytes_per_launch": byts,
+                    "note": "gathers 2*B*P rows of D floats from L2-resident operands: L2-latency bound, far from the HBM "
+                            "roofline by construction (its working set never leaves L2 at this shape)"}
+            except Exception as exc:
+                cands["sim_grads"] = {"error": str(exc), "us_per_launch": 0.0}
+    key = max(cands, key=lambda k: cands[k].get("us_per_launch", 0.0))
+    roof = dict(cands[key])
+    roof["share_of_step"] = roof.get("us_per_launch", 0.0) / us_step
+    roof["peak_source"] = peaks["src"] + (" bf16 burst" if roof.get("bound") == "tensor" else " HBM copy") + \
+        " (kernel timed alone)"
+    fl = step_flops(shape, train)
+    tf = fl / (us_step * 1e-6) / 1e12
+    roof["step"] = {"bound": "tensor", "algorithmic_flops_per_step": fl, "achieved": tf, "unit": "TFLOP/s",
+                    "peak": peaks["tf_sust"], "frac": tf / peaks["tf_sust"],
+                    "peak_source": peaks["src"] + " bf16 sustained (step timed in a long loop)", "us_per_step": us_step}
+    roof["other_kernels"] = {k: v for k, v in cands.items() if k != key}
+    return roof
 
 
 if __name__ == "__main__":

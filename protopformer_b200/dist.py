@@ -43,17 +43,39 @@ class FlatGradReducer:
             if p.grad is None or p.grad.data_ptr() != v.data_ptr():
                 p.grad = v
 
-    def allreduce(self, async_op: bool = False):
-        """Average the flat gradient over the process group (no-op for a single process)."""
+    def check_attached(self):
+        """Raises if some parameter's .grad no longer aliases the flat buffer (e.g. after an optimizer's
+        zero_grad(set_to_none=True)): reducing the flat buffer would then average stale values while autograd
+        accumulates somewhere else."""
+        for (n, p), v in zip(self.named, self.views):
+            if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                raise RuntimeError(f"gradient of {n} is detached from the flat all-reduce buffer: call "
+                                   "FlatGradReducer.zero() (not optimizer.zero_grad(set_to_none=True)) between steps")
+
+    def segment(self, names):
+        """[lo, hi) of the flat buffer covered by the (contiguous, in construction order) parameters `names`."""
+        off, lo, hi = 0, None, None
+        for n, p in self.named:
+            if n in names:
+                lo = off if lo is None else lo
+                hi = off + p.numel()
+            off += p.numel()
+        return lo, hi
+
+    def allreduce(self, async_op: bool = False, lo: int = 0, hi: int | None = None, check: bool = True):
+        """Average flat[lo:hi] (default: all of it) over the process group (no-op for a single process)."""
         if not (dist.is_available() and dist.is_initialized()):
             return None
         world = dist.get_world_size(self.group)
         if world == 1:
             return None
+        if check:
+            self.check_attached()
+        buf = self.flat if (lo == 0 and hi is None) else self.flat[lo:hi]
         if dist.get_backend(self.group) == "nccl":
-            return dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=self.group, async_op=async_op)
-        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group, async_op=False)
-        self.flat.div_(world)
+            return dist.all_reduce(buf, op=dist.ReduceOp.AVG, group=self.group, async_op=async_op)
+        work = dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=self.group, async_op=False)
+        buf.div_(world)
         return work
 
 

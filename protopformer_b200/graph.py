@@ -68,11 +68,27 @@ class GraphedHeadStep:
     # --------------------------------------------------------------------------------------------------------
     def _step_fused(self, slot: int):
         p, f = self.p, self.fused
+        works = []
+        hook = None
+        if self.train and self.allreduce_in_graph and self.impl == "v2":
+            # overlapped exchange: the prototype gradients (95 % of the flat buffer) are final before the add-on backward
+            # starts, so their all-reduce is issued there (on the step's side branch) and runs under those kernels on
+            # NCCL's stream; the add-on part follows the weight-gradient kernel.  Both join the step's stream below.
+            seg = {"protos": self.reducer.segment(("P", "Pg")), "addon": self.reducer.segment(("Wa", "ba"))}
+
+            def hook(which):
+                lo, hi = seg[which]
+                w = self.reducer.allreduce(async_op=True, lo=lo, hi=hi, check=False)
+                if w is not None:
+                    works.append(w)
         with torch.no_grad():
+            kw = dict(reduce_hook=hook) if hook is not None else {}
             f.step(self.tokens[slot], self.scores[slot], self.labels[slot], p["Wa"], p["ba"], p["P"], p["Pg"],
-                   p["Wl"], p["Wg"], self.grads if self.train else None)
-        if self.train and self.allreduce_in_graph:
-            self.reducer.allreduce()
+                   p["Wl"], p["Wg"], self.grads if self.train else None, **kw)
+        for w in works:
+            w.wait()                      # the capturing / current stream waits for NCCL's stream
+        if self.train and self.allreduce_in_graph and hook is None:
+            self.reducer.allreduce(check=False)
         self.loss[slot] = f.losses[0]
         self.logits[slot] = f.logits
         self.ppc[slot] = (f.losses[2], f.losses[3])

@@ -723,11 +723,15 @@ class FusedHeadStep:
                 self.dtokens.zero_()
 
 
-    def step(self, tokens, scores, labels, Wa, ba, P, Pg, Wl, Wg, grads=None, upstream: float = 1.0):
+    def step(self, tokens, scores, labels, Wa, ba, P, Pg, Wl, Wg, grads=None, upstream: float = 1.0, reduce_hook=None):
+        """reduce_hook(which): called once with "protos" when grads["P"], grads["Pg"] are final (on the stream that
+        produced them) and once with "addon" after grads["Wa"], grads["ba"]: the data-parallel caller issues its
+        asynchronous all-reduces there so that the first one overlaps the add-on backward."""
         B, N, Din, D, Pn, Pgn, C, m, H = self.dims
         cfg, K = self.cfg, self.cfg.K
         c = _lib.call
         main, side, side2, ev = torch.cuda.current_stream(), self.side, self.side2, self.ev
+        hook = reduce_hook or (lambda which: None)
         if self.variants["prep"] == "tc":
             # selection -> single-shot tcgen05 add-on || operand split of both prototype tensors (side branch)
             ev[3].record(main)
@@ -813,10 +817,12 @@ class FusedHeadStep:
             with torch.cuda.stream(side):           # after the PPC branch and this launch: the PPC prototype rows onto dP
                 side.wait_event(ev[2])
                 gather(4, None, self.dP_img)
+                hook("protos")
                 ev[1].record(side)
             dpre_add = self.dZs_ppc
         elif vr["bwd"] == "gather":
             gather(3, self.dZs_ppc if ppc else None, self.dP_img if ppc else None)
+            hook("protos")
             ev[1].record(main)          # (joined at the end like the staged prototype branch)
         else:
             bwd = lambda parts: c("pph_similarity_bwd2", parts, self.g_l, self.g_g, self.pairT, self.ws_bins, self.Zs,  # noqa: E731
@@ -833,6 +839,9 @@ class FusedHeadStep:
                 ev[2].record(side2)
             bwd(1)                          # token rows
             main.wait_event(ev[2])
+            if reduce_hook is not None:     # dP (side) and dPg (side2) are both needed: join first
+                main.wait_event(ev[1])
+                hook("protos")
         if self.stop_after == 4:
             main.wait_event(ev[1])
             return self.losses
@@ -848,5 +857,6 @@ class FusedHeadStep:
         else:
             c("pph_addon_bwd2", 3, tokens, self.idx32, Wa, self.dZs, self.dZc, B, N, Din, D, K,
               self.ws_addon, grads["Wa"], grads["ba"], self.dtokens)
+        hook("addon")
         main.wait_event(ev[1])
         return self.losses

@@ -43,12 +43,29 @@ case $stage in
   all)
     timeout 1500 python -m pytest tests -q -m gpu --tb=short > gpurun_out/t_all.log 2>&1; echo "== all: rc=$? $(tail -1 gpurun_out/t_all.log)" ;;
   bench)
-    timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json ;;
+    timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 6000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err ;;
+  benchw)     # the other BASELINE configs through --workload
+    for w in dogs_b256_eval cars_b64_bf16 "sweep:K=81,D=192,P=2000,B=1024" "sweep:K=196,D=384,P=8000,B=32,eval=1"; do
+      n=$(echo $w | tr ':=,' '___')
+      timeout 600 python bench.py --workload "$w" --steps 300 --warmup 20 > gpurun_out/bench_$n.json 2> gpurun_out/bench_$n.err
+      echo "== $w rc=$?"; tail -c 2500 gpurun_out/bench_$n.json; tail -3 gpurun_out/bench_$n.err
+    done ;;
+  bench2|bench4|bench8)   # N ranks on one box (gpurun --gpus N): in-graph overlapped all-reduce, then the eager one
+    n=${stage#bench}
+    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 \
+        bench.py --gpus $n --steps 1000 --warmup 50 --no-extras > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err
+    echo "== in-graph rc=$?"; tail -c 2500 gpurun_out/bench_n$n.json; tail -5 gpurun_out/bench_n$n.err
+    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 \
+        bench.py --gpus $n --steps 1000 --warmup 50 --no-extras --eager-allreduce > gpurun_out/bench_n${n}_eager.json 2> gpurun_out/bench_n${n}_eager.err
+    echo "== eager rc=$?"; tail -c 1200 gpurun_out/bench_n${n}_eager.json; tail -3 gpurun_out/bench_n${n}_eager.err ;;
+  ddp2)       # in-graph all-reduce result check at N=2
+    timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 \
+        scripts/ddp_check.py > gpurun_out/ddp2.log 2>&1; echo "== ddp2 rc=$?"; tail -8 gpurun_out/ddp2.log ;;
   smoke)
     timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3 ;;
   launches)
     timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --cache-control none -s 200 -c 60 --csv \
-        --log-file gpurun_out/launches.csv python bench.py --steps 20 --warmup 5 --no-cpu --no-aux > gpurun_out/launches.log 2>&1
+        --log-file gpurun_out/launches.csv python bench.py --steps 20 --warmup 5 --no-cpu --no-extras > gpurun_out/launches.log 2>&1
     echo "== launches rc=$?" ;;
 esac
 done
