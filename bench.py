@@ -66,13 +66,14 @@ def parse_workload(name: str, mode_flag: str | None):
     raise SystemExit(f"unknown workload {name!r}: cub_b64 | dogs_b256_eval | cars_b64_bf16 | sweep:K=..,D=..,P=..,B=..")
 
 
-def make_config(workload, shape, mode, train, world, nbuf, in_graph):
+def make_config(workload, shape, mode, train, world, nbuf, in_graph, exchange="peer"):
     """The `config` object of the JSON line: built by this one function for BOTH arms so that they are equal."""
     in_bytes = 4 * shape.B * ((1 + shape.N) * shape.Din + shape.N) + 8 * shape.B
     step = ("head fwd + PPC + CE + bwd (dtokens, dP, dPg, dWa, dba)" if train
             else "head forward (selection -> add-on -> similarity/pool -> last layers)")
     if world > 1 and train:
-        step += " + NCCL grad all-reduce (" + ("in graph, overlapped" if in_graph else "after each replay") + ")"
+        how = "NCCL grad all-reduce" if exchange == "nccl" else "grad all-reduce kernel over NVLink peer memory"
+        step += f" + {how} (" + ("in graph, overlapped with the add-on backward" if in_graph else "after each replay") + ")"
     return {"workload": workload, "per_gpu_batch": shape.B, "tokens": shape.K, "dim": shape.D,
             "prototypes": shape.P, "global_prototypes": shape.Pg, "classes": shape.C, "mode": mode, "step": step,
             "l2": f"inputs rotate over {nbuf} batches = {nbuf * in_bytes / 1e6:.0f} MB > 126 MB L2; parameters stay "
@@ -277,7 +278,7 @@ def run_reference_arm(args):
         "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": make_config(workload, shape, mode, train, world, args.nbuf, not args.eager_allreduce),
+        "config": make_config(workload, shape, mode, train, world, args.nbuf, not args.eager_allreduce, args.exchange),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -413,6 +414,9 @@ def main():
     ap.add_argument("--nbuf", type=int, default=16, help="distinct input batches the step rotates over")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="headline numbers only (no roofline / next rows / drop-in legs)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "peer_nomc", "nccl"],
+                    help="N>1 gradient exchange: the library's one-kernel all-reduce over peer memory (NVLS multicast when "
+                         "available / plain peer pointers) or NCCL")
     ap.add_argument("--eager-allreduce", action="store_true",
                     help="N>1: issue the NCCL gradient all-reduce after each graph replay instead of inside the graph")
     args = ap.parse_args()
@@ -448,7 +452,7 @@ def main():
                          ppc_cov_thresh=shape.ppc_cov_thresh, ppc_mean_thresh=shape.ppc_mean_thresh)
     nbuf = args.nbuf
     step = GraphedHeadStep(params, cfg, B=shape.B, N=shape.N, C=shape.C, m=shape.m, n_slots=nbuf, train=train,
-                           allreduce_in_graph=in_graph)
+                           allreduce_in_graph=in_graph, exchange=args.exchange if (world > 1 and train) else "nccl")
     # distinct synthetic batches per slot and per rank (weak scaling: fixed per-GPU batch)
     host = []
     for i in range(nbuf):
@@ -643,12 +647,13 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3 split, fp32 accumulate (fp32-grade)" if mode == "fp32" else "bf16, fp32 accumulate",
             "data": "synthetic",
-            "config": make_config(workload, shape, mode, train, world, nbuf, not args.eager_allreduce),
+            "config": make_config(workload, shape, mode, train, world, nbuf, not args.eager_allreduce, args.exchange),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_host.numel() * 4,
                     "ms_per_step": ms_e2e / args.steps, "last_loss" if train else "last_logit": last_loss, "host_buffers": numa},
             "gpu_launches": step.kernel_launches_per_step * args.steps,
             "gpu_launches_per_step": step.kernel_launches_per_step,
             "step_impl": step.impl,
+            "exchange": getattr(step, "exchange", None) if world > 1 else None,
             "clocks": sampler.summary(),
             "roofline": roof,
             "oracle_check": oracle_check,
@@ -659,7 +664,17 @@ def main():
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # graphs that recorded NCCL kernels keep the communicator busy: drop them first, and never let a stuck teardown
+        # turn a finished measurement into a hang
+        step.graphs.clear()
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
+        t = threading.Thread(target=dist.destroy_process_group, daemon=True)
+        t.start()
+        t.join(20)
+        sys.stdout.flush()
+        os._exit(0)
     return 0
 
 

@@ -363,6 +363,21 @@ int pph_addon_bwd3(int parts, const float* tokens, const int32_t* idx32, const f
                    int B, int N, int Din, int D, int K, void* workspace,
                    float* dWa, float* dba, float* dtokens, pph_stream_t stream);
 
+/* Gradient exchange of the data-parallel head (reference: DistributedDataParallel, main.py:369-371) as ONE kernel over
+ * NVLink / NVSwitch peer memory: averages buf[lo, lo + n) IN PLACE over `world` ranks.  buf_ptrs (HOST array, `world`
+ * entries) holds the address of the same peer-mapped ("symmetric") buffer on every rank as mapped into this process
+ * (entry `rank` is the local one); multicast_ptr is the NVLS multicast mapping of that buffer or 0 (then rank r sums
+ * chunk r of every peer in rank order and stores the average into every peer; with multicast the switch does both:
+ * multimem.ld_reduce / multimem.st).  A flag block of pph_peer_flag_bytes() bytes, ZERO-FILLED once before the first call
+ * and followed by a barrier over the ranks, lives inside every rank's buffer at flag_offset_bytes (16-byte aligned, behind
+ * the data).  Every rank must issue the same sequence of calls per `slot` (0..3; calls that may overlap in time use
+ * different slots) with the same lo, n, n_ctas.  lo and n are multiples of 4 floats.  Safe to record in CUDA graphs
+ * (flags are monotonically increasing epochs).  A peer that never arrives traps the kernel instead of hanging. */
+int pph_peer_flag_bytes(long long* bytes /* host */);
+int pph_peer_allreduce(const unsigned long long* buf_ptrs /* host */, unsigned long long multicast_ptr,
+                       long long flag_offset_bytes, int rank, int world, long long lo, long long n,
+                       int n_ctas, int slot, pph_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,14 +19,15 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from .dist import FlatGradReducer
+from .dist import FlatGradReducer, PeerGradReducer
 
 
 class GraphedHeadStep:
     def __init__(self, params: dict, cfg: ops.HeadConfig, B: int, N: int, C: int, m: int, n_slots: int = 1,
                  heads: int = 0, ppc_cov_coe: float = 0.1, ppc_mean_coe: float = 0.5, train: bool = True,
                  process_group=None, device=None, fused: bool = True, allreduce_in_graph: bool = False,
-                 schedule: int | None = None, use_ppc: bool = True, impl: str = "auto", variants=None):
+                 schedule: int | None = None, use_ppc: bool = True, impl: str = "auto", variants=None,
+                 exchange: str = "nccl"):
         """params: dict with Wa (D,Din), ba (D), P (P,D), Pg (Pg,D) [leaf tensors, requires_grad in training] and
         the frozen Wl (C,P), Wg (C,Pg).  ppc_*_coe follow scripts/train_cub.sh:43-44."""
         self.p, self.cfg, self.B, self.N, self.C, self.m = params, cfg, B, N, C, m
@@ -46,7 +47,15 @@ class GraphedHeadStep:
         self.reducer = None
         if train:
             named = [(k, params[k]) for k in ("P", "Pg", "Wa", "ba")]
-            self.reducer = FlatGradReducer(named, process_group)
+            # exchange: "nccl" = NCCL all-reduce of the flat buffer, "peer" / "peer_nomc" = the library's own one-kernel
+            # all-reduce over peer-mapped memory (with / without the NVLS multicast mapping)
+            self.exchange = exchange
+            if exchange in ("peer", "peer_nomc"):
+                self.reducer = PeerGradReducer(named, process_group, multicast=(exchange == "peer"))
+                if exchange == "peer" and not self.reducer.multicast_ptr:
+                    self.exchange = "peer_nomc"
+            else:
+                self.reducer = FlatGradReducer(named, process_group)
         self.kernel_launches_per_step = 0
         self.allreduce_in_graph = allreduce_in_graph      # record the NCCL gradient all-reduce inside the CUDA graph
         self.fused = None
@@ -76,9 +85,15 @@ class GraphedHeadStep:
             # NCCL's stream; the add-on part follows the weight-gradient kernel.  Both join the step's stream below.
             seg = {"protos": self.reducer.segment(("P", "Pg")), "addon": self.reducer.segment(("Wa", "ba"))}
 
+            aligned = all(v % 4 == 0 for v in seg["protos"])
+
             def hook(which):
                 lo, hi = seg[which]
-                w = self.reducer.allreduce(async_op=True, lo=lo, hi=hi, check=False)
+                if not aligned:           # odd sizes: one exchange of the whole buffer after the last gradient
+                    if which == "protos":
+                        return
+                    lo, hi = 0, None
+                w = self.reducer.allreduce(async_op=True, lo=lo, hi=hi, check=False, slot=0 if which == "protos" else 1)
                 if w is not None:
                     works.append(w)
         with torch.no_grad():

@@ -850,13 +850,29 @@ class FusedHeadStep:
                 main.wait_event(ev[6])              # dZs_ppc (as dpre) from the PPC branch
             # token gradient (82 CTAs) then weight gradient (112 CTAs behind a grid barrier): both want one CTA per SM, as
             # graph branches they only time-slice the machine (measured), so they run back to back
-            c("pph_addon_bwd3", 2, tokens, self.idx32, Wa, self.dZs, self.dZc, dpre_add, B, N, Din, D, K, self.ws_tc,
-              None, None, self.dtokens)
-            c("pph_addon_bwd3", 1, tokens, self.idx32, Wa, self.dZs, self.dZc, dpre_add, B, N, Din, D, K, self.ws_tc,
-              grads["Wa"], grads["ba"], None)
+            def dgrad():
+                c("pph_addon_bwd3", 2, tokens, self.idx32, Wa, self.dZs, self.dZc, dpre_add, B, N, Din, D, K, self.ws_tc,
+                  None, None, self.dtokens)
+
+            def wgrad():
+                c("pph_addon_bwd3", 1, tokens, self.idx32, Wa, self.dZs, self.dZc, dpre_add, B, N, Din, D, K, self.ws_tc,
+                  grads["Wa"], grads["ba"], None)
+
+            if reduce_hook is not None:     # weight gradient first: its exchange then runs under the token gradient
+                wgrad()
+                ev[5].record(main)
+                with torch.cuda.stream(side2):
+                    side2.wait_event(ev[5])
+                    hook("addon")
+                    ev[7].record(side2)
+                dgrad()
+                main.wait_event(ev[7])
+            else:
+                dgrad()
+                wgrad()
         else:
             c("pph_addon_bwd2", 3, tokens, self.idx32, Wa, self.dZs, self.dZc, B, N, Din, D, K,
               self.ws_addon, grads["Wa"], grads["ba"], self.dtokens)
-        hook("addon")
+            hook("addon")
         main.wait_event(ev[1])
         return self.losses

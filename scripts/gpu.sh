@@ -52,15 +52,18 @@ case $stage in
     done ;;
   bench2|bench4|bench8)   # N ranks on one box (gpurun --gpus N): in-graph overlapped all-reduce, then the eager one
     n=${stage#bench}
-    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 \
+    timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 \
         bench.py --gpus $n --steps 1000 --warmup 50 --no-extras > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err
     echo "== in-graph rc=$?"; tail -c 2500 gpurun_out/bench_n$n.json; tail -5 gpurun_out/bench_n$n.err
-    timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 \
-        bench.py --gpus $n --steps 1000 --warmup 50 --no-extras --eager-allreduce > gpurun_out/bench_n${n}_eager.json 2> gpurun_out/bench_n${n}_eager.err
-    echo "== eager rc=$?"; tail -c 1200 gpurun_out/bench_n${n}_eager.json; tail -3 gpurun_out/bench_n${n}_eager.err ;;
+    timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 \
+        bench.py --gpus $n --steps 1000 --warmup 50 --no-extras --exchange nccl > gpurun_out/bench_n${n}_nccl.json 2> gpurun_out/bench_n${n}_nccl.err
+    echo "== nccl rc=$?"; tail -c 1200 gpurun_out/bench_n${n}_nccl.json; tail -3 gpurun_out/bench_n${n}_nccl.err ;;
+  probe2)
+    timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 \
+        scripts/peer_probe.py > gpurun_out/probe2.log 2>&1; echo "== probe2 rc=$?"; grep -v "^W\|^\*\|OMP" gpurun_out/probe2.log | tail -30 ;;
   ddp2)       # in-graph all-reduce result check at N=2
-    timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 \
-        scripts/ddp_check.py > gpurun_out/ddp2.log 2>&1; echo "== ddp2 rc=$?"; tail -8 gpurun_out/ddp2.log ;;
+    PPH_TIMELINE=1 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 \
+        scripts/ddp_check.py > gpurun_out/ddp2.log 2>&1; echo "== ddp2 rc=$?"; grep -v "^W\|^\*\|OMP" gpurun_out/ddp2.log | tail -60 ;;
   smoke)
     timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3 ;;
   launches)
