@@ -412,6 +412,8 @@ def main():
     ap.add_argument("--mode", default=None, choices=["fp32", "bf16"],
                     help="similarity precision: fp32 = 3-term bf16 split (1e-4 parity), bf16 = single pass")
     ap.add_argument("--nbuf", type=int, default=16, help="distinct input batches the step rotates over")
+    ap.add_argument("--e2e-load", default="selected", choices=["selected", "full"],
+                    help="end-to-end leg: transfer only the token rows the head consumes (default) or the whole batch")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="headline numbers only (no roofline / next rows / drop-in legs)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "peer_nomc", "nccl"],
@@ -531,6 +533,26 @@ def main():
     ready = [torch.cuda.Event() for _ in range(2)]
     done = [torch.cuda.Event() for _ in range(2)]
 
+    selected = args.e2e_load == "selected"
+    h2d_bytes = (4 * shape.B * shape.N + 8 * shape.B + 4 * shape.B * (shape.K + 1) * shape.Din) if selected else in_bytes
+    # what the last e2e step must reproduce: the same batch through the device-resident path
+    last_slot = (args.steps - 1) % nbuf
+    step.run(last_slot)
+    if world > 1 and train:
+        step.allreduce_grads()
+    torch.cuda.synchronize()
+    want_last = float(result_of(last_slot).reshape(-1)[0].item())
+
+    load_graphs = {}
+    if selected:      # one recorded transfer per (slot, staging buffer) pair of the ring
+        for s in range(2):
+            for i in range(nbuf):
+                if i % 2 == s or nbuf % 2:
+                    b = host[i]
+                    load_graphs[(s, i)] = step.capture_load_host(s, b["tokens"], b["scores"], b["labels"])
+        step.run(last_slot)           # slots 0 / 1 were overwritten by the captures' warm-up transfers: harmless
+        torch.cuda.synchronize()
+
     def e2e_loop(n):
         cur = torch.cuda.current_stream()
         for i in range(n):
@@ -538,7 +560,10 @@ def main():
             with torch.cuda.stream(copy_stream):
                 copy_stream.wait_event(done[s])                 # slot s no longer read by step i-2
                 b = host[i % nbuf]
-                step.load(s, b["tokens"], b["scores"], b["labels"])
+                if selected:
+                    load_graphs[(s, i % nbuf)].replay()
+                else:
+                    step.load(s, b["tokens"], b["scores"], b["labels"])
                 ready[s].record(copy_stream)
             cur.wait_event(ready[s])
             step.run(s)
@@ -557,6 +582,7 @@ def main():
     e0.record()
     last_loss = e2e_loop(args.steps)
     e1.record()
+    assert last_loss == want_last, f"end-to-end result {last_loss} != device-resident result {want_last} of the same batch"
     barrier()
     ms_e2e = e0.elapsed_time(e1)
     if world > 1:
@@ -648,7 +674,10 @@ def main():
             "dtype": "bf16x3 split, fp32 accumulate (fp32-grade)" if mode == "fp32" else "bf16, fp32 accumulate",
             "data": "synthetic",
             "config": make_config(workload, shape, mode, train, world, nbuf, not args.eager_allreduce, args.exchange),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_host.numel() * 4,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
+                    "h2d": ("selection first: scores + labels by copy, then the CLS row and the K selected token rows of every "
+                            "image read from the pinned host batch by pph_gather_rows_host (the other rows are never read by "
+                            f"the head; a full copy would be {in_bytes} bytes)") if selected else "full batch by cudaMemcpyAsync", "d2h_bytes_per_step": out_host.numel() * 4,
                     "ms_per_step": ms_e2e / args.steps, "last_loss" if train else "last_logit": last_loss, "host_buffers": numa},
             "gpu_launches": step.kernel_launches_per_step * args.steps,
             "gpu_launches_per_step": step.kernel_launches_per_step,

@@ -363,6 +363,14 @@ int pph_addon_bwd3(int parts, const float* tokens, const int32_t* idx32, const f
                    int B, int N, int Din, int D, int K, void* workspace,
                    float* dWa, float* dba, float* dtokens, pph_stream_t stream);
 
+/* Selection-first input transfer for tokens that live in pinned (mapped) HOST memory: copies the CLS row and the K
+ * selected token rows of every image (idx32 from pph_select_topk, protopformer.py:156-166) from tokens_host
+ * [B, 1+N, Din] to the same positions of tokens_dev [B, 1+N, Din] by zero-copy loads over PCIe; the other rows of
+ * tokens_dev are left untouched (the head's forward and backward never read them).  tokens_host must be page-locked
+ * host memory (cudaHostAlloc / cudaHostRegister); PPH_EINVAL otherwise.  Din a multiple of 4. */
+int pph_gather_rows_host(const float* tokens_host, const int32_t* idx32, int B, int N, int Din, int K,
+                         float* tokens_dev, int n_ctas, pph_stream_t stream);
+
 /* Gradient exchange of the data-parallel head (reference: DistributedDataParallel, main.py:369-371) as ONE kernel over
  * NVLink / NVSwitch peer memory: averages buf[lo, lo + n) IN PLACE over `world` ranks.  buf_ptrs (HOST array, `world`
  * entries) holds the address of the same peer-mapped ("symmetric") buffer on every rank as mapped into this process

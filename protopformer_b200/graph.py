@@ -159,6 +159,37 @@ class GraphedHeadStep:
             self.scores[slot].copy_(scores, non_blocking=True)
             self.labels[slot].copy_(labels, non_blocking=True)
 
+    def load_host(self, slot: int, tokens, scores, labels, n_ctas: int = 48):
+        """Selection-first transfer of one batch from PINNED host tensors (current stream): scores and labels by copy,
+        the top-K ranking on the device, then only the CLS row and the K selected rows of every image are read out of
+        the host buffer by a gather kernel (pph_gather_rows_host).  The slot's other token rows keep stale values that
+        neither the forward nor the backward reads.  Returns the bytes that crossed the bus."""
+        from . import _lib
+        assert tokens.is_pinned() and tokens.is_contiguous() and tokens.dtype == torch.float32
+        if not hasattr(self, "_load_idx"):
+            self._load_idx = [torch.empty(self.B, self.cfg.K, dtype=torch.int32, device=self.tokens[0].device)
+                              for _ in self.tokens]
+        B, N, K = self.B, self.N, self.cfg.K
+        H = scores.shape[1] if scores.dim() == 3 else 1
+        Din = tokens.shape[-1]
+        with torch.no_grad():
+            self.scores[slot].copy_(scores, non_blocking=True)
+            self.labels[slot].copy_(labels, non_blocking=True)
+            _lib.call("pph_select_topk", self.scores[slot], B, H, N, K, self._load_idx[slot], None)
+            _lib.call("pph_gather_rows_host", tokens.data_ptr(), self._load_idx[slot], B, N, Din, K,
+                      self.tokens[slot].detach(), n_ctas)
+        return scores.numel() * 4 + labels.numel() * 8 + B * (K + 1) * Din * 4
+
+    def capture_load_host(self, slot: int, tokens, scores, labels, n_ctas: int = 48):
+        """load_host() of one fixed (slot, pinned staging buffer) pair recorded as a CUDA graph: a caller that cycles
+        through a ring of staging buffers replays it (one host call) on its copy stream."""
+        self.load_host(slot, tokens, scores, labels, n_ctas)          # allocates the index buffers outside the capture
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            self.load_host(slot, tokens, scores, labels, n_ctas)
+        return g
+
     def run(self, slot: int = 0):
         self.graphs[slot].replay()
         return self.loss[slot]

@@ -58,6 +58,8 @@ case $stage in
     timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 \
         bench.py --gpus $n --steps 1000 --warmup 50 --no-extras --exchange nccl > gpurun_out/bench_n${n}_nccl.json 2> gpurun_out/bench_n${n}_nccl.err
     echo "== nccl rc=$?"; tail -c 1200 gpurun_out/bench_n${n}_nccl.json; tail -3 gpurun_out/bench_n${n}_nccl.err ;;
+  hostgather)
+    timeout 200 python scripts/host_gather_times.py 2>&1 | tail -12 ;;
   probe2)
     timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 \
         scripts/peer_probe.py > gpurun_out/probe2.log 2>&1; echo "== probe2 rc=$?"; grep -v "^W\|^\*\|OMP" gpurun_out/probe2.log | tail -30 ;;

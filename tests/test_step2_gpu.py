@@ -562,3 +562,36 @@ def test_five_launch_step_other_batch_sizes(B):
     for k in ("P", "Pg", "Wa", "ba"):
         assert norm_rel(p1[k].grad.cpu(), p2[k].grad.cpu()) < 5e-3, k
     assert norm_rel(s1.fused.dtokens.cpu(), s2.fused.dtokens.cpu()) < 5e-3
+
+
+def test_selection_first_host_transfer_feeds_the_same_step():
+    """GraphedHeadStep.load_host: only the CLS row and the selected rows cross the bus (read by a kernel from pinned host
+    memory); the step's results are bitwise those of a full copy of the batch."""
+    shape = synth.SHAPES["cub_b8"]
+    case = synth.make_case(shape, seed=11)
+    step, params = _make_step(shape, case, "fp32")
+    step.run(0)
+    torch.cuda.synchronize()
+    want = (step.fused.losses.clone(), step.fused.dtokens.clone(), params["P"].grad.clone(), params["Wa"].grad.clone())
+    idx = step.fused.idx32.long().cpu()
+    step.tokens[0].detach().fill_(float("nan"))                       # stale rows must never be read
+    host = {k: case[k].pin_memory() for k in ("tokens", "scores", "labels")}
+    moved = step.load_host(0, host["tokens"], host["scores"], host["labels"])
+    assert moved == 4 * shape.B * shape.N + 8 * shape.B + 4 * shape.B * (shape.K + 1) * shape.Din
+    torch.cuda.synchronize()
+    dev_tok = step.tokens[0].detach().cpu()
+    for b in range(shape.B):
+        rows = torch.cat([torch.zeros(1, dtype=torch.long), idx[b] + 1])
+        assert torch.equal(dev_tok[b, rows], case["tokens"][b, rows])
+        other = torch.ones(shape.N + 1, dtype=torch.bool)
+        other[rows] = False
+        assert torch.isnan(dev_tok[b, other]).all()                   # nothing else was transferred
+    step.run(0)
+    torch.cuda.synchronize()
+    got = (step.fused.losses, step.fused.dtokens, params["P"].grad, params["Wa"].grad)
+    for a, b in zip(want, got):
+        assert torch.equal(a, b)
+    from protopformer_b200 import _lib as L
+    with pytest.raises(RuntimeError):                                  # pageable memory is refused, not copied silently
+        L.call("pph_gather_rows_host", case["tokens"].data_ptr(), step._load_idx[0], shape.B, shape.N, shape.Din, shape.K,
+               step.tokens[0].detach(), 8)
