@@ -36,6 +36,11 @@ case $stage in
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$k" -s 0 -c 6 -o gpurun_out/r2_$k -f \
         python scripts/run_step.py cub_b64 fp32 v2 3 > gpurun_out/ncuk_$k.log 2>&1
     echo "== ncuk $k rc=$?"; tail -2 gpurun_out/ncuk_$k.log ;;
+  ncufinal)   # --set full capture of every kernel of the shipped step (second eager step) -> profiles/r2_ncu_full_step_kernels.txt
+    timeout 900 ncu --set full --clock-control none --import-source on \
+        -k regex:"select_topk|tcshot|similarity_tc2|head_mid|head_ppc|sim_grads|ppc_rows_add|split_rows" -s 11 -c 11 \
+        -o gpurun_out/r2_final -f python scripts/run_step.py cub_b64 fp32 v2 3 > gpurun_out/ncufinal.log 2>&1
+    echo "== ncufinal rc=$?"; tail -2 gpurun_out/ncufinal.log ;;
   ncu1)       # same capture of the round-1 launch sequence (reference point for the A/B)
     timeout 900 ncu --set full --clock-control none --import-source on -s 32 -c 16 -o gpurun_out/r2_step1 -f \
         python scripts/run_step.py cub_b64 fp32 v1 3 > gpurun_out/ncu1.log 2>&1
@@ -63,9 +68,10 @@ case $stage in
   probe2)
     timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 \
         scripts/peer_probe.py > gpurun_out/probe2.log 2>&1; echo "== probe2 rc=$?"; grep -v "^W\|^\*\|OMP" gpurun_out/probe2.log | tail -30 ;;
-  ddp2)       # in-graph all-reduce result check at N=2
-    PPH_TIMELINE=1 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 \
-        scripts/ddp_check.py > gpurun_out/ddp2.log 2>&1; echo "== ddp2 rc=$?"; grep -v "^W\|^\*\|OMP" gpurun_out/ddp2.log | tail -60 ;;
+  ddp2|ddp4|ddp8)       # in-graph gradient exchange: result check, step time and kernel timeline at N ranks
+    n=${stage#ddp}
+    PPH_TIMELINE=1 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29513 \
+        scripts/ddp_check.py > gpurun_out/ddp$n.log 2>&1; echo "== ddp$n rc=$?"; grep -v "^W\|^\*\|OMP" gpurun_out/ddp$n.log | grep "us/step\|peer_all\|nccl\|next replay" | tail -40 ;;
   smoke)
     timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -3 ;;
   launches)

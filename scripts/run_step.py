@@ -23,7 +23,7 @@ case = {k: v.to(dev) for k, v in synth.make_case(s, seed=1).items()}
 cfg = ops.HeadConfig(K=s.K, global_coe=s.global_coe, mode=mode, ppc_cov_thresh=s.ppc_cov_thresh,
                      ppc_mean_thresh=s.ppc_mean_thresh)
 cls = ops.FusedHeadStep if impl == "v2" else ops.FusedHeadStepV1
-kw = dict(variants=dict(ppc="split")) if impl == "v2" else {}
+kw = {}                    # the shipped default schedule (late PPC branch, gather backward, tcgen05 add-on kernels)
 f = cls(cfg, s.B, s.N, s.Din, s.D, s.P, s.Pg, s.C, s.m, dev, **kw)
 params = {k: case[k] for k in ("Wa", "ba", "P", "Pg")}
 red = FlatGradReducer([(k, params[k]) for k in ("P", "Pg", "Wa", "ba")])
