@@ -363,6 +363,19 @@ int pph_addon_bwd3(int parts, const float* tokens, const int32_t* idx32, const f
                    int B, int N, int Din, int D, int K, void* workspace,
                    float* dWa, float* dba, float* dtokens, pph_stream_t stream);
 
+/* PPC loss on a DENSE activation map: `get_PPC_loss(total_proto_act, cls_attn_rollout, original_fea_len, label)` as the
+ * reference writes it (protopformer.py:259-288) for callers that hold the (B,P,h,w) map as a tensor.  act [B,P,K] (the map
+ * flattened over h,w), idx32 [B,K] ascending selected tokens (pph_select_topk of cls_attn_rollout, :273-274), labels [B].
+ * fwd: losses[0] = L_cov, losses[1] = L_mean; stats [B,m,8], partial [B,2] and a ZERO-INITIALISED counter are scratch kept for
+ * the backward.  bwd: dact [B,P,K] is written completely (zeros outside the label-class rows) for the upstream scalars
+ * g_cov, g_mean (device pointers).  1 <= m <= 32, N a perfect square.  Deterministic. */
+int pph_ppc_dense_fwd(const float* act, const int32_t* idx32, const int64_t* labels, int B, int P, int K, int m, int N,
+                      float cov_thresh, float mean_thresh, float* stats, float* partial, unsigned int* counter,
+                      float* losses, pph_stream_t stream);
+int pph_ppc_dense_bwd(const float* act, const int32_t* idx32, const int64_t* labels, const float* stats,
+                      const float* g_cov, const float* g_mean, int B, int P, int K, int m, int N, float mean_thresh,
+                      float* dact, pph_stream_t stream);
+
 /* Selection-first input transfer for tokens that live in pinned (mapped) HOST memory: copies the CLS row and the K
  * selected token rows of every image (idx32 from pph_select_topk, protopformer.py:156-166) from tokens_host
  * [B, 1+N, Din] to the same positions of tokens_dev [B, 1+N, Din] by zero-copy loads over PCIe; the other rows of

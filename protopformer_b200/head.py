@@ -171,10 +171,16 @@ class PPNet(nn.Module):
         return out.logits, (None, attn_loss, total_proto_act, cls_attn_rollout, original_fea_len)
 
     def get_PPC_loss(self, total_proto_act, cls_attn_rollout, original_fea_len, label):
-        """protopformer.py:259-288.  `total_proto_act` is the ProtoMap returned by forward() in training mode; the
-        selected-token list it carries is the one the reference would recompute from `cls_attn_rollout` (:273-274)."""
+        """protopformer.py:259-288.  `total_proto_act` is normally the ProtoMap returned by forward() in training mode (the
+        selected-token list it carries is the one the reference would recompute from `cls_attn_rollout`, :273-274, and the
+        label-class slice is recomputed from the token features instead of being gathered from a (B,P,h,w) tensor).  A
+        dense (B,P,h,w) tensor is accepted as in the reference: the loss and its gradient w.r.t. that tensor come from
+        the dense-map kernels."""
         if not isinstance(total_proto_act, ProtoMap):
-            raise TypeError("get_PPC_loss expects the ProtoMap handle returned by forward() in training mode")
+            if not torch.is_tensor(total_proto_act) or total_proto_act.dim() != 4:
+                raise TypeError("get_PPC_loss expects the ProtoMap returned by forward() or a (B,P,h,w) tensor")
+            return ops.ppc_loss_dense(self._cfg(), total_proto_act, cls_attn_rollout, label,
+                                      self.num_prototypes_per_class, int(original_fea_len))
         pm = total_proto_act
         return ops.ppc_loss(pm.cfg, pm.tf, self.prototype_vectors, pm.p2l, label,
                             self.num_prototypes_per_class, int(original_fea_len))

@@ -456,6 +456,48 @@ def ppc_loss(cfg: HeadConfig, tf: TokenFeatures, P, p2l, labels, m: int, N: int)
     return _PPC.apply(tf.Zs, P2d, tf.z2s, p2l, tf.idx32, labels, m, N, cfg)
 
 
+class _PPCDense(torch.autograd.Function):
+    """get_PPC_loss on a dense (B,P,K) activation tensor (protopformer.py:259-288); gradient w.r.t. the tensor."""
+
+    @staticmethod
+    def forward(ctx, act, idx32, labels, m, N, cov_thresh, mean_thresh):
+        B, P, K = act.shape
+        dev = act.device
+        stats = torch.empty(B, m, 8, dtype=torch.float32, device=dev)
+        partial = torch.empty(B, 2, dtype=torch.float32, device=dev)
+        counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        losses = torch.empty(2, dtype=torch.float32, device=dev)
+        _lib.call("pph_ppc_dense_fwd", act, idx32, labels, B, P, K, m, N, float(cov_thresh), float(mean_thresh), stats,
+                  partial, counter, losses)
+        ctx.save_for_backward(act, idx32, labels, stats)
+        ctx.dims = (B, P, K, m, N, float(mean_thresh))
+        return losses[0], losses[1]
+
+    @staticmethod
+    def backward(ctx, g_cov, g_mean):
+        act, idx32, labels, stats = ctx.saved_tensors
+        B, P, K, m, N, mean_thresh = ctx.dims
+        zero = torch.zeros((), dtype=torch.float32, device=act.device)
+        g_cov = zero if g_cov is None else g_cov.to(torch.float32).contiguous()
+        g_mean = zero if g_mean is None else g_mean.to(torch.float32).contiguous()
+        dact = torch.empty_like(act)
+        _lib.call("pph_ppc_dense_bwd", act, idx32, labels, stats, g_cov, g_mean, B, P, K, m, N, mean_thresh, dact)
+        return dact, None, None, None, None, None, None
+
+
+def ppc_loss_dense(cfg: HeadConfig, total_proto_act: torch.Tensor, cls_attn_rollout: torch.Tensor, labels, m: int, N: int):
+    """The reference's `get_PPC_loss` signature for a caller that holds the activation map as a (B,P,h,w) tensor:
+    the selected-token list is recomputed from `cls_attn_rollout` exactly as protopformer.py:273-274 does (top-K with
+    K = h*w, ascending), the label-class rows are gathered from the map.  -> (ppc_cov_loss, ppc_mean_loss)."""
+    side = int(round(math.sqrt(N)))
+    assert side * side == N, "original_fea_len must be a perfect square (protopformer.py:260)"
+    assert total_proto_act.is_cuda and total_proto_act.dtype == torch.float32, "float32 CUDA tensor expected (no CPU path)"
+    act = total_proto_act.flatten(2).contiguous()
+    K = act.shape[-1]
+    idx32 = select_topk(cls_attn_rollout.detach(), K)
+    return _PPCDense.apply(act, idx32, labels.contiguous(), m, N, cfg.ppc_cov_thresh, cfg.ppc_mean_thresh)
+
+
 # ------------------------------------------------------------------------------------------------------------------
 # Fused training / inference step: the same entry points in a fixed sequence over pre-allocated buffers, no autograd
 # graph and no PyTorch glue kernels in between (what tools/engine_proto.py:49-76 amounts to for the head).

@@ -63,6 +63,9 @@ case $stage in
     timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 \
         bench.py --gpus $n --steps 1000 --warmup 50 --no-extras --exchange nccl > gpurun_out/bench_n${n}_nccl.json 2> gpurun_out/bench_n${n}_nccl.err
     echo "== nccl rc=$?"; tail -c 1200 gpurun_out/bench_n${n}_nccl.json; tail -3 gpurun_out/bench_n${n}_nccl.err ;;
+  variants)   # A/B of the two variant switches: rollout normalisation (PPH_ROLLOUT=3) and staged class maps (PPH_CLASSMAP=2)
+    for v in 0 3; do echo "PPH_ROLLOUT=$v"; PPH_ROLLOUT=$v timeout 200 python scripts/rollout_bench.py "11,64,3,197;11,64,6,197" 2>&1 | cut -c1-160 | tail -2; done
+    for v in 1 2; do echo "PPH_CLASSMAP=$v"; PPH_CLASSMAP=$v timeout 200 python scripts/next_rows_bench.py 2>&1 | grep class_maps | cut -c1-200; done ;;
   hostgather)
     timeout 200 python scripts/host_gather_times.py 2>&1 | tail -12 ;;
   probe2)

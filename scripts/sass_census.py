@@ -4,7 +4,7 @@ import re
 import subprocess
 import sys
 
-keys = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "SYNCS", "LDGSTS", "MULTIMEM", "REDG", "ATOMG", "BAR.SYNC",
+keys = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UTMASTG", "SYNCS", "LDGSTS", "LDGMC", "REDG", "ATOMG", "BAR.SYNC",
         "ACQBULK", "LDG", "STG", "LDS", "STS", "FFMA", "HFMA2"]
 cur, acc = None, collections.OrderedDict()
 for line in sys.stdin:
@@ -24,6 +24,6 @@ for line in sys.stdin:
 names = subprocess.run(["c++filt"], input="\n".join(acc), capture_output=True, text=True).stdout.splitlines()
 print("# SASS mnemonic census of protopformer_b200/lib/libprotohead_b200.so (cuobjdump -sass)")
 print("# UTCHMMA = tcgen05.mma, UTCBAR = tcgen05.commit, LDTM = tcgen05.ld, UTMALDG = TMA load, SYNCS = mbarrier, "
-      "LDGSTS = cp.async, MULTIMEM = multimem.ld_reduce / multimem.st")
+      "LDGSTS = cp.async, LDGMC = multimem.ld_reduce (the multimem.st is an STG on the multicast address)")
 for (f, c), d in zip(acc.items(), names):
     print(f"{d[:130]}\n    instructions {c['_n']:6d}  " + "  ".join(f"{k}={c[k]}" for k in keys if c[k]))

@@ -91,6 +91,35 @@ def test_ppnet_dropin_eval_train_push(name, precision):
         assert norm_rel(tokens.grad.reshape(-1, shape.Din).cpu()[::st], g["g_tokens"]) < 5e-4
 
 
+@pytest.mark.parametrize("name", ["cub_b8_s1", "small_s1", "cars_b4_s1"])
+def test_get_ppc_loss_accepts_a_dense_map_tensor(name):
+    """protopformer.py:259-271 takes any (B,P,h,w) tensor: the dense-map kernels must give the reference fixture's losses
+    and the oracle's gradient with respect to that tensor."""
+    from oracle import protohead_oracle as O
+    shape, case, g, fn = load_golden(name)
+    net, feats = _build(shape, case, fn, "fp32")
+    net.train()
+    labels = case["labels"].cuda()
+    ref = O.head_forward(case, shape.K, shape.global_coe, fn)
+    side = int(round(shape.K ** 0.5))
+    dense_cpu = ref["act_map"].reshape(shape.B, shape.P, side, side).clone().requires_grad_(True)
+    cov_o, mean_o = O.ppc_loss(dense_cpu.flatten(2), ref["idx"], case["labels"], shape.m, shape.N, shape.ppc_cov_thresh,
+                               shape.ppc_mean_thresh)
+    (0.3 * cov_o + 0.7 * mean_o).backward()
+    dense = ref["act_map"].reshape(shape.B, shape.P, side, side).cuda().requires_grad_(True)
+    cov, mean = net.get_PPC_loss(dense, case["scores"].cuda(), shape.N, labels)
+    (0.3 * cov + 0.7 * mean).backward()
+    assert rel_close(cov.cpu(), g["ppc_cov"], 1e-4) and rel_close(mean.cpu(), g["ppc_mean"], 1e-4)
+    assert rel_close(cov.cpu(), cov_o.detach(), 1e-5) and rel_close(mean.cpu(), mean_o.detach(), 1e-5)
+    assert norm_rel(dense.grad.cpu(), dense_cpu.grad) < 1e-4
+    rows = (case["labels"][:, None] * shape.m + torch.arange(shape.m)[None]).long()
+    mask = torch.ones(shape.B, shape.P, dtype=torch.bool)
+    mask[torch.arange(shape.B)[:, None], rows] = False
+    assert (dense.grad.cpu()[mask] == 0).all()                       # only the label-class rows receive gradient
+    with pytest.raises(TypeError):
+        net.get_PPC_loss([1, 2, 3], case["scores"].cuda(), shape.N, labels)
+
+
 def test_ppnet_under_autocast_and_grad_scaler():
     """The reference runs the head under torch.cuda.amp.autocast with a loss scaler (engine_proto.py:48,76-77):
     the custom ops keep their own fp32 cast policy and scale linearly."""

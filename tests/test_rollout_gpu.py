@@ -106,12 +106,12 @@ def test_cait_start_row_ties_and_fusions_against_oracle():
         assert rel_close(got.cpu(), want, 1e-5, 1e-9), (fusion, max_rel(got.cpu(), want, 1e-9))
 
 
-def test_rollout_variant_3_in_subprocess():
-    """The library reads PPH_ROLLOUT once per process, so the variant runs the fixture / oracle tests in a child."""
+def test_rollout_exact_division_variant_in_subprocess():
+    """The library reads PPH_ROLLOUT once per process, so the exact-division normalisation (PPH_ROLLOUT=2; the default is one reciprocal per row) runs the fixture / oracle tests in a child."""
     import os
     import subprocess
     import sys
-    env = dict(os.environ, PPH_ROLLOUT="3")
+    env = dict(os.environ, PPH_ROLLOUT="2")
     r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-m", "gpu", "-x", "-k", "not subprocess"], env=env, capture_output=True,
                        text=True, cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0, r.stdout[-3000:]
