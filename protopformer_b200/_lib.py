@@ -115,11 +115,17 @@ def load() -> C.CDLL:
     return _lib
 
 
+_DTYPES = (torch.float32, torch.int32, torch.int64, torch.bfloat16, torch.uint8, torch.int8, torch.uint16, torch.int16)
+
+
 def _ptr(t):
     if t is None:
         return None
     assert t.is_cuda, "prototype-head tensors must live on a CUDA device (no CPU path exists)"
     assert t.is_contiguous(), "prototype-head tensors must be contiguous"
+    # the C ABI takes float / int32 / int64 data, bf16 operand copies and byte workspaces: a half or double tensor
+    # (e.g. after model.half()) would be reinterpreted silently -- refuse it here
+    assert t.dtype in _DTYPES, f"prototype-head entry points do not take {t.dtype} tensors (cast to float32 first)"
     return t.data_ptr()
 
 

@@ -38,7 +38,7 @@ class_maps_kernel(const float* __restrict__ Zs, const float* __restrict__ z2s, c
         for (int d = lane; d < D; d += 32) s = fmaf(z[d], pr[d], s);
         s = warp_sum(s);
         if (lane == 0) {
-            const float dist = fmaxf(z2s[(size_t)b * K + k] + (p2l[p] - 2.0f * s), 0.0f);
+            const float dist = relu_keep_nan(z2s[(size_t)b * K + k] + (p2l[p] - 2.0f * s));
             const int n = idx[(size_t)b * K + k];
             if (n >= 0 && n < N) out[(size_t)q * N + n] = act_of_dist(dist, act_fn, eps);
         }
@@ -93,7 +93,7 @@ class_maps2_kernel(const float* __restrict__ Zs, const float* __restrict__ z2s, 
             s = fmaf(a.w, w.w, s);
         }
         const int p = (int)y * m + q;
-        const float dist = fmaxf(z2s[(size_t)b * K + k] + (p2l[p] - 2.0f * s), 0.0f);
+        const float dist = relu_keep_nan(z2s[(size_t)b * K + k] + (p2l[p] - 2.0f * s));
         const int n = idx[(size_t)b * K + k];
         if (n >= 0 && n < N) out[(size_t)q * N + n] = act_of_dist(dist, act_fn, eps);
     }

@@ -82,6 +82,10 @@ inline cudaError_t opt_in_smem(K kern, size_t bytes) {
 // ---------------------------------------------------------------------------------------------------------------
 // device helpers
 // ---------------------------------------------------------------------------------------------------------------
+// relu as torch computes it: NaN stays NaN (fmaxf(NaN, 0) would return 0 and hide a diverged step from the
+// caller's isfinite(loss) check, tools/engine_proto.py:68-70)
+__device__ __forceinline__ float relu_keep_nan(float x) { return x < 0.0f ? 0.0f : x; }
+
 // First statement of every kernel (see launch_k): let the dependent grid start its prologue, then wait for the
 // prerequisite grids.  Both are no-ops for a launch without the programmatic attribute.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -385,7 +385,7 @@ __device__ __forceinline__ void ppc_role(const MidArgs& a, int b, int part, int 
                 a0 = fmaf(z.x, p.x, a0); a1 = fmaf(z.y, p.y, a1); a2 = fmaf(z.z, p.z, a2); a3 = fmaf(z.w, p.w, a3);
             }
             const float dot = (a0 + a1) + (a2 + a3);
-            const float d = fmaxf(zz + fmaf(-2.0f, dot, __ldg(a.p2l + prow0 + j)), 0.0f);
+            const float d = relu_keep_nan(zz + fmaf(-2.0f, dot, __ldg(a.p2l + prow0 + j)));
             dsl[j * K + r] = d;
             wbuf[j * K + r] = act_of_dist(d, a.act_fn, a.eps);
         }
@@ -418,7 +418,7 @@ __device__ __forceinline__ void ppc_role(const MidArgs& a, int b, int part, int 
         if (lane == 0) {
             float* s8 = st + j * 8;
             s8[0] = S; s8[1] = mr; s8[2] = mc; s8[3] = Vr; s8[4] = Vc; s8[5] = pre; s8[6] = 0.f; s8[7] = 0.f;
-            cov_sum += fmaxf(pre, 0.0f);
+            cov_sum += relu_keep_nan(pre);
         }
     }
     const float cov_img = block_sum_any(lane == 0 ? cov_sum : 0.f, red, nwarp);     // its barriers also publish st[]
@@ -427,7 +427,7 @@ __device__ __forceinline__ void ppc_role(const MidArgs& a, int b, int part, int 
         const int i = t / m, j = t - i * m;
         if (i != j) {
             const float dr = st[i * 8 + 1] - st[j * 8 + 1], dc = st[i * 8 + 2] - st[j * 8 + 2];
-            mean_sum += fmaxf(a.mean_thresh - sqrtf(dr * dr + dc * dc), 0.0f);
+            mean_sum += relu_keep_nan(a.mean_thresh - sqrtf(dr * dr + dc * dc));
         }
     }
     const float mean_img = block_sum_any(mean_sum, red, nwarp);

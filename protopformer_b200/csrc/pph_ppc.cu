@@ -117,7 +117,7 @@ ppc_fwd_kernel(const float* __restrict__ Zs, const float* __restrict__ z2s, cons
                     a0 = fmaf(z.x, p.x, a0); a1 = fmaf(z.y, p.y, a1); a2 = fmaf(z.z, p.z, a2); a3 = fmaf(z.w, p.w, a3);
                 }
                 const float dot = (a0 + a1) + (a2 + a3);
-                const float d = fmaxf(zz + fmaf(-2.0f, dot, __ldg(p2l + prow0 + j)), 0.0f);
+                const float d = relu_keep_nan(zz + fmaf(-2.0f, dot, __ldg(p2l + prow0 + j)));
                 s.dsl[j * K + k0 + r] = d;
                 s.wbuf[j * K + k0 + r] = act_of_dist(d, act_fn, eps);
                 dslice[((size_t)b * m + j) * K + k0 + r] = d;
@@ -154,7 +154,7 @@ ppc_fwd_kernel(const float* __restrict__ Zs, const float* __restrict__ z2s, cons
         if (lane == 0) {
             float* st = s.st + j * 8;
             st[0] = S; st[1] = mr; st[2] = mc; st[3] = Vr; st[4] = Vc; st[5] = pre; st[6] = 0.f; st[7] = 0.f;
-            cov_sum += fmaxf(pre, 0.0f);
+            cov_sum += relu_keep_nan(pre);
         }
     }
     const float cov_img = block_sum_256(lane == 0 ? cov_sum : 0.f, red);   // includes the barrier that publishes st[]
@@ -165,7 +165,7 @@ ppc_fwd_kernel(const float* __restrict__ Zs, const float* __restrict__ z2s, cons
         const int i = t / m, j = t - i * m;
         if (i != j) {
             const float dr = s.st[i * 8 + 1] - s.st[j * 8 + 1], dc = s.st[i * 8 + 2] - s.st[j * 8 + 2];
-            mean_sum += fmaxf(mean_thresh - sqrtf(dr * dr + dc * dc), 0.0f);
+            mean_sum += relu_keep_nan(mean_thresh - sqrtf(dr * dr + dc * dc));
         }
     }
     const float mean_img = block_sum_256(mean_sum, red);

@@ -72,7 +72,7 @@ similarity_local_simt_kernel(const float* __restrict__ Zs, const float* __restri
             for (int i = 0; i < 6; ++i) {
                 const int k = kc + tx + 16 * i;
                 if (k >= K) continue;
-                const float d = fmaxf(__ldg(z2s + (size_t)b * K + k) + fmaf(-2.0f, acc[i][j], p2), 0.0f);
+                const float d = relu_keep_nan(__ldg(z2s + (size_t)b * K + k) + fmaf(-2.0f, acc[i][j], p2));
                 if (dist_map) dist_map[((size_t)b * P + p) * K + k] = d;
                 if (act_map) act_map[((size_t)b * P + p) * K + k] = act_of_dist(d, act_fn, eps);
                 if (d < best[j]) { best[j] = d; best_k[j] = k; }   // ascending k within a thread: lowest index wins
@@ -91,7 +91,7 @@ similarity_local_simt_kernel(const float* __restrict__ Zs, const float* __restri
         const int p = p0 + ty * 4 + j;
         if (tx == 0 && p < P) {
             dmin[(size_t)b * P + p] = best[j];
-            argmin[(size_t)b * P + p] = best_k[j];
+            argmin[(size_t)b * P + p] = best_k[j] == 0x7fffffff ? 0 : best_k[j];   // all distances +inf / NaN: a valid row
             act[(size_t)b * P + p] = act_of_dist(best[j], act_fn, eps);
         }
     }
@@ -103,7 +103,7 @@ struct GlobalSimEpi {   // CLS token vs global prototypes: one "token" per image
     int Pg, act_fn;
     float eps;
     __device__ __forceinline__ void operator()(int b, int p, float acc, float) const {
-        const float d = fmaxf(__ldg(z2c + b) + fmaf(-2.0f, acc, __ldg(p2g + p)), 0.0f);
+        const float d = relu_keep_nan(__ldg(z2c + b) + fmaf(-2.0f, acc, __ldg(p2g + p)));
         dmin_g[(size_t)b * Pg + p] = d;
         act_g[(size_t)b * Pg + p] = act_of_dist(d, act_fn, eps);
     }

@@ -128,7 +128,7 @@ __device__ __forceinline__ void tc_epilogue_local_ilp(const TcParams& prm, const
                         if (best[cc] < bb || (best[cc] == bb && bk[cc] < kk)) { bb = best[cc]; kk = bk[cc]; }
                     const int b = b0 + g;
                     if (pv && b < prm.B) {
-                        const float dd = fmaxf(bb + p2, 0.0f);
+                        const float dd = relu_keep_nan(bb + p2);
                         const size_t o = (size_t)b * prm.P + p;
                         prm.dmin_l[o] = dd;
                         prm.argmin_l[o] = kk;
@@ -159,7 +159,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& prm, const TcTi
         auto store = [&](int g, float best, int bk) {
             const int b = b0 + g;
             if (pv && b < prm.B) {
-                const float d = fmaxf(best + p2, 0.0f);
+                const float d = relu_keep_nan(best + p2);
                 const size_t o = (size_t)b * prm.P + p;
                 prm.dmin_l[o] = d;
                 prm.argmin_l[o] = bk;
@@ -226,7 +226,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcParams& prm, const TcTi
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 if (c0 + j < ncols && pv) {
-                    const float d = fmaxf(fmaf(-2.0f, __uint_as_float(v[j]), x2[c0 + j]) + p2, 0.0f);
+                    const float d = relu_keep_nan(fmaf(-2.0f, __uint_as_float(v[j]), x2[c0 + j]) + p2);
                     const size_t o = (size_t)(b0 + c0 + j) * prm.Pg + p;
                     prm.dmin_g[o] = d;
                     prm.act_g[o] = act_of_dist(d, prm.act_fn, prm.eps);

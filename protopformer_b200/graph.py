@@ -10,6 +10,11 @@ from static device buffers ("slots") and leaves its results in static tensors:
     step.run(slot)                               # replay
     step.loss[slot], step.logits[slot], step.dtokens[slot], param.grad (views of step.reducer.flat)
 
+Slots hold INPUTS only.  The results (loss, logits, PPC terms, dtokens, parameter gradients) live in ONE set of buffers
+shared by all slots -- replays are serial on one stream -- so `step.loss[a]` and `step.loss[b]` are the same tensor:
+read (or copy out) the results of a replay before the next `run()`.  `use_ppc=False` leaves the PPC terms out of the
+loss and the gradients, which is what the reference does before epoch 20 (tools/engine_proto.py:63).
+
 Reference call sites this mirrors: tools/engine_proto.py:49-66 (forward, CE, get_PPC_loss, weighted sum) and :76
 (backward).  The optimizer step and the backbone are outside this path.
 """

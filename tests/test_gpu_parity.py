@@ -310,3 +310,21 @@ def test_sweep_corner_fixtures(name, mode):
     for k, ref in (("logits", "logits"), ("act_l", "act_l"), ("dmin_l", "dmin_l")):
         assert rel_close(getattr(out, k).cpu(), g[ref], 1e-4), (k, max_rel(getattr(out, k).cpu(), g[ref]))
     assert argmax_mismatch_outside_near_ties(out.argmin.cpu(), g["argmax"], g["near_tie"]) == 0
+
+
+@pytest.mark.parametrize("mode", ["fp32_fma", "fp32"])
+def test_nan_prototype_gives_nan_activation_like_torch_relu(mode):
+    """torch's relu keeps NaN (protopformer.py:217), so a diverged prototype must surface as a non-finite activation and
+    loss (engine_proto.py:68-70 stops on it) instead of being clamped to distance 0."""
+    from protopformer_b200 import ops, synth
+    shape = synth.SHAPES["cub_b8"]
+    case = synth.make_case(shape, seed=3)
+    d = {k: v.cuda() for k, v in case.items()}
+    d["P"][5, 7] = float("nan")
+    cfg = ops.HeadConfig(K=shape.K, global_coe=shape.global_coe, mode=mode)
+    out = ops.head_forward(cfg, d["tokens"], d["scores"], d["Wa"], d["ba"], d["P"], d["Pg"], d["Wl"], d["Wg"])
+    act = out.act_l.cpu()
+    assert torch.isnan(act[:, 5]).all()
+    assert torch.isfinite(act[:, :5]).all() and torch.isfinite(act[:, 6:]).all()
+    assert not torch.isfinite(out.logits).any()           # every class reads every prototype
+    assert int(out.argmin.min()) >= 0 and int(out.argmin.max()) < shape.K
