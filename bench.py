@@ -543,6 +543,9 @@ def main():
     torch.cuda.synchronize()
     want_last = float(result_of(last_slot).reshape(-1)[0].item())
 
+    host_pipe = selected and train and step.impl == "v2" and (world == 1 or in_graph)
+    if host_pipe:
+        step.capture_host_pipeline()
     load_graphs = {}
     if selected:      # one recorded transfer per (slot, staging buffer) pair of the ring
         for s in range(2):
@@ -566,13 +569,16 @@ def main():
                     step.load(s, b["tokens"], b["scores"], b["labels"])
                 ready[s].record(copy_stream)
             cur.wait_event(ready[s])
-            step.run(s)
-            if world > 1 and train:
-                step.allreduce_grads()
-            out_host.copy_(result_of(s), non_blocking=True)
+            if host_pipe:             # selection from the transfer, loss stored to pinned host memory by the kernel itself
+                step.run_host(s)
+            else:
+                step.run(s)
+                if world > 1 and train:
+                    step.allreduce_grads()
+                out_host.copy_(result_of(s), non_blocking=True)
             done[s].record(cur)
         torch.cuda.synchronize()
-        return float(out_host.reshape(-1)[0].item())
+        return float(step.loss_host[(n - 1) % 2][0].item()) if host_pipe else float(out_host.reshape(-1)[0].item())
 
     for s in range(2):
         done[s].record(torch.cuda.current_stream())
@@ -677,7 +683,9 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes,
                     "h2d": ("selection first: scores + labels by copy, then the CLS row and the K selected token rows of every "
                             "image read from the pinned host batch by pph_gather_rows_host (the other rows are never read by "
-                            f"the head; a full copy would be {in_bytes} bytes)") if selected else "full batch by cudaMemcpyAsync", "d2h_bytes_per_step": out_host.numel() * 4,
+                            f"the head; a full copy would be {in_bytes} bytes)") if selected else "full batch by cudaMemcpyAsync", "d2h_bytes_per_step": 16 if host_pipe else out_host.numel() * 4,
+                    "d2h": ("(total, ce, ppc_cov, ppc_mean) stored into pinned host memory by the kernel that completes the loss"
+                            if host_pipe else "cudaMemcpyAsync of the result on the step's stream"),
                     "ms_per_step": ms_e2e / args.steps, "last_loss" if train else "last_logit": last_loss, "host_buffers": numa},
             "gpu_launches": step.kernel_launches_per_step * args.steps,
             "gpu_launches_per_step": step.kernel_launches_per_step,

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PPH_VERSION 200
+#define PPH_VERSION 201
 
 /* argument errors */
 #define PPH_EINVAL   (-1)   /* bad dimension / null pointer */
@@ -298,7 +298,11 @@ int pph_head_mid(const float* act_l, const float* act_g, const float* dmin_l, co
                  const int32_t* idx32, float cov_thresh, float mean_thresh, float cov_coe, float mean_coe,
                  void* workspace, void* bwd_workspace,
                  float* logits, float* logits_g, float* logits_l, float* losses, float* dlogits,
-                 float* g_l, float* g_g, float* pairT, float* dZs_ppc, float* dP_img, pph_stream_t stream);
+                 float* g_l, float* g_g, float* pairT, float* dZs_ppc, float* dP_img,
+                 float* losses_mirror /* NULL, or 4 floats (16-byte aligned; may be mapped pinned HOST memory) that receive
+                                         (total, ce, ppc_cov, ppc_mean) with the same store that completes losses[0]: the
+                                         caller's device->host read of the step result without a copy node */,
+                 pph_stream_t stream);
 
 /* (a8 part 2), second implementation: same results as pph_similarity_bwd(PPH_BWD_GRADS) from operands staged in shared
  * memory by feature slices (no L2 row gathers), every row summed in a fixed order (no atomics on data).  Three kernels,

@@ -50,7 +50,7 @@ SIGNATURES = {
     "pph_head_prep_supported": [_i, _i, _i, _i, _i],
     "pph_head_prep": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _f] + [_p] * 14 + [_p, _i, _p, _p, _p, _p, _p] * 2 + [_p],
     "pph_head_mid_ws_bytes": [_i, _i, _i, _i, _i, _i, _i, C.POINTER(C.c_longlong)],
-    "pph_head_mid": [_p] * 8 + [_i] * 8 + [_f, _i, _f, _f, _i, _i] + [_p] * 5 + [_f] * 4 + [_p] * 13,
+    "pph_head_mid": [_p] * 8 + [_i] * 8 + [_f, _i, _f, _f, _i, _i] + [_p] * 5 + [_f] * 4 + [_p] * 14,
     "pph_similarity_bwd2_supported": [_i, _i, _i, _i, _i],
     "pph_similarity_bwd2_ws_bytes": [_i, _i, _i, _i, C.POINTER(C.c_longlong)],
     "pph_similarity_bwd2": [_i] + [_p] * 8 + [_i] * 6 + [_p, _p, _i] + [_p] * 5,

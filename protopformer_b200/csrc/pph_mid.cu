@@ -43,6 +43,7 @@ struct MidArgs {
     const float *Wl, *Wg;
     const int64_t* labels;
     float *logits, *logits_g, *logits_l, *losses, *dlogits, *g_l, *g_g;
+    float* losses_mirror;              // optional second home of losses[0..3] (e.g. mapped pinned host memory), or nullptr
     float2* pairT;
     // workspace
     float *part, *dlT, *ce_part, *ppc_part, *ppc_losses;
@@ -82,9 +83,14 @@ __device__ __forceinline__ float block_sum_mid(float v, float* red) {
 __device__ __forceinline__ void write_total(const MidArgs& a) {
     const float ce = __ldcg(a.losses + 1);
     const float cov = a.have_ppc ? __ldcg(a.ppc_losses) : 0.f, mean = a.have_ppc ? __ldcg(a.ppc_losses + 1) : 0.f;
-    a.losses[0] = ce + a.cov_coe * cov + a.mean_coe * mean;
+    const float total = ce + a.cov_coe * cov + a.mean_coe * mean;
+    a.losses[0] = total;
     a.losses[2] = cov;
     a.losses[3] = mean;
+    if (a.losses_mirror) {      // the caller's copy of the result: one 16-byte store (over PCIe when it is host memory)
+        *reinterpret_cast<float4*>(a.losses_mirror) = make_float4(total, ce, cov, mean);
+        __threadfence_system();
+    }
 }
 __device__ __forceinline__ void role_finished(const MidArgs& a) {      // one thread
     if (!a.have_ppc) {
@@ -646,11 +652,12 @@ extern "C" int pph_head_mid(const float* act_l, const float* act_g, const float*
                             void* workspace, void* bwd_workspace,
                             float* logits, float* logits_g, float* logits_l, float* losses, float* dlogits,
                             float* g_l, float* g_g, float* pairT, float* dZs_ppc, float* dP_img,
-                            pph_stream_t stream) {
+                            float* losses_mirror, pph_stream_t stream) {
     using namespace pph;
     PPH_REQUIRE(act_l && dmin_l && Wl && labels && workspace && logits && logits_g && logits_l && losses, PPH_EINVAL,
                 "pph_head_mid: null pointer");
     PPH_REQUIRE(Pg == 0 || (act_g && dmin_g && Wg), PPH_EINVAL, "pph_head_mid: null global-branch pointer");
+    PPH_REQUIRE((reinterpret_cast<uintptr_t>(losses_mirror) & 15) == 0, PPH_EINVAL, "pph_head_mid: losses_mirror must be 16-byte aligned");
     PPH_REQUIRE(B >= 1 && K >= 1 && D >= 4 && P >= 1 && Pg >= 0 && C >= 1 && m >= 1 && N >= 2, PPH_EINVAL,
                 "pph_head_mid: bad dims");
     PPH_REQUIRE(C <= 256, PPH_EUNSUP, "pph_head_mid: C=%d > 256 (use the modular entry points)", C);
@@ -679,6 +686,7 @@ extern "C" int pph_head_mid(const float* act_l, const float* act_g, const float*
     a.act_l = act_l; a.act_g = act_g; a.dmin_l = dmin_l; a.dmin_g = dmin_g; a.argmin_l = argmin_l;
     a.Wl = Wl; a.Wg = Wg; a.labels = labels;
     a.logits = logits; a.logits_g = logits_g; a.logits_l = logits_l; a.losses = losses; a.dlogits = dlogits;
+    a.losses_mirror = losses_mirror;
     a.g_l = g_l; a.g_g = g_g; a.pairT = reinterpret_cast<float2*>(pairT);
     a.part = w.part; a.dlT = w.dlT; a.ce_part = w.ce_part; a.ppc_part = w.ppc_part; a.ppc_losses = w.ppc_losses;
     a.ctr = w.ctr;

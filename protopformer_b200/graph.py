@@ -80,7 +80,7 @@ class GraphedHeadStep:
                 self.grads = dict(zip(("P", "Pg", "Wa", "ba"), self.reducer.views))
 
     # --------------------------------------------------------------------------------------------------------
-    def _step_fused(self, slot: int):
+    def _step_fused(self, slot: int, **extra):
         p, f = self.p, self.fused
         works = []
         hook = None
@@ -103,6 +103,7 @@ class GraphedHeadStep:
                     works.append(w)
         with torch.no_grad():
             kw = dict(reduce_hook=hook) if hook is not None else {}
+            kw.update(extra)
             f.step(self.tokens[slot], self.scores[slot], self.labels[slot], p["Wa"], p["ba"], p["P"], p["Pg"],
                    p["Wl"], p["Wg"], self.grads if self.train else None, **kw)
         for w in works:
@@ -163,6 +164,42 @@ class GraphedHeadStep:
             self.tokens[slot].copy_(tokens, non_blocking=True)
             self.scores[slot].copy_(scores, non_blocking=True)
             self.labels[slot].copy_(labels, non_blocking=True)
+
+    def capture_host_pipeline(self):
+        """Second set of step graphs for callers that feed the slots through load_host(): the step takes the selected-token
+        list the transfer already computed (no selection launch of its own) and the kernel that completes the loss also
+        stores (total, ce, ppc_cov, ppc_mean) into `self.loss_host[slot]` (pinned host memory) -- the caller's device->host
+        read of the result costs no copy node and no stream round trip.  Replay with run_host(slot)."""
+        assert self.fused is not None and self.impl == "v2", "host pipeline graphs need the v2 step"
+        dev = self.tokens[0].device
+        if not hasattr(self, "_load_idx"):
+            self._load_idx = [torch.empty(self.B, self.cfg.K, dtype=torch.int32, device=dev) for _ in self.tokens]
+        self.loss_host = [torch.zeros(4).pin_memory() for _ in self.tokens]
+        self.graphs_host = []
+        ctx = torch.enable_grad() if self.train else torch.no_grad()
+        with ctx:
+            for slot in range(len(self.tokens)):
+                extra = dict(idx32=self._load_idx[slot], loss_mirror=self.loss_host[slot].data_ptr())
+                from . import _lib
+                with torch.no_grad():                     # a valid index list for the eager warm-up below
+                    _lib.call("pph_select_topk", self.scores[slot], self.B,
+                              self.scores[slot].shape[1] if self.scores[slot].dim() == 3 else 1, self.N, self.cfg.K,
+                              self._load_idx[slot], None)
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    self._step_fused(slot, **extra)
+                torch.cuda.current_stream().wait_stream(side)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self._step_fused(slot, **extra)
+                self.graphs_host.append(g)
+        return self
+
+    def run_host(self, slot: int = 0):
+        self.graphs_host[slot].replay()
+        return self.loss_host[slot]
 
     def load_host(self, slot: int, tokens, scores, labels, n_ctas: int = 48):
         """Selection-first transfer of one batch from PINNED host tensors (current stream): scores and labels by copy,

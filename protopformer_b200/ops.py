@@ -765,10 +765,17 @@ class FusedHeadStep:
                 self.dtokens.zero_()
 
 
-    def step(self, tokens, scores, labels, Wa, ba, P, Pg, Wl, Wg, grads=None, upstream: float = 1.0, reduce_hook=None):
+    def step(self, tokens, scores, labels, Wa, ba, P, Pg, Wl, Wg, grads=None, upstream: float = 1.0, reduce_hook=None,
+             idx32=None, loss_mirror=None):
         """reduce_hook(which): called once with "protos" when grads["P"], grads["Pg"] are final (on the stream that
         produced them) and once with "addon" after grads["Wa"], grads["ba"]: the data-parallel caller issues its
-        asynchronous all-reduces there so that the first one overlaps the add-on backward."""
+        asynchronous all-reduces there so that the first one overlaps the add-on backward.
+        idx32: the ascending selected-token list (B,K) if the caller already ranked this batch's scores (the
+        selection-first host transfer does): the step then skips its own selection launch and `self.idx32` is not
+        updated.  loss_mirror: address of 4 floats (16-byte aligned, e.g. mapped pinned host memory) that receive
+        (total, ce, ppc_cov, ppc_mean) straight from the kernel that completes the loss."""
+        own_idx = self.idx32  # noqa: F841
+        sel_idx = own_idx if idx32 is None else idx32
         B, N, Din, D, Pn, Pgn, C, m, H = self.dims
         cfg, K = self.cfg, self.cfg.K
         c = _lib.call
@@ -784,8 +791,9 @@ class FusedHeadStep:
                 if self.train and self.variants["addon_bwd"] == "tc":
                     self.dtokens.zero_()            # rows of unselected tokens: a memset node off the critical path
                 ev[4].record(side)
-            c("pph_select_topk", scores, B, max(H, 1), N, K, self.idx32, None)
-            c("pph_addon_fwd2", tokens, self.idx32, Wa, ba, B, N, Din, D, K, self.Zs, self.Zc, self.z2s, self.z2c,
+            if idx32 is None:
+                c("pph_select_topk", scores, B, max(H, 1), N, K, sel_idx, None)
+            c("pph_addon_fwd2", tokens, sel_idx, Wa, ba, B, N, Din, D, K, self.Zs, self.Zc, self.z2s, self.z2c,
               float(cfg.center), self.z2s_ctr, self.z2c_ctr, self.z2s_hi, self.z2c_hi, self.Zs_hi, self.Zs_lo,
               self.Zc_hi, self.Zc_lo, self.ws_tc)
             main.wait_event(ev[4])
@@ -796,7 +804,7 @@ class FusedHeadStep:
                 with torch.cuda.stream(side):
                     self.dtokens.zero_()
                     ev[4].record(side)
-            c("pph_head_prep", scores, tokens, Wa, ba, B, max(H, 1), N, Din, D, K, float(cfg.center), self.idx32, None,
+            c("pph_head_prep", scores, tokens, Wa, ba, B, max(H, 1), N, Din, D, K, float(cfg.center), sel_idx, None,
               self.Zs, self.Zc, self.z2s, self.z2c, self.z2s_ctr, self.z2c_ctr, self.z2s_hi, self.z2c_hi,
               self.Zs_hi, self.Zs_lo, self.Zc_hi, self.Zc_lo,
               P, Pn, self.P_hi, self.P_lo, self.p2, self.p2_ctr, self.p2_hi,
@@ -823,11 +831,11 @@ class FusedHeadStep:
         def mid(use_ppc):
             c("pph_head_mid", self.act_l, self.act_g, self.dmin_l, self.dmin_g, self.argmin, Wl, Wg, labels,
               B, K, D, Pn, Pgn, C, m, N, float(cfg.global_coe), cfg.act_id, float(cfg.eps), float(upstream),
-              1 if self.train else 0, use_ppc, self.Zs, self.z2s, P, self.p2, self.idx32,
+              1 if self.train else 0, use_ppc, self.Zs, self.z2s, P, self.p2, sel_idx,
               float(cfg.ppc_cov_thresh), float(cfg.ppc_mean_thresh), self.cov_coe, self.mean_coe,
               self.ws_mid, self.ws_bins, self.logits, self.logits_g, self.logits_l, self.losses, self.dlogits,
               self.g_l, self.g_g, self.pairT if vr["bwd"] == "staged" else None, self.dZs_ppc if ppc else None,
-              self.dP_img if ppc else None)
+              self.dP_img if ppc else None, loss_mirror)
 
         if split_ppc:        # PPC loss forward + backward as a concurrent branch beside the last layers
             ev[0].record(main)
@@ -893,11 +901,11 @@ class FusedHeadStep:
             # token gradient (82 CTAs) then weight gradient (112 CTAs behind a grid barrier): both want one CTA per SM, as
             # graph branches they only time-slice the machine (measured), so they run back to back
             def dgrad():
-                c("pph_addon_bwd3", 2, tokens, self.idx32, Wa, self.dZs, self.dZc, dpre_add, B, N, Din, D, K, self.ws_tc,
+                c("pph_addon_bwd3", 2, tokens, sel_idx, Wa, self.dZs, self.dZc, dpre_add, B, N, Din, D, K, self.ws_tc,
                   None, None, self.dtokens)
 
             def wgrad():
-                c("pph_addon_bwd3", 1, tokens, self.idx32, Wa, self.dZs, self.dZc, dpre_add, B, N, Din, D, K, self.ws_tc,
+                c("pph_addon_bwd3", 1, tokens, sel_idx, Wa, self.dZs, self.dZc, dpre_add, B, N, Din, D, K, self.ws_tc,
                   grads["Wa"], grads["ba"], None)
 
             if reduce_hook is not None:     # weight gradient first: its exchange then runs under the token gradient
@@ -913,7 +921,7 @@ class FusedHeadStep:
                 dgrad()
                 wgrad()
         else:
-            c("pph_addon_bwd2", 3, tokens, self.idx32, Wa, self.dZs, self.dZc, B, N, Din, D, K,
+            c("pph_addon_bwd2", 3, tokens, sel_idx, Wa, self.dZs, self.dZc, B, N, Din, D, K,
               self.ws_addon, grads["Wa"], grads["ba"], self.dtokens)
             hook("addon")
         main.wait_event(ev[1])

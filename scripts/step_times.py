@@ -109,7 +109,7 @@ for impl, variants in ARMS:
                       C, m, N, float(cfg.global_coe), cfg.act_id, float(cfg.eps), 1.0, train_, ppc_, f.Zs, f.z2s, p["P"],
                       f.p2, f.idx32, float(cfg.ppc_cov_thresh), float(cfg.ppc_mean_thresh), 0.1, 0.5, f.ws_mid, f.ws_bins,
                       f.logits, f.logits_g, f.logits_l, f.losses, f.dlogits, f.g_l, f.g_g, f.pairT,
-                      f.dZs_ppc if ppc_ else None, f.dP_img if ppc_ else None)
+                      f.dZs_ppc if ppc_ else None, f.dP_img if ppc_ else None, None)
                 per["head_mid"] = timed_graph(lambda: mid(1, 1))
                 per["head_mid(no ppc)"] = timed_graph(lambda: mid(1, 0))
                 per["head_mid(eval)"] = timed_graph(lambda: mid(0, 0))

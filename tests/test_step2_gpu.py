@@ -151,7 +151,7 @@ def _run_mid(shape, d, cfg, idx, tf, pl, dmin_l, argmin, act_l, dmin_g, act_g, t
                1 if train else 0, 1 if use_ppc else 0, tf.Zs, tf.z2s, d["P"].reshape(P, -1), pl.p2, idx,
                float(cfg.ppc_cov_thresh), float(cfg.ppc_mean_thresh), 0.1, 0.5, o["ws"], o["bins"],
                o["logits"], o["logits_g"], o["logits_l"], o["losses"], o["dlogits"], o["g_l"], o["g_g"], o["pairT"],
-               o["dZs_ppc"] if use_ppc else None, o["dP_img"] if use_ppc else None)
+               o["dZs_ppc"] if use_ppc else None, o["dP_img"] if use_ppc else None, None)
     torch.cuda.synchronize()
     return o
 
@@ -592,6 +592,14 @@ def test_selection_first_host_transfer_feeds_the_same_step():
     for a, b in zip(want, got):
         assert torch.equal(a, b)
     from protopformer_b200 import _lib as L
+    # the host pipeline graphs: selection taken from the transfer, loss mirrored into pinned host memory by the kernel
+    step.capture_host_pipeline()
+    step.load_host(0, host["tokens"], host["scores"], host["labels"])
+    lh = step.run_host(0)
+    torch.cuda.synchronize()
+    assert torch.equal(lh, want[0].cpu())
+    for a, b in zip(want[1:], (step.fused.dtokens, params["P"].grad, params["Wa"].grad)):
+        assert torch.equal(a, b)
     with pytest.raises(RuntimeError):                                  # pageable memory is refused, not copied silently
         L.call("pph_gather_rows_host", case["tokens"].data_ptr(), step._load_idx[0], shape.B, shape.N, shape.Din, shape.K,
                step.tokens[0].detach(), 8)
