@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define PPH_VERSION 201
+#define PPH_VERSION 202
 
 /* argument errors */
 #define PPH_EINVAL   (-1)   /* bad dimension / null pointer */
@@ -352,7 +352,7 @@ int pph_addon_bwd2(int parts, const float* tokens, const int32_t* idx32, const f
  *   pph_addon_bwd3 = pph_addon_bwd2 (inputs dpre_s / dpre_c) on tensor cores; with PPH_ADDON_DGRAD the rows of dtokens
  *   that belong to selected tokens (and the CLS rows) are written, every other row must have been ZERO-FILLED by the
  *   caller; PPH_ADDON_WGRAD reduces its split-k partials in-kernel behind a grid barrier (needs <= SM-count CTAs).
- * pph_addon_tc2_supported: bit 0 forward, bit 1 DGRAD, bit 2 WGRAD can run this shape.  workspace:
+ * pph_addon_tc2_supported: bit 0 forward, bit 1 DGRAD, bit 2 WGRAD, bit 3 pph_select_addon_fwd can run this shape.  workspace:
  * pph_addon_tc2_ws_bytes() bytes, ZERO-FILLED once before first use (shared by the three calls of a step). */
 int pph_addon_tc2_supported(int B, int N, int Din, int D, int K);
 int pph_addon_tc2_ws_bytes(int B, int N, int Din, int D, int K, long long* bytes /* host */);
@@ -362,6 +362,15 @@ int pph_addon_fwd2(const float* tokens, const int32_t* idx32, const float* Wa, c
                    float center, float* z2s_ctr, float* z2c_ctr, float* z2s_hi, float* z2c_hi,
                    uint16_t* Zs_hi, uint16_t* Zs_lo, uint16_t* Zc_hi, uint16_t* Zc_lo,
                    void* workspace, pph_stream_t stream);
+/* Selection + gather + add-on in ONE launch (protopformer.py:157-172): pph_select_topk's ranking (same total order, head
+ * mean over H, NaN first) runs in the prologue of pph_addon_fwd2's kernel -- every CTA ranks the scores of the images its
+ * row tile touches -- and idx32 [B,K] is an OUTPUT.  Same numerics as pph_select_topk followed by pph_addon_fwd2. */
+int pph_select_addon_fwd(const float* scores /* [B,H,N] */, int H, const float* tokens, const float* Wa, const float* ba,
+                         int B, int N, int Din, int D, int K, int32_t* idx32 /* out */,
+                         float* Zs, float* Zc, float* z2s, float* z2c,
+                         float center, float* z2s_ctr, float* z2c_ctr, float* z2s_hi, float* z2c_hi,
+                         uint16_t* Zs_hi, uint16_t* Zs_lo, uint16_t* Zc_hi, uint16_t* Zc_lo,
+                         void* workspace, pph_stream_t stream);
 int pph_addon_bwd3(int parts, const float* tokens, const int32_t* idx32, const float* Wa,
                    const float* dpre_s, const float* dpre_c, const float* dpre_add_s /* [B,K,D] added to dpre_s, or NULL */,
                    int B, int N, int Din, int D, int K, void* workspace,

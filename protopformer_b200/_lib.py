@@ -62,6 +62,7 @@ SIGNATURES = {
     "pph_addon_tc2_ws_bytes": [_i, _i, _i, _i, _i, C.POINTER(C.c_longlong)],
     "pph_addon_fwd2": [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _f] + [_p] * 10,
     "pph_addon_bwd3": [_i] + [_p] * 6 + [_i] * 5 + [_p] * 5,
+    "pph_select_addon_fwd": [_p, _i, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _f] + [_p] * 10,
     "pph_ppc_dense_fwd": [_p, _p, _p, _i, _i, _i, _i, _i, _f, _f, _p, _p, _p, _p, _p],
     "pph_ppc_dense_bwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _f, _p, _p],
     "pph_gather_rows_host": [_p, _p, _i, _i, _i, _i, _p, _i, _p],
@@ -77,7 +78,7 @@ KERNELS_PER_CALL = {
     "pph_ppc_bwd": 1, "pph_logits_bwd": 1, "pph_similarity_bwd": 2, "pph_addon_bwd": 3, "pph_loss_tail": 1, "pph_loss_combine": 1, "pph_rollout_scores": 2, "pph_adamw_step": 1, "pph_class_maps": 1, "pph_rollout_cls_rows": 1,
     "pph_head_prep": 1, "pph_head_mid": 1, "pph_similarity_bwd_fused": 1, "pph_addon_bwd2": 1, "pph_addon_fwd2": 1,
     "pph_peer_allreduce": 1, "pph_gather_rows_host": 1,
-    "pph_ppc_dense_fwd": 1, "pph_ppc_dense_bwd": 1,
+    "pph_ppc_dense_fwd": 1, "pph_ppc_dense_bwd": 1, "pph_select_addon_fwd": 1,
 }
 
 _ENV_OPTIONS = {"PPH_PDL": "pdl", "PPH_SIM_LANES": "sim_lanes", "PPH_SIM_SHARED": "sim_shared", "PPH_SIM_EPI": "sim_epi",

@@ -36,6 +36,91 @@ struct FwdAOp {     // (row = r, k = din): gathered token rows
         if (r < src.R && k0 < src.Din) ld8(tokens + src(r) + k0, v); else zero8(v);
     }
 };
+// Gathered token rows with the SELECTION done by the kernel that consumes it (protopformer.py:157-166 in one launch): every
+// CTA ranks the CLS-attention scores of the (<= 4) images its 128-row tile touches -- rank by counting with the same
+// total order as select_topk_kernel (larger score first, lower index on ties, NaN first) -- and keeps the ascending index
+// lists in shared memory; the CTAs of the first column tile also write them to idx_out for the kernels downstream.
+struct FwdSelAOp {
+    static constexpr bool kContigK = true;
+    static constexpr bool kSelect = true;
+    const float* tokens;
+    const float* scores;       // [B, H, N]
+    int32_t* idx_out;          // [B, K]
+    int B, N, Din, K, R, H;
+    __host__ __device__ static int images_per_tile(int K) { return 127 / (K + 1) + 2; }
+    __host__ __device__ static int words(int N, int K) { return images_per_tile(K) * (((N + 3) & ~3) + 8 + K); }
+    __device__ __forceinline__ void prologue(int m0, int* smi, bool write_out) const {
+        const int tid = threadIdx.x, lane = tid & 31, nthr = blockDim.x;
+        const int b_lo = m0 / (K + 1), b_hi = min(m0 + 127, R - 1) / (K + 1), n_here = b_hi - b_lo + 1;
+        const int nimg = images_per_tile(K), Np = (N + 3) & ~3, N32 = (N + 31) & ~31;
+        float* sc = reinterpret_cast<float*>(smi);            // [nimg][Np]  fused scores (-inf padding)
+        int* cnt = smi + nimg * Np;                           // [nimg][8]   selected tokens per 32-token group
+        int* sidx = cnt + nimg * 8;                           // [nimg][K]   ascending selected tokens
+        for (int w = tid; w < n_here * Np; w += nthr) {
+            const int i = w / Np, n = w - i * Np;
+            float v = -INFINITY;
+            if (n < N) {
+                const float* row = scores + (size_t)(b_lo + i) * H * N;
+                float a = row[n];
+                for (int h = 1; h < H; ++h) a += row[(size_t)h * N + n];
+                v = H > 1 ? a / (float)H : a;
+                if (v != v) v = INFINITY;
+            }
+            sc[i * Np + n] = v;
+        }
+        __syncthreads();
+        const int items = n_here * N32;                       // warp-aligned: 32-token groups never straddle images
+        bool sel[2] = {false, false};
+        unsigned mask[2] = {0u, 0u};
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int w = tid + p * nthr;
+            if (w < items) {
+                const int i = w / N32, n = w - i * N32;
+                if (n < N) {
+                    const float v = sc[i * Np + n];
+                    const float4* s4 = reinterpret_cast<const float4*>(sc + i * Np);
+                    int rank = 0;
+                    for (int j = 0; j < Np; j += 4) {
+                        const float4 q = s4[j >> 2];
+                        rank += (q.x > v) || (q.x == v && j + 0 < n);
+                        rank += (q.y > v) || (q.y == v && j + 1 < n);
+                        rank += (q.z > v) || (q.z == v && j + 2 < n);
+                        rank += (q.w > v) || (q.w == v && j + 3 < n);
+                    }
+                    sel[p] = rank < K;
+                }
+                mask[p] = __ballot_sync(0xffffffffu, sel[p]);
+                if (lane == 0) cnt[i * 8 + (n >> 5)] = __popc(mask[p]);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            const int w = tid + p * nthr;
+            if (w < items && sel[p]) {
+                const int i = w / N32, n = w - i * N32;
+                int pos = __popc(mask[p] & ((1u << lane) - 1u));
+                for (int g = 0; g < (n >> 5); ++g) pos += cnt[i * 8 + g];
+                if (pos < K) {
+                    sidx[i * K + pos] = n;
+                    if (write_out) idx_out[(size_t)(b_lo + i) * K + pos] = n;
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ void load8(int r, int k0, float (&v)[8], int m0, const int* smi) const {
+        if (r < R && k0 < Din) {
+            const int b = r / (K + 1), j = r - b * (K + 1);
+            const int nimg = images_per_tile(K), Np = (N + 3) & ~3;
+            const int* sidx = smi + nimg * (Np + 8);
+            const int tok = j < K ? 1 + sidx[(b - m0 / (K + 1)) * K + j] : 0;
+            ld8(tokens + ((long)b * (1 + N) + tok) * Din + k0, v);
+        } else {
+            zero8(v);
+        }
+    }
+};
 struct FwdBOp {     // (row = n, k = din): Wa[n, din]
     static constexpr bool kContigK = true;
     const float* Wa;

@@ -251,7 +251,8 @@ extern "C" int pph_addon_tc2_supported(int B, int N, int Din, int D, int K) {
     using namespace pph;
     if (B < 1 || N < 1 || K < 1 || K > N || B * (K + 1) > 1008 * kTsBM) return 0;
     const Tc2Plan p = tc2_plan(B, Din, D, K, 148);
-    return (p.fwd_ok ? 1 : 0) | (p.dx_ok ? 2 : 0) | (p.w_ok ? 4 : 0);
+    const bool sel_ok = p.fwd_ok && N <= 256 && FwdSelAOp::words(N, K) <= 128 * 16;
+    return (p.fwd_ok ? 1 : 0) | (p.dx_ok ? 2 : 0) | (p.w_ok ? 4 : 0) | (sel_ok ? 8 : 0);
 }
 
 extern "C" int pph_addon_tc2_ws_bytes(int B, int N, int Din, int D, int K, long long* bytes) {
@@ -283,6 +284,30 @@ extern "C" int pph_addon_fwd2(const float* tokens, const int32_t* idx32, const f
     e.npart = w.npart; e.cnt = w.fwd_cnt; e.Rpad = ceil_div(R, kTsBM) * kTsBM;
     return launch_tcshot(R, D, Din, p.bn_fwd, ceil_div(Din, kTsBK) * kTsBK, w.sync_ctr, a, b, e, as_stream(stream),
                          "pph_addon_fwd2(tcgen05 single shot)");
+}
+
+extern "C" int pph_select_addon_fwd(const float* scores, int H, const float* tokens, const float* Wa, const float* ba,
+                                    int B, int N, int Din, int D, int K, int32_t* idx32,
+                                    float* Zs, float* Zc, float* z2s, float* z2c,
+                                    float center, float* z2s_ctr, float* z2c_ctr, float* z2s_hi, float* z2c_hi,
+                                    uint16_t* Zs_hi, uint16_t* Zs_lo, uint16_t* Zc_hi, uint16_t* Zc_lo,
+                                    void* workspace, pph_stream_t stream) {
+    using namespace pph;
+    PPH_REQUIRE(scores && tokens && idx32 && Wa && ba && Zs && Zc && z2s && z2c && workspace, PPH_EINVAL,
+                "pph_select_addon_fwd: null pointer");
+    PPH_REQUIRE(B >= 1 && H >= 1 && N >= 1 && K >= 1 && K <= N, PPH_EINVAL, "pph_select_addon_fwd: bad dims");
+    const Tc2Plan p = tc2_plan(B, Din, D, K, tc2_sms());
+    PPH_REQUIRE(p.fwd_ok && B * (K + 1) <= 1008 * kTsBM && N <= 256 && FwdSelAOp::words(N, K) <= 128 * 16, PPH_EUNSUP,
+                "pph_select_addon_fwd: N=%d K=%d Din=%d D=%d outside the fused selection + add-on kernel", N, K, Din, D);
+    const int R = B * (K + 1);
+    const Tc2Ws w = tc2_carve(workspace, R);
+    FwdSelAOp a{tokens, scores, idx32, B, N, Din, K, R, H};
+    FwdBOp b{Wa, D, Din};
+    FwdEpi2 e;
+    static_cast<FwdEpi&>(e) = FwdEpi{ba, Zs, Zc, z2s, z2c, z2s_ctr, z2c_ctr, z2s_hi, z2c_hi, Zs_hi, Zs_lo, Zc_hi, Zc_lo, center, K, D};
+    e.npart = w.npart; e.cnt = w.fwd_cnt; e.Rpad = ceil_div(R, kTsBM) * kTsBM;
+    return launch_tcshot(R, D, Din, p.bn_fwd, ceil_div(Din, kTsBK) * kTsBK, w.sync_ctr, a, b, e, as_stream(stream),
+                         "pph_select_addon_fwd(tcgen05 single shot)");
 }
 
 extern "C" int pph_addon_bwd3(int parts, const float* tokens, const int32_t* idx32, const float* Wa,

@@ -45,6 +45,13 @@ struct op_is_quad { static constexpr bool value = false; };
 template <class Op>
 struct op_is_quad<Op, decltype((void)Op::kQuad)> { static constexpr bool value = Op::kQuad; };
 
+// A operands that compute their own row list first (FwdSelAOp): prologue(m0, smem words, write_out) by all threads, then
+// load8(r, k0, v, m0, smem words).  The words live in the epilogue's scratch area, idle until the accumulator is drained.
+template <class Op, class = void>
+struct op_selects { static constexpr bool value = false; };
+template <class Op>
+struct op_selects<Op, decltype((void)Op::kSelect)> { static constexpr bool value = Op::kSelect; };
+
 // Extra epilogue contract on top of pph_tcgemm.cuh's:
 //   static constexpr bool kGridReduce;                       // run reduce() on every CTA after a grid-wide barrier
 //   __device__ void reduce(int cta, int n_ctas, int tid, int nthreads) const;
@@ -81,6 +88,11 @@ tcshot_kernel(int M, int N, int Kd, int BN, int k_per_split, unsigned int* sync_
         rowptr[(tid - 128) * 3 + 0] = p3[0]; rowptr[(tid - 128) * 3 + 1] = p3[1]; rowptr[(tid - 128) * 3 + 2] = p3[2];
     }
 
+    if constexpr (op_selects<AOp>::value) {
+        a_op.prologue(m0, reinterpret_cast<int*>(scratch), blockIdx.y == 0 && blockIdx.z == 0);
+        __syncthreads();
+    }
+
     // ---- fill: k-block kb+1's global loads are in flight while k-block kb is converted and stored -------------------
     constexpr bool kAQ = op_is_quad<AOp>::value, kBQ = op_is_quad<BOp>::value;
     const int nbg = BN * 8;                                  // B groups of 8 k per k-block (<= 1024: two per thread)
@@ -112,8 +124,14 @@ tcshot_kernel(int M, int N, int Kd, int BN, int k_per_split, unsigned int* sync_
                 const int g = tid + i * kTsThreads;
                 const int row = AOp::kContigK ? (g >> 3) : (g & (kTsBM - 1));
                 const int c = AOp::kContigK ? (g & 7) : (g >> 7);
-                if (k0 + c * 8 < kz1) a_op.load8(m0 + row, k0 + c * 8, va[set][i]);
-                else zero8v(va[set][i]);
+                if (k0 + c * 8 < kz1) {
+                    if constexpr (op_selects<AOp>::value)
+                        a_op.load8(m0 + row, k0 + c * 8, va[set][i], m0, reinterpret_cast<const int*>(scratch));
+                    else
+                        a_op.load8(m0 + row, k0 + c * 8, va[set][i]);
+                } else {
+                    zero8v(va[set][i]);
+                }
             }
         }
         if constexpr (kBQ) {

@@ -710,8 +710,11 @@ class FusedHeadStep:
         # last layers AND the token-side gradients (its token gradient enters through the add-on backward's operand,
         # its prototype rows through the prototype-row launch on the same side branch)
         v = {"prep": "tc" if (tc_bits & 1) else "simt",
-             "addon_bwd": "tc" if (tc_bits & 6) == 6 else "simt", "bwd": "gather", "ppc": "late"}
+             "addon_bwd": "tc" if (tc_bits & 6) == 6 else "simt", "bwd": "gather", "ppc": "late",
+             "select": "fused" if (tc_bits & 8) else "kernel"}
         v.update(variants or {})
+        if v["select"] == "fused" and not (tc_bits & 8):
+            v["select"] = "kernel"
         if v["prep"] == "tc" and not (tc_bits & 1):
             v["prep"] = "simt"
         if v["addon_bwd"] == "tc" and (tc_bits & 6) != 6:
@@ -791,11 +794,17 @@ class FusedHeadStep:
                 if self.train and self.variants["addon_bwd"] == "tc":
                     self.dtokens.zero_()            # rows of unselected tokens: a memset node off the critical path
                 ev[4].record(side)
-            if idx32 is None:
-                c("pph_select_topk", scores, B, max(H, 1), N, K, sel_idx, None)
-            c("pph_addon_fwd2", tokens, sel_idx, Wa, ba, B, N, Din, D, K, self.Zs, self.Zc, self.z2s, self.z2c,
-              float(cfg.center), self.z2s_ctr, self.z2c_ctr, self.z2s_hi, self.z2c_hi, self.Zs_hi, self.Zs_lo,
-              self.Zc_hi, self.Zc_lo, self.ws_tc)
+            if idx32 is None and self.variants["select"] == "fused":
+                # the ranking runs in the add-on kernel's prologue: one launch for protopformer.py:157-172
+                c("pph_select_addon_fwd", scores, max(H, 1), tokens, Wa, ba, B, N, Din, D, K, sel_idx, self.Zs, self.Zc,
+                  self.z2s, self.z2c, float(cfg.center), self.z2s_ctr, self.z2c_ctr, self.z2s_hi, self.z2c_hi, self.Zs_hi,
+                  self.Zs_lo, self.Zc_hi, self.Zc_lo, self.ws_tc)
+            else:
+                if idx32 is None:
+                    c("pph_select_topk", scores, B, max(H, 1), N, K, sel_idx, None)
+                c("pph_addon_fwd2", tokens, sel_idx, Wa, ba, B, N, Din, D, K, self.Zs, self.Zc, self.z2s, self.z2c,
+                  float(cfg.center), self.z2s_ctr, self.z2c_ctr, self.z2s_hi, self.z2c_hi, self.Zs_hi, self.Zs_lo,
+                  self.Zc_hi, self.Zc_lo, self.ws_tc)
             main.wait_event(ev[4])
         else:
             if self.train and self.variants["addon_bwd"] == "tc":

@@ -33,7 +33,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
         assert name in _lib.SIGNATURES, f"{name} has no ctypes signature"
         assert len(_lib.SIGNATURES[name]) == nargs, f"{name}: header has {nargs} args, binding {len(_lib.SIGNATURES[name])}"
     assert set(_lib.SIGNATURES) == set(decl)
-    assert lib.pph_version() == 201
+    assert lib.pph_version() == 202
 
 
 def test_sass_contains_blackwell_tensor_and_tma_instructions():

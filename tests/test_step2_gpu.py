@@ -369,6 +369,47 @@ def test_addon_fwd2_single_shot_matches_oracle(key, seed):
     assert rel_close(o["z2c_hi"].cpu(), (o["Zc_hi"].float() ** 2).sum(-1).cpu(), 1e-5)
 
 
+@pytest.mark.parametrize("key,seed,heads", [(k, s, 0) for k, s in TC2_CASES] + [("cub_b8", 5, 3), ("cub_b64", 6, 6)])
+def test_fused_selection_addon_forward_equals_the_two_launches(key, seed, heads):
+    """pph_select_addon_fwd = pph_select_topk (bit-exact index lists, ties and NaN included) + pph_addon_fwd2 (bitwise the
+    same features, operands and norms: same arithmetic, the row list just comes from shared memory)."""
+    ops, L = _ops(), _lib()
+    shape = synth.SHAPES[key]
+    case = synth.make_case(shape, seed=seed, heads=heads)
+    d = _d(case)
+    B, N, Din, D, K = shape.B, shape.N, shape.Din, shape.D, shape.K
+    assert L.load().pph_addon_tc2_supported(B, N, Din, D, K) & 8
+    scores = d["scores_h"] if heads else d["scores"].clone()
+    if not heads:                      # ties and a NaN: the ranking rule must be the select kernel's
+        scores[0, 5] = scores[0, 9]
+        scores[1 % B, 7] = float("nan")
+        scores[B - 1, :4] = scores[B - 1, 4]
+    idx = ops.select_topk(scores, K)                 # (held to the oracle / torch.topk, ties and NaN, in test_gpu_parity.py)
+    if heads:
+        assert torch.equal(idx.cpu().long(), O.select_tokens(scores.cpu(), K))
+    bf = torch.bfloat16
+
+    def outs():
+        return dict(Zs=_e(B, K, D), Zc=_e(B, D), z2s=_e(B, K), z2c=_e(B), z2s_ctr=_e(B, K), z2c_ctr=_e(B), z2s_hi=_e(B, K),
+                    z2c_hi=_e(B), Zs_hi=_e(B * K, D, dt=bf), Zs_lo=_e(B * K, D, dt=bf), Zc_hi=_e(B, D, dt=bf),
+                    Zc_lo=_e(B, D, dt=bf))
+    a, b = outs(), outs()
+    ws = ops._ws("pph_addon_tc2_ws_bytes", B, N, Din, D, K, zero=True, device=DEV)
+    L.call("pph_addon_fwd2", d["tokens"], idx, d["Wa"].reshape(D, Din), d["ba"], B, N, Din, D, K, a["Zs"], a["Zc"],
+           a["z2s"], a["z2c"], 0.5, a["z2s_ctr"], a["z2c_ctr"], a["z2s_hi"], a["z2c_hi"], a["Zs_hi"], a["Zs_lo"],
+           a["Zc_hi"], a["Zc_lo"], ws)
+    idx2 = torch.full((B, K), -1, dtype=torch.int32, device=DEV)
+    for _ in range(2):
+        L.call("pph_select_addon_fwd", scores, max(heads, 1), d["tokens"], d["Wa"].reshape(D, Din), d["ba"], B, N, Din, D, K,
+               idx2, b["Zs"], b["Zc"], b["z2s"], b["z2c"], 0.5, b["z2s_ctr"], b["z2c_ctr"], b["z2s_hi"], b["z2c_hi"],
+               b["Zs_hi"], b["Zs_lo"], b["Zc_hi"], b["Zc_lo"], ws)
+    torch.cuda.synchronize()
+    assert torch.equal(idx2, idx)
+    for k in a:
+        assert torch.equal(a[k].view(torch.int16 if a[k].dtype == bf else torch.int32),
+                           b[k].view(torch.int16 if b[k].dtype == bf else torch.int32)), k
+
+
 @pytest.mark.parametrize("key,seed", TC2_CASES)
 def test_addon_bwd3_single_shot_matches_float64(key, seed):
     ops, L = _ops(), _lib()
@@ -401,12 +442,12 @@ def test_addon_bwd3_single_shot_matches_float64(key, seed):
         assert norm_rel(dba.cpu(), dpre.sum((0, 1))) < 2e-5
 
 
-_S = dict(prep="simt", addon_bwd="simt", bwd="staged", ppc="inline")
-_T = dict(prep="tc", addon_bwd="tc", bwd="gather", ppc="late")
+_S = dict(prep="simt", addon_bwd="simt", bwd="staged", ppc="inline", select="kernel")
+_T = dict(prep="tc", addon_bwd="tc", bwd="gather", ppc="late", select="fused")
 
 
 @pytest.mark.parametrize("variants", [_S, _T, dict(_T, ppc="inline"), dict(_T, ppc="split"), dict(_T, bwd="staged", ppc="split"), dict(_S, bwd="gather"),
-                                      dict(_S, ppc="split"), dict(_T, prep="simt"), dict(_T, addon_bwd="simt")])
+                                      dict(_S, ppc="split"), dict(_T, prep="simt"), dict(_T, addon_bwd="simt"), dict(_T, select="kernel")])
 def test_step_variants_agree_with_the_oracle(variants):
     shape, case, g, fn = load_golden("cub_b8_s1")
     step, params = _make_step(shape, case, "fp32", variants=variants)
