@@ -79,15 +79,7 @@ struct FwdSelAOp {
                 const int i = w / N32, n = w - i * N32;
                 if (n < N) {
                     const float v = sc[i * Np + n];
-                    const float4* s4 = reinterpret_cast<const float4*>(sc + i * Np);
-                    int rank = 0;
-                    for (int j = 0; j < Np; j += 4) {
-                        const float4 q = s4[j >> 2];
-                        rank += (q.x > v) || (q.x == v && j + 0 < n);
-                        rank += (q.y > v) || (q.y == v && j + 1 < n);
-                        rank += (q.z > v) || (q.z == v && j + 2 < n);
-                        rank += (q.w > v) || (q.w == v && j + 3 < n);
-                    }
+                    const int rank = rank_by_count(reinterpret_cast<const float4*>(sc + i * Np), n, Np, v);
                     sel[p] = rank < K;
                 }
                 mask[p] = __ballot_sync(0xffffffffu, sel[p]);

@@ -86,6 +86,30 @@ inline cudaError_t opt_in_smem(K kern, size_t bytes) {
 // caller's isfinite(loss) check, tools/engine_proto.py:68-70)
 __device__ __forceinline__ float relu_keep_nan(float x) { return x < 0.0f ? 0.0f : x; }
 
+// Rank of element n of a score row in the selection order (larger first, lower index first on equal scores): the number of
+// elements that beat it.  `s4` = the row in shared memory, padded to a multiple of 4 with -inf; v = s[n], never NaN (NaN is
+// canonicalised to +inf when the row is staged).  Elements before n beat it when >=, elements after n when >: one compare
+// per element instead of the (>, ==, index) triple.
+__device__ __forceinline__ int rank_by_count(const float4* s4, int n, int n_pad, float v) {
+    int rank = 0;
+    const int nq = n >> 2;
+    for (int j = 0; j < nq; ++j) {
+        const float4 q = s4[j];
+        rank += (q.x >= v) + (q.y >= v) + (q.z >= v) + (q.w >= v);
+    }
+    {
+        const float4 q = s4[nq];
+        const int r = n & 3;
+        rank += (r > 0 ? q.x >= v : false) + (r > 1 ? q.y >= v : (r < 1 && q.y > v)) +
+                (r > 2 ? q.z >= v : (r < 2 && q.z > v)) + (r < 3 && q.w > v);
+    }
+    for (int j = nq + 1; j < (n_pad >> 2); ++j) {
+        const float4 q = s4[j];
+        rank += (q.x > v) + (q.y > v) + (q.z > v) + (q.w > v);
+    }
+    return rank;
+}
+
 // First statement of every kernel (see launch_k): let the dependent grid start its prologue, then wait for the
 // prerequisite grids.  Both are no-ops for a launch without the programmatic attribute.
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

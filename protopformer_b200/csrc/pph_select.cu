@@ -41,15 +41,7 @@ select_topk_kernel(const float* __restrict__ scores, int H, int N, int K,
         bool sel = false;
         if (n < N) {
             const float v = s[n];
-            int rank = 0;
-            const float4* s4 = reinterpret_cast<const float4*>(s);
-            for (int j = 0; j < Npad; j += 4) {
-                const float4 q = s4[j >> 2];           // broadcast read
-                rank += (q.x > v) || (q.x == v && j + 0 < n);
-                rank += (q.y > v) || (q.y == v && j + 1 < n);
-                rank += (q.z > v) || (q.z == v && j + 2 < n);
-                rank += (q.w > v) || (q.w == v && j + 3 < n);
-            }
+            const int rank = rank_by_count(reinterpret_cast<const float4*>(s), n, Npad, v);
             sel = rank < K;
         }
         const unsigned m = __ballot_sync(0xffffffffu, sel);

@@ -709,13 +709,18 @@ class FusedHeadStep:
         # "split" = its own concurrent launch joined before the backward, "late" = concurrent launch that overlaps the
         # last layers AND the token-side gradients (its token gradient enters through the add-on backward's operand,
         # its prototype rows through the prototype-row launch on the same side branch)
-        v = {"prep": "tc" if (tc_bits & 1) else "simt",
+        # "prep": "tc" = single-shot tcgen05 add-on forward (k range resident: Din <= 192), "tc1" = the pipelined tcgen05 kernel
+        # of round 1 (any Din % 8 == 0: DeiT-S / Dogs, Din = 384), "simt" = exact-FP32 CUDA-core kernel
+        tc1_ok = Din % 8 == 0 and D % 8 == 0 and cfg.mode_id != _lib.MODE_FP32_FMA
+        v = {"prep": "tc" if (tc_bits & 1) else ("tc1" if tc1_ok else "simt"),
              "addon_bwd": "tc" if (tc_bits & 6) == 6 else "simt", "bwd": "gather", "ppc": "late",
              "select": "fused" if (tc_bits & 8) else "kernel"}
         v.update(variants or {})
         if v["select"] == "fused" and not (tc_bits & 8):
             v["select"] = "kernel"
         if v["prep"] == "tc" and not (tc_bits & 1):
+            v["prep"] = "tc1" if tc1_ok else "simt"
+        if v["prep"] == "tc1" and not tc1_ok:
             v["prep"] = "simt"
         if v["addon_bwd"] == "tc" and (tc_bits & 6) != 6:
             v["addon_bwd"] = "simt"
@@ -784,8 +789,8 @@ class FusedHeadStep:
         c = _lib.call
         main, side, side2, ev = torch.cuda.current_stream(), self.side, self.side2, self.ev
         hook = reduce_hook or (lambda which: None)
-        if self.variants["prep"] == "tc":
-            # selection -> single-shot tcgen05 add-on || operand split of both prototype tensors (side branch)
+        if self.variants["prep"] in ("tc", "tc1"):
+            # selection -> tcgen05 add-on || operand split of both prototype tensors (side branch)
             ev[3].record(main)
             side.wait_event(ev[3])
             with torch.cuda.stream(side):
@@ -794,7 +799,13 @@ class FusedHeadStep:
                 if self.train and self.variants["addon_bwd"] == "tc":
                     self.dtokens.zero_()            # rows of unselected tokens: a memset node off the critical path
                 ev[4].record(side)
-            if idx32 is None and self.variants["select"] == "fused":
+            if self.variants["prep"] == "tc1":
+                if idx32 is None:
+                    c("pph_select_topk", scores, B, max(H, 1), N, K, sel_idx, None)
+                c("pph_addon_fwd", tokens, sel_idx, Wa, ba, B, N, Din, D, K, self.Zs, self.Zc, self.z2s, self.z2c,
+                  float(cfg.center), self.z2s_ctr, self.z2c_ctr, self.z2s_hi, self.z2c_hi, self.Zs_hi, self.Zs_lo,
+                  self.Zc_hi, self.Zc_lo)
+            elif idx32 is None and self.variants["select"] == "fused":
                 # the ranking runs in the add-on kernel's prologue: one launch for protopformer.py:157-172
                 c("pph_select_addon_fwd", scores, max(H, 1), tokens, Wa, ba, B, N, Din, D, K, sel_idx, self.Zs, self.Zc,
                   self.z2s, self.z2c, float(cfg.center), self.z2s_ctr, self.z2c_ctr, self.z2s_hi, self.z2c_hi, self.Zs_hi,

@@ -38,7 +38,7 @@ case $stage in
     echo "== ncuk $k rc=$?"; tail -2 gpurun_out/ncuk_$k.log ;;
   ncufinal)   # --set full capture of every kernel of the shipped step (second eager step) -> profiles/r2_ncu_full_step_kernels.txt
     timeout 900 ncu --set full --clock-control none --import-source on \
-        -k regex:"select_topk|tcshot|similarity_tc2|head_mid|head_ppc|sim_grads|ppc_rows_add|split_rows" -s 11 -c 11 \
+        -k regex:"select_topk|tcshot|similarity_tc2|head_mid|head_ppc|sim_grads|ppc_rows_add|split_rows" -s 10 -c 10 \
         -o gpurun_out/r2_final -f python scripts/run_step.py cub_b64 fp32 v2 3 > gpurun_out/ncufinal.log 2>&1
     echo "== ncufinal rc=$?"; tail -2 gpurun_out/ncufinal.log ;;
   ncu1)       # same capture of the round-1 launch sequence (reference point for the A/B)
