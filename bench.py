@@ -298,16 +298,7 @@ def measure_next_rows(shape, params, dev, peaks):
         L, H, T, B = 11, 3, shape.N + 1, min(shape.B, 64)
         g = torch.Generator(device=dev).manual_seed(0)
         attn = [torch.softmax(2.0 * torch.randn(B, H, T, T, device=dev, generator=g), dim=-1) for _ in range(L)]
-        for _ in range(3):
-            ops.rollout_scores(attn)
-        torch.cuda.synchronize()
-        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        r0.record()
-        for _ in range(10):
-            ops.rollout_scores(attn)
-        r1.record()
-        torch.cuda.synchronize()
-        us = 1e3 * r0.elapsed_time(r1) / 10
+        us = graph_time_us(lambda i: ops.rollout_scores(attn), 4)
         nbytes = float(L * B * H * T * T * 4)
         out["rollout"] = {"kernel": "rollout_prepare2_kernel + rollout_chain2_kernel", "bound": "hbm",
                           "achieved": nbytes / us / 1e3, "peak": peaks["hbm"], "unit": "GB/s",

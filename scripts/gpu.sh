@@ -64,7 +64,7 @@ case $stage in
         bench.py --gpus $n --steps 1000 --warmup 50 --no-extras --exchange nccl > gpurun_out/bench_n${n}_nccl.json 2> gpurun_out/bench_n${n}_nccl.err
     echo "== nccl rc=$?"; tail -c 1200 gpurun_out/bench_n${n}_nccl.json; tail -3 gpurun_out/bench_n${n}_nccl.err ;;
   variants)   # A/B of the two variant switches: rollout normalisation (PPH_ROLLOUT=3) and staged class maps (PPH_CLASSMAP=2)
-    for v in 0 3; do echo "PPH_ROLLOUT=$v"; PPH_ROLLOUT=$v timeout 200 python scripts/rollout_bench.py "11,64,3,197;11,64,6,197" 2>&1 | cut -c1-160 | tail -2; done
+    for v in 0 2; do echo "PPH_ROLLOUT=$v"; PPH_ROLLOUT=$v timeout 200 python scripts/rollout_bench.py "11,64,3,197;11,64,6,197" 2>&1 | cut -c1-160 | tail -2; done
     for v in 1 2; do echo "PPH_CLASSMAP=$v"; PPH_CLASSMAP=$v timeout 200 python scripts/next_rows_bench.py 2>&1 | grep class_maps | cut -c1-200; done ;;
   e2e)
     for e in "" nocopy norows nod2h "nocopy,nosel" "nocopy,nosel,norows"; do EXP=$e timeout 200 python scripts/e2e_timeline.py 32 2 2>&1 | grep "^#"; done
