@@ -137,6 +137,59 @@ struct LbEpi {
     __device__ __forceinline__ void finish(State&, int, int, int, float*, bool) const {}
 };
 
+// ---- backward on CUDA cores, exact FP32 FMA: g[b,p] = (sum_c up[b,c] W[c,p]) * act'(dmin[b,p]).  The tcgen05 version above
+// rounds the upstream gradient to bf16 hi + lo (2^-17 relative per element); the CLS-token gradient then takes
+// Z * sum_p g - sum_p g P, a difference of two sums that nearly cancel, and the rounding came out as 3.5e-4 of the largest
+// token-gradient entry on the CLS rows (scripts/measure_tolerances.py).  This kernel is what the autograd path uses; the
+// graphed step computes the same product in FP32 inside pph_head_mid.  Thread = prototype (coalesced W rows), 8 images per
+// CTA in registers, the upstream rows of those images in shared memory.
+constexpr int kLbfTB = 8, kLbfThreads = 256;
+
+__global__ void __launch_bounds__(kLbfThreads)
+logits_bwd_fma_kernel(const float* __restrict__ dlogits, const float* __restrict__ dlogits_g, const float* __restrict__ dlogits_l,
+                      const float* __restrict__ Wl, const float* __restrict__ Wg, const float* __restrict__ dmin_l,
+                      const float* __restrict__ dmin_g, int B, int P, int Pg, int C, int nbl, float gc, int act_fn, float eps,
+                      float* __restrict__ g_l, float* __restrict__ g_g) {
+    pdl_sync();
+    extern __shared__ float up[];                      // [kLbfTB][C]
+    const bool global = (int)blockIdx.x >= nbl;
+    const int p = ((int)blockIdx.x - (global ? nbl : 0)) * kLbfThreads + threadIdx.x;
+    const int np = global ? Pg : P;
+    const float* W = global ? Wg : Wl;
+    const float* extra = global ? dlogits_g : dlogits_l;
+    const float coef = global ? gc : 1.0f - gc;
+    const int b0 = blockIdx.y * kLbfTB;
+    for (int i = threadIdx.x; i < kLbfTB * C; i += kLbfThreads) {
+        const int bi = i / C, c = i - bi * C;
+        float x = 0.f;
+        if (b0 + bi < B) {
+            const size_t o = (size_t)(b0 + bi) * C + c;
+            x = coef * __ldg(dlogits + o);
+            if (extra) x += __ldg(extra + o);
+        }
+        up[i] = x;
+    }
+    __syncthreads();
+    if (p >= np) return;
+    float acc[kLbfTB];
+#pragma unroll
+    for (int i = 0; i < kLbfTB; ++i) acc[i] = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < C; ++c) {
+        const float w = __ldg(W + (size_t)c * np + p);
+#pragma unroll
+        for (int i = 0; i < kLbfTB; ++i) acc[i] = fmaf(up[i * C + c], w, acc[i]);
+    }
+    const float* dmin = global ? dmin_g : dmin_l;
+    float* g = global ? g_g : g_l;
+#pragma unroll
+    for (int i = 0; i < kLbfTB; ++i)
+        if (b0 + i < B) {
+            const size_t o = (size_t)(b0 + i) * np + p;
+            g[o] = acc[i] * dact_of_dist(__ldg(dmin + o), act_fn, eps);
+        }
+}
+
 }  // namespace pph
 
 extern "C" int pph_logits_fwd(const float* act_l, const float* act_g, const float* Wl, const float* Wg,
@@ -161,6 +214,13 @@ extern "C" int pph_logits_bwd(const float* dlogits, const float* dlogits_g, cons
                 "pph_logits_bwd: null pointer");
     PPH_REQUIRE(B >= 0 && P >= 1 && Pg >= 0 && C >= 1, PPH_EINVAL, "pph_logits_bwd: bad dims");
     if (B == 0) return 0;
+    if (option(kOptLogitsBwd) != 1 && (size_t)kLbfTB * C * sizeof(float) <= 48 * 1024) {      // default: exact FP32 FMA
+        const int nbl = ceil_div(P, kLbfThreads), nbg = Pg > 0 ? ceil_div(Pg, kLbfThreads) : 0;
+        launch_k(logits_bwd_fma_kernel, dim3(nbl + nbg, ceil_div(B, kLbfTB)), dim3(kLbfThreads), sizeof(float) * kLbfTB * C,
+                 as_stream(stream), dlogits, dlogits_g, dlogits_l, Wl, Wg, dmin_l, dmin_g, B, P, Pg, C, nbl, global_coe, act_fn,
+                 eps, g_l, g_g);
+        return launch_status("pph_logits_bwd");
+    }
     const int Plpad = ceil_div(P, kTgBM) * kTgBM;
     LbAOp a{Wl, Wg, P, Plpad, Pg, C};
     LbBOp b{dlogits, dlogits_g, dlogits_l, B, C, Plpad, global_coe};

@@ -69,6 +69,8 @@ case $stage in
   e2e)
     for e in "" nocopy norows nod2h "nocopy,nosel" "nocopy,nosel,norows"; do EXP=$e timeout 200 python scripts/e2e_timeline.py 32 2 2>&1 | grep "^#"; done
     EXP=nocopy PPH_TIMELINE=1 timeout 200 python scripts/e2e_timeline.py 32 2 2>&1 | grep -v Warn | tail -30 ;;
+  tolerances)
+    timeout 600 python scripts/measure_tolerances.py > gpurun_out/tolerances.json 2> gpurun_out/tolerances.err; cat gpurun_out/tolerances.json; tail -3 gpurun_out/tolerances.err ;;
   gatherparts)
     timeout 200 python scripts/gather_parts.py 2>&1 | tail -4 ;;
   hostgather)

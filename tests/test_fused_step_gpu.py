@@ -75,11 +75,11 @@ def test_fused_step_is_bit_reproducible_and_matches_modular_path():
     mod.run(0)
     torch.cuda.synchronize()
     assert rel_close(mod.loss[0].cpu(), la[0].cpu(), 1e-6)
-    # the modular path runs the round-1 kernels (tcgen05 3-term split in every small GEMM, atomics in the PPC rows): it
-    # is the less accurate arm -- the fused step is held to the oracle directly in tests/test_step2_gpu.py
+    # two different kernel sequences for the same gradients, each within 1e-4 of the float64 oracle on its own
+    # (tests/test_gpu_parity.py, tests/test_step2_gpu.py): 2e-4 between them
     for k in ("P", "Pg", "Wa", "ba"):
-        assert norm_rel(mparams[k].grad.cpu(), params[k].grad.cpu()) < 5e-4, k
-    assert norm_rel(mod.dtokens[0].cpu(), dta.cpu()) < 5e-4
+        assert norm_rel(mparams[k].grad.cpu(), params[k].grad.cpu()) < 2e-4, k
+    assert norm_rel(mod.dtokens[0].cpu(), dta.cpu()) < 2e-4
 
 
 def test_stream_schedules_agree_bitwise():

@@ -6,7 +6,8 @@ Tolerances (north_star):
   * argmin over tokens: bit-exact outside the fixture's near-tie pairs (reference top-2 gap < 1e-4) in the fp32 modes;
   * fp32 modes ('fp32' = 3-term bf16 split on tcgen05, 'fp32_fma'): logits / activations / min distances / losses
     within 1e-4 relative on the init-like distribution, 1e-3 on the matched (cancellation-regime) distribution where
-    the reference itself is only good to ~2e-4 against float64; gradients within 5e-4 of the largest entry;
+    the reference itself is only good to ~2e-4 against float64; gradients within 1e-4 of the largest entry against the
+    oracle's float64 autograd (GRAD_TOL_F64) and 2e-4 against the reference's own fp32 gradients;
   * bf16 mode: measured and stated below (BF16_TOL).
 """
 import numpy as np
@@ -21,7 +22,17 @@ from tests.util import (GOLDEN_CASES, argmax_mismatch_outside_near_ties, load_go
 pytestmark = pytest.mark.gpu
 
 # bf16 single-pass mode, measured on B200 (see DESIGN.md "bf16 mode"): max relative error per output
-BF16_TOL = dict(logits=2e-3, act=2e-2, dmin=2e-2, loss=5e-3, grad=5e-2, argmin_flip_frac=0.03)
+# bf16 mode: 2x the maximum measured over all fixtures (scripts/measure_tolerances.py, B200): "init" fixtures measured
+# logits 1.1e-4, act / dmin 1.1e-3, loss 3e-6, gradients 8.3e-4, argmin flips 0.35 %; the "matched" (cancellation regime)
+# fixtures logits 1.0e-4, act 3.0e-3, dmin 5.2e-3, loss 2.2e-5, gradients 5.8e-3, flips 0.22 %; the separate global / local
+# logits (no averaging between the branches) measured up to 3.5e-4
+BF16_TOL = dict(logits=7e-4, act=2.5e-3, dmin=2.5e-3, loss=1e-5, grad=2e-3, argmin_flip_frac=0.007)
+BF16_TOL_MATCHED = dict(logits=7e-4, act=6e-3, dmin=1.1e-2, loss=5e-5, grad=1.2e-2, argmin_flip_frac=0.005)
+# fp32 modes, gradients: max |a - b| / max |b| against the oracle's autograd in FLOAT64 (the fp32 oracle is itself up to 1e-4
+# away from float64 on these sums); measured maximum 8.5e-5 (g_P, K = 144 / D = 384 fixture) on the "init" fixtures and 1.1e-4
+# (g_Pg) on the "matched" ones, whose outputs are themselves only held to 1e-3: 2x there
+GRAD_TOL_F64 = 1e-4
+GRAD_TOL_FIXTURE = 2e-4      # against the reference's own fp32 gradients (fixture): both sides carry fp32 summation noise
 
 
 def _dev():
@@ -143,13 +154,12 @@ def test_forward_matches_reference_fixture(name, mode):
     res = dict(logits=out.logits, logits_global=out.logits_global, logits_local=out.logits_local,
                act_l=out.act_l, dmin_l=out.dmin_l)
     if mode == "bf16":
-        tol = dict(logits=BF16_TOL["logits"], logits_global=BF16_TOL["logits"], logits_local=BF16_TOL["logits"],
-                   act_l=BF16_TOL["act"], dmin_l=BF16_TOL["dmin"])
-        scale = 10.0 if "matched" in name else 1.0      # cancellation regime: d -> small, relative error grows
+        bt = BF16_TOL_MATCHED if "matched" in name else BF16_TOL      # cancellation regime: d -> small, relative error grows
+        tol = dict(logits=bt["logits"], logits_global=bt["logits"], logits_local=bt["logits"], act_l=bt["act"], dmin_l=bt["dmin"])
         for k, v in res.items():
-            assert max_rel(v.cpu(), g[k]) < tol[k] * scale, (k, max_rel(v.cpu(), g[k]))
+            assert max_rel(v.cpu(), g[k]) < tol[k], (k, max_rel(v.cpu(), g[k]))
         flips = (out.argmin.cpu().long() != torch.as_tensor(g["argmax"]).long()).float().mean().item()
-        assert flips < BF16_TOL["argmin_flip_frac"] * scale, flips
+        assert flips < bt["argmin_flip_frac"], flips
     else:
         for k, v in res.items():
             assert rel_close(v.cpu(), g[k], _rtol(name)), (k, max_rel(v.cpu(), g[k]))
@@ -195,16 +205,16 @@ def test_train_step_matches_reference_fixture(name, mode):
     loss = ce + 0.1 * cov + 0.5 * mean
     loss.backward()
     bf16 = mode == "bf16"
-    scale = 10.0 if ("matched" in name and bf16) else 1.0
-    tol = BF16_TOL["loss"] * scale if bf16 else _rtol(name)
+    bt = BF16_TOL_MATCHED if "matched" in name else BF16_TOL
+    tol = bt["loss"] if bf16 else _rtol(name)
     # the PPC loss is always evaluated in fp32 from Zs/P -> fp32 tolerance in every mode
     assert rel_close(cov.cpu(), g["ppc_cov"], _rtol(name)), (cov.item(), g["ppc_cov"])
     assert rel_close(mean.cpu(), g["ppc_mean"], _rtol(name)), (mean.item(), g["ppc_mean"])
     assert rel_close(ce.cpu(), g["ce"], tol)
     assert rel_close(loss.cpu(), g["loss"], tol)
     # gradients: oracle autograd routed through the token the kernel picked (near-tie policy)
-    ref = O.head_train_step(case, shape, fn=fn, route=out.argmin.cpu().long())
-    gt = BF16_TOL["grad"] * scale if bf16 else 5 * _rtol(name)
+    ref = O.head_train_step(case, shape, fn=fn, route=out.argmin.cpu().long(), dtype=torch.float64)
+    gt = bt["grad"] if bf16 else GRAD_TOL_F64 * (2.0 if "matched" in name else 1.0)
     got = dict(g_tokens=leaves["tokens"].grad, g_P=leaves["P"].grad, g_Pg=leaves["Pg"].grad,
                g_Wa=leaves["Wa"].grad, g_ba=leaves["ba"].grad)
     for k, v in got.items():
@@ -218,7 +228,9 @@ def test_train_step_matches_reference_fixture(name, mode):
             stride = 1 if shape.name in ("tiny", "small") else int(g["meta"][9])
             for k in ("g_tokens", "g_P", "g_Pg", "g_Wa"):
                 t = got[k].cpu().reshape(-1, got[k].shape[-1])
-                assert norm_rel(t[::stride], g[k]) < gt, (k, norm_rel(t[::stride], g[k]))
+                # (the "matched" fixtures' fp32 reference gradients are themselves ~3e-4 from float64: measured 2.97e-4 here)
+                ft = GRAD_TOL_FIXTURE * (2.5 if "matched" in name else 1.0)
+                assert norm_rel(t[::stride], g[k]) < ft, (k, norm_rel(t[::stride], g[k]))
 
 
 def test_backward_is_linear_in_upstream_gradient_and_propagates_nonfinite():

@@ -86,9 +86,9 @@ def test_ppnet_dropin_eval_train_push(name, precision):
         full = shape.name in ("tiny", "small")
         st = 1 if full else int(g["meta"][9])
         gp = net.prototype_vectors.grad.reshape(shape.P, shape.D).cpu()
-        assert norm_rel(gp[::st], g["g_P"]) < 5e-4
-        assert norm_rel(net.add_on_layers[0].weight.grad.reshape(shape.D, shape.Din).cpu()[::st], g["g_Wa"]) < 5e-4
-        assert norm_rel(tokens.grad.reshape(-1, shape.Din).cpu()[::st], g["g_tokens"]) < 5e-4
+        assert norm_rel(gp[::st], g["g_P"]) < 2e-4
+        assert norm_rel(net.add_on_layers[0].weight.grad.reshape(shape.D, shape.Din).cpu()[::st], g["g_Wa"]) < 2e-4
+        assert norm_rel(tokens.grad.reshape(-1, shape.Din).cpu()[::st], g["g_tokens"]) < 2e-4
 
 
 @pytest.mark.parametrize("name", ["cub_b8_s1", "small_s1", "cars_b4_s1"])

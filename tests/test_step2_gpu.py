@@ -567,8 +567,8 @@ def test_five_launch_step_is_bit_reproducible_and_matches_round1_sequence():
     # the round-1 sequence is the less accurate arm (tcgen05 3-term split in the small GEMMs, routed through slightly
     # different Z): the five-launch step is held to the oracle directly (test_benchmarked_shape_against_oracle)
     for k in ("P", "Pg", "Wa", "ba"):
-        assert norm_rel(p1[k].grad.cpu(), a[k].cpu()) < 5e-3, (k, norm_rel(p1[k].grad.cpu(), a[k].cpu()))
-    assert norm_rel(s1.fused.dtokens.cpu(), dta.cpu()) < 5e-3
+        assert norm_rel(p1[k].grad.cpu(), a[k].cpu()) < 2e-4, (k, norm_rel(p1[k].grad.cpu(), a[k].cpu()))
+    assert norm_rel(s1.fused.dtokens.cpu(), dta.cpu()) < 2e-4
 
 
 def test_five_launch_eval_step_and_no_ppc():
