@@ -75,6 +75,9 @@ case $stage in
     timeout 200 python scripts/gather_parts.py 2>&1 | tail -4 ;;
   hostgather)
     timeout 200 python scripts/host_gather_times.py 2>&1 | tail -12 ;;
+  mgtest)     # multi-GPU pytest group (gpurun --gpus 2)
+    timeout 600 python -m pytest tests/test_peer_exchange_multigpu.py -q -m gpu --tb=short > gpurun_out/t_mg.log 2>&1
+    echo "== mgtest rc=$? $(tail -1 gpurun_out/t_mg.log)" ;;
   probe2)
     timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 \
         scripts/peer_probe.py > gpurun_out/probe2.log 2>&1; echo "== probe2 rc=$?"; grep -v "^W\|^\*\|OMP" gpurun_out/probe2.log | tail -30 ;;
