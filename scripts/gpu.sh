@@ -81,6 +81,15 @@ case $stage in
   probe2)
     timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 \
         scripts/peer_probe.py > gpurun_out/probe2.log 2>&1; echo "== probe2 rc=$?"; grep -v "^W\|^\*\|OMP" gpurun_out/probe2.log | tail -30 ;;
+  driver2)    # exactly what the driver runs at N = 2: both arms, default extras, its launch line
+    t0=$(date +%s)
+    timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 \
+        bench.py --impl reference --gpus 2 --steps 20 --warmup 3 > gpurun_out/driver2_ref.json 2> gpurun_out/driver2_ref.err
+    echo "== reference arm rc=$? $(( $(date +%s) - t0 )) s"; tail -c 700 gpurun_out/driver2_ref.json
+    t0=$(date +%s)
+    timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29542 \
+        bench.py --gpus 2 --steps 500 --warmup 20 > gpurun_out/driver2.json 2> gpurun_out/driver2.err
+    echo "== our arm rc=$? $(( $(date +%s) - t0 )) s"; tail -c 1500 gpurun_out/driver2.json; tail -3 gpurun_out/driver2.err ;;
   ddp2|ddp4|ddp8)       # in-graph gradient exchange: result check, step time and kernel timeline at N ranks
     n=${stage#ddp}
     PPH_TIMELINE=1 timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29513 \
