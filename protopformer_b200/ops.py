@@ -527,7 +527,7 @@ def ppc_loss_dense(cfg: HeadConfig, total_proto_act: torch.Tensor, cls_attn_roll
 # graph and no PyTorch glue kernels in between (what tools/engine_proto.py:49-76 amounts to for the head).
 # ------------------------------------------------------------------------------------------------------------------
 class FusedHeadStepV1:
-    """Round-1 launch sequence (16 launches over three streams), kept as the fallback for shapes the five-launch step
+    """Round-1 launch sequence (16 launches over three streams), kept as the fallback for shapes the round-2 step (FusedHeadStep)
     was not built for and as an A/B arm.  forward (+ PPC + cross-entropy + backward) of the head for a fixed shape.
 
     step(tokens, scores, labels, Wa, ba, P, Pg, Wl, Wg, grads) launches, in order:
@@ -698,7 +698,7 @@ def _ws(fn: str, *dims, zero: bool, device) -> torch.Tensor:
 
 
 def fused_step_supported(B, N, Din, D, K, P, Pg, C, m) -> bool:
-    """Host-side check (no device needed): can the five-launch step run this shape?"""
+    """Host-side check (no device needed): can FusedHeadStep (the round-2 launch sequence) run this shape?"""
     lib = _lib.load()
     if C > 256 or B < 1 or B > 64 * 74:
         return False
@@ -708,13 +708,20 @@ def fused_step_supported(B, N, Din, D, K, P, Pg, C, m) -> bool:
 
 
 class FusedHeadStep:
-    """forward (+ PPC + cross-entropy + backward) of the head for a fixed shape in five launches on the current stream:
+    """forward (+ PPC + cross-entropy + backward) of the head for a fixed shape: 10 launches over the current stream and two
+    side branches (default variants):
 
-      pph_head_prep        selection + gather + add-on + sigmoid + bf16 operands (tokens and both prototype tensors)
-      pph_similarity_fwd   tcgen05 distances, log similarity, min / argmin over tokens (the (B,P,K) map stays in TMEM)
-      pph_head_mid         last layers + cross-entropy + last-layer backward || token bins || PPC loss fwd + bwd
-      pph_similarity_bwd2  x3 concurrent kinds: token rows | prototype rows | CLS rows (+ the PPC gradients)   [training]
-      pph_addon_bwd2       dWa, dba, dtokens                                    [training]
+      pph_select_addon_fwd      selection + gather + add-on + sigmoid + bf16 operands (tcgen05, single shot)
+        || pph_split_rows x2    bf16 operands / norms of both prototype tensors, memset of dtokens           (side branch)
+      pph_similarity_fwd        tcgen05 distances, log similarity, min / argmin over tokens (the (B,P,K) map stays in TMEM)
+      pph_head_mid (LL)         last layers + cross-entropy + last-layer backward, token bins, class lists
+        || pph_head_mid (PPC)   PPC loss forward + backward                                        [training, side branch]
+      pph_similarity_bwd_fused  argmin-routed gradients: dP, dPg, pre-activation gradients of the tokens      [training]
+        || ppc rows add         PPC prototype rows onto dP                                          [training, side branch]
+      pph_addon_bwd3 x2         dtokens, then dWa | dba (tcgen05, single shot)                                [training]
+
+    `variants` selects alternative kernels per stage (exact-FP32 CUDA-core add-on kernels, the staged sparse backward, the
+    stand-alone selection launch, PPC inline) -- every combination is covered by tests/test_step2_gpu.py.
 
     Same results interface as FusedHeadStepV1: losses (4,) = (total, ce, ppc_cov, ppc_mean), logits, logits_g, logits_l,
     act_l, dmin_l, argmin, idx32, dtokens; parameter gradients are OVERWRITTEN in the tensors of `grads`
@@ -723,7 +730,7 @@ class FusedHeadStep:
     def __init__(self, cfg: HeadConfig, B, N, Din, D, P, Pg, C, m, device, heads: int = 0, ppc_cov_coe: float = 0.1,
                  ppc_mean_coe: float = 0.5, train: bool = True, use_ppc: bool = True, schedule=None, variants=None):
         if not fused_step_supported(B, N, Din, D, cfg.K, P, Pg, C, m):
-            raise ValueError("shape outside the five-launch step: use FusedHeadStepV1")
+            raise ValueError("shape outside FusedHeadStep's kernels: use FusedHeadStepV1")
         self.cfg, self.train, self.use_ppc = cfg, train, use_ppc
         # kernel choice per stage: "tc" = single-shot tcgen05 kernels (pph_addon_fwd2 / pph_addon_bwd3) where the shape
         # allows, "simt" = the exact-FP32 CUDA-core kernels (pph_head_prep / pph_addon_bwd2)

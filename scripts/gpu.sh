@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 for stage in "$@"; do
 case $stage in
   step2)      # new kernels, one pytest process per kernel so a device trap in one does not poison the others
-    for k in head_prep head_mid similarity_bwd2 addon_bwd2 "five_launch or benchmarked"; do
+    for k in head_prep head_mid similarity_bwd2 addon_bwd2 "bit_reproducible or benchmarked"; do
       n=$(echo $k | tr ' ' '_')
       timeout 600 python -m pytest tests/test_step2_gpu.py -q --tb=short -k "$k" > gpurun_out/t_$n.log 2>&1
       echo "== $k: rc=$? $(tail -1 gpurun_out/t_$n.log)"

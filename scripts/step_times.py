@@ -1,4 +1,4 @@
-"""Per-launch and whole-step timings of the five-launch step next to the round-1 sequence (CUDA graphs, CUDA events).
+"""Per-launch and whole-step timings of the round-2 step next to the round-1 sequence (CUDA graphs, CUDA events).
 
     python scripts/step_times.py [shape=cub_b64] [mode=fp32] [B override]
 """

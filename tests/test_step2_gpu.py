@@ -1,5 +1,5 @@
-"""The five-launch training step (pph_head_prep -> pph_similarity_fwd -> pph_head_mid -> pph_similarity_bwd2 ->
-pph_addon_bwd2) kernel by kernel against the CPU oracle, against the round-1 entry points on identical device inputs,
+"""The round-2 training step (ops.FusedHeadStep: pph_select_addon_fwd / pph_head_prep -> pph_similarity_fwd -> pph_head_mid ->
+pph_similarity_bwd_fused / pph_similarity_bwd2 -> pph_addon_bwd3 / pph_addon_bwd2) kernel by kernel against the CPU oracle, against the round-1 entry points on identical device inputs,
 and end to end against the reference fixtures -- including the benchmarked shape (cub_b64) in both precision modes.
 
 Tolerances: indices bit-exact; FP32-FMA kernels (prep, mid, bwd2, addon_bwd2) within 2e-5 relative of the oracle /
@@ -546,7 +546,7 @@ def test_benchmarked_shape_against_oracle(mode):
         assert e < tol["grad"], (k, e)
 
 
-def test_five_launch_step_is_bit_reproducible_and_matches_round1_sequence():
+def test_step_is_bit_reproducible_and_matches_round1_sequence():
     shape = synth.SHAPES["cub_b64"]
     case = synth.make_case(shape, seed=4)
     s2, p2 = _make_step(shape, case, "fp32")
@@ -565,7 +565,7 @@ def test_five_launch_step_is_bit_reproducible_and_matches_round1_sequence():
     torch.cuda.synchronize()
     assert rel_close(s1.fused.losses.cpu(), la.cpu(), 1e-4)
     # the round-1 sequence is the less accurate arm (tcgen05 3-term split in the small GEMMs, routed through slightly
-    # different Z): the five-launch step is held to the oracle directly (test_benchmarked_shape_against_oracle)
+    # different Z): the round-2 step is held to the oracle directly (test_benchmarked_shape_against_oracle)
     for k in ("P", "Pg", "Wa", "ba"):
         assert norm_rel(p1[k].grad.cpu(), a[k].cpu()) < 2e-4, (k, norm_rel(p1[k].grad.cpu(), a[k].cpu()))
     assert norm_rel(s1.fused.dtokens.cpu(), dta.cpu()) < 2e-4
