@@ -682,6 +682,7 @@ def main():
             "gpu_launches_per_step": step.kernel_launches_per_step,
             "step_impl": step.impl,
             "exchange": getattr(step, "exchange", None) if world > 1 else None,
+            "exchange_note": getattr(step, "exchange_note", "") if world > 1 else "",
             "clocks": sampler.summary(),
             "roofline": roof,
             "oracle_check": oracle_check,

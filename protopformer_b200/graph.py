@@ -54,11 +54,16 @@ class GraphedHeadStep:
             named = [(k, params[k]) for k in ("P", "Pg", "Wa", "ba")]
             # exchange: "nccl" = NCCL all-reduce of the flat buffer, "peer" / "peer_nomc" = the library's own one-kernel
             # all-reduce over peer-mapped memory (with / without the NVLS multicast mapping)
-            self.exchange = exchange
+            self.exchange, self.exchange_note = exchange, ""
             if exchange in ("peer", "peer_nomc"):
-                self.reducer = PeerGradReducer(named, process_group, multicast=(exchange == "peer"))
-                if exchange == "peer" and not self.reducer.multicast_ptr:
-                    self.exchange = "peer_nomc"
+                try:
+                    self.reducer = PeerGradReducer(named, process_group, multicast=(exchange == "peer"))
+                    if exchange == "peer" and not self.reducer.multicast_ptr:
+                        self.exchange = "peer_nomc"
+                except Exception as exc:      # no peer-mapped memory on this box (no P2P / symmetric memory): NCCL instead
+                    self.exchange = "nccl"
+                    self.exchange_note = f"peer memory unavailable ({type(exc).__name__}: {exc}); fell back to NCCL"
+                    self.reducer = FlatGradReducer(named, process_group)
             else:
                 self.reducer = FlatGradReducer(named, process_group)
         self.kernel_launches_per_step = 0

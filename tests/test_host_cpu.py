@@ -220,3 +220,22 @@ def test_bench_reference_arm_prints_the_contract_line():
         assert k in d, k
     assert d["config"]["workload"] == "cub_b64" and d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["value"] > 0
+
+
+def test_bench_arms_build_identical_config_objects():
+    """The driver compares the `config` of the two bench arms: both must come out of one function with the same arguments."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    for wl in ("cub_b64", "dogs_b256_eval", "cars_b64_bf16", "sweep:K=49,D=384,P=4000,B=32"):
+        name, shape, mode, train = bench.parse_workload(wl, None)
+        for world in (1, 2, 8):
+            a = bench.make_config(name, shape, mode, train, world, 16, True, "peer")
+            b = bench.make_config(name, shape, mode, train, world, 16, True, "peer")
+            assert a == b and a["workload"] == wl and a["parallelism"] == f"dp{world}"
+            assert ("all-reduce" in a["step"]) == (world > 1 and train)
+    name, shape, mode, train = bench.parse_workload("dogs_b256_eval", None)
+    assert not train and shape.D == 384 and mode == "fp32"
+    assert bench.parse_workload("cars_b64_bf16", None)[2] == "bf16"
+    assert bench.step_flops(shape, False) < bench.step_flops(shape, True)
