@@ -89,6 +89,18 @@ class FusedHeadAdamW:
         return int(self._step_state[0].item())
 
     def zero_grad(self, set_to_none: bool = True):
+        """torch.optim semantics (set_to_none by default, as the reference's loop relies on), EXCEPT when the optimizer was
+        built over external gradient buffers (`grads=`: e.g. the views of dist.FlatGradReducer's flat all-reduce buffer): those
+        are zeroed in place and stay attached -- dropping them would make autograd accumulate into fresh tensors while the
+        all-reduce and this optimizer keep reading the stale buffer."""
+        if self._grads is not None:
+            for gr, p in zip(self._grads, self._flat):
+                gr.zero_()
+                if p.grad is not None and p.grad.data_ptr() != gr.data_ptr():
+                    p.grad = None
+                if p.requires_grad and p.is_leaf and p.grad is None:
+                    p.grad = gr
+            return
         for p in self._flat:
             if p.grad is not None:
                 if set_to_none:

@@ -23,9 +23,10 @@ case $stage in
   times)
     timeout 300 python scripts/step_times.py cub_b64 fp32 > gpurun_out/times_b64.json 2> gpurun_out/times_b64.err; tail -c 1500 gpurun_out/times_b64.json
     timeout 300 python scripts/step_times.py cub_b64 fp32 1024 > gpurun_out/times_b1024.json 2> gpurun_out/times_b1024.err; tail -c 1500 gpurun_out/times_b1024.json ;;
-  sanitize)
-    timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_step2_gpu.py -q --tb=line \
-        -k "tiny or small or cub_b8" > gpurun_out/sanitize.log 2>&1
+  sanitize)   # compute-sanitizer memcheck over the small-shape tests of every kernel added in round 2
+    timeout 1200 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_step2_gpu.py tests/test_module_gpu.py \
+        tests/test_classmap.py tests/test_gpu_parity.py -q --tb=line -m gpu \
+        -k "(tiny or small or cub_b8 or selection_first or dense) and not subprocess and not benchmarked" > gpurun_out/sanitize.log 2>&1
     echo "== sanitize rc=$?"; grep -E "ERROR SUMMARY|Invalid|passed|failed" gpurun_out/sanitize.log | head -20 ;;
   ncu2)       # one --set full capture of each kernel of the five-launch step (second eager step)
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:"head_prep|similarity_tc2|head_mid|sim_grads2|addon_bwd2" \

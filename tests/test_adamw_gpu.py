@@ -86,3 +86,26 @@ def test_fused_adamw_refuses_cpu_tensors():
     from protopformer_b200.optim import FusedHeadAdamW
     with pytest.raises(ValueError):
         FusedHeadAdamW([torch.zeros(4, 4)])
+
+
+def test_zero_grad_keeps_the_flat_all_reduce_views_attached():
+    """optimizer.zero_grad() (set_to_none by default) must not detach the gradients from the flat
+    all-reduce buffer the optimizer and the exchange read."""
+    from protopformer_b200.dist import FlatGradReducer
+    from protopformer_b200.optim import FusedHeadAdamW
+    dev = torch.device("cuda:0")
+    ps = [torch.randn(7, 5, device=dev, requires_grad=True), torch.randn(11, device=dev, requires_grad=True)]
+    red = FlatGradReducer([("a", ps[0]), ("b", ps[1])])
+    opt = FusedHeadAdamW([{"params": ps, "lr": 1e-3, "weight_decay": 0.0}], grads=red.views)
+    (ps[0].sum() * 2.0 + ps[1].sum()).backward()
+    assert float(red.flat.abs().sum()) > 0
+    opt.zero_grad()
+    assert float(red.flat.abs().sum()) == 0.0
+    red.check_attached()                                    # still the same storage
+    (ps[0].sum() * 3.0).backward()
+    assert torch.equal(red.views[0], torch.full_like(ps[0], 3.0))
+    ps[0].grad = None                                       # a caller that dropped it anyway ...
+    with pytest.raises(RuntimeError):
+        red.check_attached()                                # ... is told so instead of averaging a stale buffer
+    opt.zero_grad()
+    red.check_attached()                                    # and zero_grad() re-attaches
