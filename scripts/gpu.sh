@@ -72,6 +72,9 @@ case $stage in
     EXP=nocopy PPH_TIMELINE=1 timeout 200 python scripts/e2e_timeline.py 32 2 2>&1 | grep -v Warn | tail -30 ;;
   tolerances)
     timeout 600 python scripts/measure_tolerances.py > gpurun_out/tolerances.json 2> gpurun_out/tolerances.err; cat gpurun_out/tolerances.json; tail -3 gpurun_out/tolerances.err ;;
+  rollout)
+    timeout 300 python -m pytest tests/test_rollout_gpu.py -q -m gpu --tb=short 2>&1 | tail -2
+    timeout 200 python scripts/rollout_bench.py 2>&1 | cut -c1-150 | tail -4 ;;
   gatherparts)
     timeout 200 python scripts/gather_parts.py 2>&1 | tail -4 ;;
   hostgather)
