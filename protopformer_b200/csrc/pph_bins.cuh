@@ -10,14 +10,18 @@ namespace pph {
 // pass A builds per-warp histograms (match.any groups equal tokens inside a 32-prototype step), an exclusive scan
 // over (token, warp) turns them into per-warp write cursors, pass B replays the same steps and places every
 // prototype -> inside a bin prototypes are in ascending order, independent of scheduling (deterministic sums).
-// Also emits, per token, the first work item of the bin when bins are cut into chunks of kBinChunk entries.
+// Also emits, per token, the first work item of the bin when bins are cut into chunks of kBinChunk entries, and (when
+// item_desc is given) one 16-byte descriptor per work item -- (token, first entry, end entry, chunks of the bin | chunk << 16),
+// token = -1 for the unused tail of the image's item range -- so that the gradient kernel starts a work item with ONE load
+// instead of a search over item_start plus four bound loads (a chain of dependent L2 latencies in front of every gather).
 constexpr int kBinChunk = 32;
+__host__ __device__ inline int bin_items_per_image(int K, int P) { return K + (P + kBinChunk - 1) / kBinChunk; }
 
 // One CTA of 256 threads per image b; smi: 8*K + 2*(K+1) ints of shared memory.
 template <bool kCoherentKeys = false>
 __device__ __forceinline__ void
 bin_tokens_body(int b, const int32_t* __restrict__ argmin_l, int K, int P, int32_t* __restrict__ bin_start,
-                int32_t* __restrict__ item_start, int32_t* __restrict__ bin_list, int* smi) {
+                int32_t* __restrict__ item_start, int32_t* __restrict__ bin_list, int* smi, int4* __restrict__ item_desc = nullptr) {
     int* hist = smi;                      // [8][K]   per-warp histogram, then per-warp cursor
     int* tot = smi + 8 * K;               // [K+1]    bin offsets
     int* itm = tot + K + 1;               // [K+1]    work-item offsets
@@ -70,6 +74,16 @@ bin_tokens_body(int b, const int32_t* __restrict__ argmin_l, int K, int P, int32
     for (int k = tid; k <= K; k += 256) {
         bin_start[(size_t)b * (K + 1) + k] = tot[k];
         item_start[(size_t)b * (K + 1) + k] = itm[k];
+    }
+    if (item_desc) {
+        const int ipi = bin_items_per_image(K, P);
+        int4* dsc = item_desc + (size_t)b * ipi;
+        for (int k = tid; k < K; k += 256) {
+            const int e0 = tot[k], e1 = tot[k + 1], i0 = itm[k], nch = itm[k + 1] - i0;
+            for (int c = 0; c < nch; ++c)
+                dsc[i0 + c] = make_int4(k, e0 + c * kBinChunk, min(e1, e0 + (c + 1) * kBinChunk), nch | (c << 16));
+        }
+        for (int i = itm[K] + tid; i < ipi; i += 256) dsc[i] = make_int4(-1, 0, 0, 0);
     }
     __syncthreads();
     int32_t* list = bin_list + (size_t)b * P;

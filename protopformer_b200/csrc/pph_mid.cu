@@ -49,6 +49,7 @@ struct MidArgs {
     float *part, *dlT, *ce_part, *ppc_part, *ppc_losses;
     unsigned int* ctr;      // [0] barrier, [1] done, [2] fin, [3] ppc ticket
     int32_t *bin_start, *item_start, *bin_list;
+    int4* item_desc;
     int32_t *cls_id, *cls_start, *cls_item, *cls_order;
     // PPC role
     const float *Zs, *z2s, *Pl, *p2l;
@@ -541,7 +542,7 @@ head_mid_kernel(const MidArgs a) {
         ll_role<CJ>(a, sm_mid);
     } else if (bid < a.n_ll + a.n_bin) {
         bin_tokens_body<false>(bid - a.n_ll, a.argmin_l, a.K, a.P, a.bin_start, a.item_start, a.bin_list,
-                        reinterpret_cast<int*>(sm_mid));
+                        reinterpret_cast<int*>(sm_mid), a.item_desc);
     } else if (bid < a.n_ll + a.n_bin + a.n_ppc) {
         ppc_role(a, bid - a.n_ll - a.n_bin, 0, 1, sm_mid);
     } else {
@@ -691,11 +692,13 @@ extern "C" int pph_head_mid(const float* act_l, const float* act_g, const float*
     a.part = w.part; a.dlT = w.dlT; a.ce_part = w.ce_part; a.ppc_part = w.ppc_part; a.ppc_losses = w.ppc_losses;
     a.ctr = w.ctr;
     a.bin_start = a.item_start = a.bin_list = nullptr;
+    a.item_desc = nullptr;
     a.cls_id = a.cls_start = a.cls_item = a.cls_order = nullptr;
     a.n_cls_cta = 0;
     if (train) {
         const Step2Bins bw = carve_bins(bwd_workspace, B, K, P);
         a.bin_start = bw.bin_start; a.item_start = bw.item_start; a.bin_list = bw.bin_list;
+        a.item_desc = bw.item_desc;
         a.cls_id = bw.cls_id; a.cls_start = bw.cls_start; a.cls_item = bw.cls_item; a.cls_order = bw.cls_order;
         if (have_ppc && run_ll && bin_tokens_smem_bytes(P / m) <= 200 * 1024) a.n_cls_cta = 1;
     }

@@ -15,11 +15,11 @@
 namespace pph {
 
 __global__ void __launch_bounds__(256)
-bin_tokens_kernel(const int32_t* __restrict__ argmin_l, int K, int P, int32_t* __restrict__ bin_start,
+bin_tokens_kernel(int4* __restrict__ item_desc, const int32_t* __restrict__ argmin_l, int K, int P, int32_t* __restrict__ bin_start,
                   int32_t* __restrict__ item_start, int32_t* __restrict__ bin_list) {
     pdl_sync();
     extern __shared__ int smi[];
-    bin_tokens_body<false>(blockIdx.x, argmin_l, K, P, bin_start, item_start, bin_list, smi);
+    bin_tokens_body<false>(blockIdx.x, argmin_l, K, P, bin_start, item_start, bin_list, smi, item_desc);
 }
 
 // Extras of the fused training step (pph_similarity_bwd_fused): per-image PPC prototype rows summed over the images of
@@ -103,29 +103,17 @@ proto_grad_body(int vb, const float* __restrict__ g_l, const float* __restrict__
 // and the last warp to finish adds them in chunk order -> balanced AND deterministic.
 template <int DV, bool FULL>
 __device__ __forceinline__ void
-token_grad_body(int vb, const float* __restrict__ g_l, const int32_t* __restrict__ bin_start,
-                const int32_t* __restrict__ item_start, const int32_t* __restrict__ bin_list,
+token_grad_body(int vb, const float* __restrict__ g_l, const int4* __restrict__ item_desc, const int32_t* __restrict__ bin_list,
                 const float* __restrict__ Zs, const float* __restrict__ Pl, int B, int K, int D, int P,
                 int items_per_image, float* part, float* part_gsum, unsigned int* counters,
                 const float* __restrict__ add_dZs, float* __restrict__ dZs, const BwdExtras& ex) {
     const int gw = vb * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     const int b = gw / items_per_image, item = gw - b * items_per_image;
     if (b >= B) return;
-    const int32_t* ist = item_start + (size_t)b * (K + 1);
-    if (item >= __ldg(ist + K)) return;
-    // token of this item: the last k with item_start[k] <= item   (lane-parallel search over <= 256 tokens)
-    int k = 0;
-    for (int k0 = 0; k0 < K; k0 += 32) {
-        const int kk = k0 + lane;
-        const bool le = kk < K && __ldg(ist + kk) <= item;
-        const unsigned m = __ballot_sync(0xffffffffu, le);
-        if (m) k = k0 + 31 - __clz(m);
-        if (m != 0xffffffffu) break;
-    }
-    const int chunk = item - __ldg(ist + k);
-    const int nchunks = __ldg(ist + k + 1) - __ldg(ist + k);
-    const int e0 = __ldg(bin_start + (size_t)b * (K + 1) + k) + chunk * kBinChunk;
-    const int e1 = min(__ldg(bin_start + (size_t)b * (K + 1) + k + 1), e0 + kBinChunk);
+    // one 16-byte descriptor per work item (written with the bins): token, entry range, chunk count | chunk << 16
+    const int4 dsc = __ldg(item_desc + (size_t)b * items_per_image + item);
+    if (dsc.x < 0) return;
+    const int k = dsc.x, e0 = dsc.y, e1 = dsc.z, nchunks = dsc.w & 0xffff, chunk = dsc.w >> 16;
     const int32_t* list = bin_list + (size_t)b * P;
     const float* gb = g_l + (size_t)b * P;
     float acc[DV];
@@ -188,7 +176,7 @@ token_grad_body(int vb, const float* __restrict__ g_l, const int32_t* __restrict
     ticket = __shfl_sync(0xffffffffu, ticket, 0);
     if (ticket != (unsigned int)(nchunks - 1)) return;
     __threadfence();
-    const size_t slot0 = (size_t)b * items_per_image + __ldg(ist + k);
+    const size_t slot0 = slot - chunk;
     float tot[DV];
 #pragma unroll
     for (int i = 0; i < DV; ++i) tot[i] = 0.f;
@@ -213,7 +201,11 @@ token_grad_body(int vb, const float* __restrict__ g_l, const int32_t* __restrict
 // CLS-token gradient: dZc[b,:] = 2 (Zc[b,:] sum_p g_g[b,p] - sum_p g_g[b,p] Pg[p,:]).  CTA = 8 images x a slice of
 // the global prototypes (rows read once per CTA, coalesced), fixed-order two-level sum: per-slice partials in
 // `part` [slices][B][D], then the last CTA of each image group adds the slices in order (deterministic).
-constexpr int kClsTB = 8, kClsThreads = 256;
+constexpr int kClsTB = 8, kClsThreads = 256, kClsSlices = 16;
+// The CLS slices are the long pole of the launch (token rows alone 15.9 us, prototype rows alone 17.1 us, token + CLS 29.3 us).
+// Tried, measured, reverted: 32 slices of 64 rows with the final sum dealt to all threads (66 us), the dealt final sum alone
+// (44.5 us), 2 images x 64 rows x 32 slices (38.9 us, more re-read rows) -- every restructuring of this body so far made the
+// launch slower; a separate tensor-core product for dZc (a dense B x Pg x D GEMM) is the open item.
 
 __device__ __forceinline__ void
 cls_grad_body(int slice, int bgroup, int nslices, const float* __restrict__ g_g, const float* __restrict__ Zc,
@@ -304,6 +296,7 @@ ppc_rows_add_kernel(const float* __restrict__ dP_img, const int32_t* __restrict_
 
 struct BwdWorkspace {
     int32_t *bin_start, *item_start, *bin_list;
+    int4* item_desc;
     unsigned int *tok_counters, *cls_counters;
     float *tok_part, *tok_gsum, *cls_part;
     int items_per_image;
@@ -315,16 +308,17 @@ static BwdWorkspace carve_ws(void* base, int B, int K, int D, int P, int Pg) {
     char* p = static_cast<char*>(base);
     size_t off = 0;
     auto take = [&](size_t n) { char* r = p ? p + off : nullptr; off += (n + 255) / 256 * 256; return r; };
-    w.items_per_image = K + (P + kBinChunk - 1) / kBinChunk;
+    w.items_per_image = bin_items_per_image(K, P);
     // counters first: they are the part that must start zeroed
     w.tok_counters = reinterpret_cast<unsigned int*>(take(sizeof(int) * (size_t)B * K));
     w.cls_counters = reinterpret_cast<unsigned int*>(take(sizeof(int) * (size_t)((B + kClsTB - 1) / kClsTB + 1)));
     w.bin_start = reinterpret_cast<int32_t*>(take(sizeof(int) * (size_t)B * (K + 1)));
     w.item_start = reinterpret_cast<int32_t*>(take(sizeof(int) * (size_t)B * (K + 1)));
     w.bin_list = reinterpret_cast<int32_t*>(take(sizeof(int) * (size_t)B * P));
+    w.item_desc = reinterpret_cast<int4*>(take(sizeof(int4) * (size_t)B * w.items_per_image));
     w.tok_part = reinterpret_cast<float*>(take(sizeof(float) * (size_t)B * w.items_per_image * D));
     w.tok_gsum = reinterpret_cast<float*>(take(sizeof(float) * (size_t)B * w.items_per_image));
-    w.cls_part = reinterpret_cast<float*>(take(Pg > 0 ? sizeof(float) * (size_t)16 * B * D : 0));
+    w.cls_part = reinterpret_cast<float*>(take(Pg > 0 ? sizeof(float) * (size_t)kClsSlices * B * D : 0));
     w.bytes = off + 256;
     return w;
 }
@@ -339,7 +333,7 @@ static BwdWorkspace carve_ws(void* base, int B, int K, int D, int P, int Pg) {
 template <int DV, bool FULL>
 __global__ void __launch_bounds__(256)
 sim_grads_kernel(const float* __restrict__ g_l, const float* __restrict__ g_g, const int32_t* __restrict__ argmin_l,
-                 const int32_t* __restrict__ bin_start, const int32_t* __restrict__ item_start,
+                 const int4* __restrict__ item_desc,
                  const int32_t* __restrict__ bin_list, const float* __restrict__ Zs, const float* __restrict__ Zc,
                  const float* __restrict__ Pl, const float* __restrict__ Pgl, int B, int K, int D, int P, int Pg,
                  int items_per_image, int n_cls, int n_slices, int p_per_slice, int n_proto,
@@ -360,7 +354,7 @@ sim_grads_kernel(const float* __restrict__ g_l, const float* __restrict__ g_g, c
         return;
     }
     vb -= n_proto;
-    token_grad_body<DV, FULL>(vb, g_l, bin_start, item_start, bin_list, Zs, Pl, B, K, D, P, items_per_image, tok_part,
+    token_grad_body<DV, FULL>(vb, g_l, item_desc, bin_list, Zs, Pl, B, K, D, P, items_per_image, tok_part,
                               tok_gsum, tok_counters, add_dZs, dZs, ex);
 }
 
@@ -370,14 +364,14 @@ static int launch_bwd(const float* g_l, const float* g_g, const int32_t* argmin_
                       int B, int K, int D, int P, int Pg, const float* add_dZs, const float* add_dPl,
                       float* dZs, float* dZc, float* dPl, float* dPg, cudaStream_t st, const BwdExtras& ex,
                       int roles = 3) {
-    const int slices = 16;
+    const int slices = kClsSlices;
     const int p_per_slice = Pg > 0 ? ceil_div(ceil_div(Pg, slices), 64) * 64 : 64;
     const int nsl = Pg > 0 ? ceil_div(Pg, p_per_slice) : 0;
     // roles: bit 0 token-side rows (dZs, dZc), bit 1 prototype rows (dPl, dPg) -- independent, may run as two launches
     const int n_cls = (roles & 1) ? nsl * ceil_div(B, kClsTB) : 0;
     const int n_proto = (roles & 2) ? ceil_div(P + Pg, 8) : 0;
     const int n_tok = (roles & 1) ? ceil_div(B * w.items_per_image, 8) : 0;
-    launch_k(sim_grads_kernel<DV, FULL>, dim3(n_cls + n_proto + n_tok), dim3(256), (size_t)(0), st, g_l, g_g, argmin_l, w.bin_start, w.item_start, w.bin_list, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, w.items_per_image, n_cls, nsl, p_per_slice, n_proto, w.tok_part, w.tok_gsum, w.tok_counters, w.cls_part, w.cls_counters, add_dZs, add_dPl, dZs, dZc, dPl, dPg, ex);
+    launch_k(sim_grads_kernel<DV, FULL>, dim3(n_cls + n_proto + n_tok), dim3(256), (size_t)(0), st, g_l, g_g, argmin_l, w.item_desc, w.bin_list, Zs, Zc, Pl, Pgl, B, K, D, P, Pg, w.items_per_image, n_cls, nsl, p_per_slice, n_proto, w.tok_part, w.tok_gsum, w.tok_counters, w.cls_part, w.cls_counters, add_dZs, add_dPl, dZs, dZc, dPl, dPg, ex);
     return launch_status("pph_similarity_bwd(grads)");
 }
 
@@ -402,7 +396,7 @@ extern "C" int pph_similarity_bwd(const float* g_l, const float* g_g, const int3
         const size_t bs = sizeof(int) * ((size_t)8 * K + 2 * (size_t)(K + 1));
         PPH_REQUIRE(bs <= 48 * 1024, PPH_EUNSUP, "pph_similarity_bwd: K too large");
         const BwdWorkspace wb = carve_ws(workspace, B, K, D, P, Pg);
-        launch_k(bin_tokens_kernel, dim3(B), dim3(256), (size_t)(bs), as_stream(stream), argmin_l, K, P, wb.bin_start, wb.item_start, wb.bin_list);
+        launch_k(bin_tokens_kernel, dim3(B), dim3(256), (size_t)(bs), as_stream(stream), wb.item_desc, argmin_l, K, P, wb.bin_start, wb.item_start, wb.bin_list);
         return launch_status("pph_similarity_bwd(bin)");
     }
     PPH_REQUIRE(g_l && argmin_l && Zs && Pl && dZs && dPl, PPH_EINVAL, "pph_similarity_bwd: null local pointer");
@@ -421,7 +415,7 @@ extern "C" int pph_similarity_bwd(const float* g_l, const float* g_g, const int3
     const BwdWorkspace w = carve_ws(workspace, B, K, D, P, Pg);
     int rc = 0;
     if (parts & PPH_BWD_BIN) {
-        launch_k(bin_tokens_kernel, dim3(B), dim3(256), (size_t)(bin_smem), st, argmin_l, K, P, w.bin_start, w.item_start, w.bin_list);
+        launch_k(bin_tokens_kernel, dim3(B), dim3(256), (size_t)(bin_smem), st, w.item_desc, argmin_l, K, P, w.bin_start, w.item_start, w.bin_list);
         rc = launch_status("pph_similarity_bwd(bin)");
         if (rc) return rc;
     }
@@ -464,6 +458,7 @@ extern "C" int pph_similarity_bwd_fused(int parts, const float* g_l, const float
     BwdWorkspace w = carve_ws(workspace, B, K, D, P, Pg);
     const Step2Bins bins = carve_bins(step_workspace, B, K, P);
     w.bin_start = bins.bin_start; w.item_start = bins.item_start; w.bin_list = bins.bin_list;
+    w.item_desc = bins.item_desc;
     const BwdExtras ex{dP_img, bins.cls_start, bins.cls_order, m, dpre_out};
     cudaStream_t st = as_stream(stream);
     const float* add_dPl = nullptr;

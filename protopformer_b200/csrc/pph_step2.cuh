@@ -1,6 +1,7 @@
 // Scratch layouts shared by the kernels of the fused training step (pph_prep.cu, pph_mid.cu, pph_simgrad2.cu).
 #pragma once
 
+#include "pph_bins.cuh"
 #include "pph_common.cuh"
 
 namespace pph {
@@ -14,6 +15,7 @@ namespace pph {
 struct Step2Bins {
     int32_t *bin_start, *item_start, *bin_list;
     int32_t *cls_id, *cls_start, *cls_item, *cls_order;
+    int4* item_desc;         // [B][bin_items_per_image(K, P)] work-item descriptors of the gather kernel (pph_bins.cuh)
     size_t bytes;
 };
 
@@ -29,6 +31,7 @@ inline Step2Bins carve_bins(void* base, int B, int K, int P) {
     w.cls_start = reinterpret_cast<int32_t*>(take(sizeof(int) * (size_t)(P + 1)));      // n_cls = P / m <= P
     w.cls_item = reinterpret_cast<int32_t*>(take(sizeof(int) * (size_t)(P + 1)));
     w.cls_order = reinterpret_cast<int32_t*>(take(sizeof(int) * (size_t)B));
+    w.item_desc = reinterpret_cast<int4*>(take(sizeof(int4) * (size_t)B * bin_items_per_image(K, P)));
     w.bytes = off + 256;
     return w;
 }

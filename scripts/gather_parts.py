@@ -48,3 +48,8 @@ for parts in (1, 2, 3):
                                 params["Pg"].detach(), s.B, s.K, s.D, s.P, s.Pg, s.m, f.ws_gather, f.ws_bins, None, None, 1,
                                 f.dZs, f.dZc, gP, gPg))
     print(f"parts={parts}: {t:.1f} us")
+
+# token rows alone (no global prototypes -> no CLS slices): which piece is the long pole of parts = 1?
+t = timed(lambda: _lib.call("pph_similarity_bwd_fused", 1, f.g_l, None, f.argmin, f.Zs, None, params["P"].detach(), None, s.B, s.K,
+                            s.D, s.P, 0, s.m, f.ws_gather, f.ws_bins, None, None, 1, f.dZs, None, gP, None))
+print(f"token rows only: {t:.1f} us")
