@@ -83,7 +83,7 @@ KERNELS_PER_CALL = {
 
 _ENV_OPTIONS = {"PPH_PDL": "pdl", "PPH_SIM_LANES": "sim_lanes", "PPH_SIM_SHARED": "sim_shared", "PPH_SIM_EPI": "sim_epi",
                 "PPH_ROLLOUT": "rollout", "PPH_CLASSMAP": "classmap", "PPH_DEBUG": "debug",
-                "PPH_LOGITS_BWD": "logits_bwd"}
+                "PPH_LOGITS_BWD": "logits_bwd", "PPH_GATHER": "gather"}
 
 _lib = None
 _launches = 0

@@ -18,7 +18,7 @@ void set_error(const char* fmt, ...) {
 
 // defaults: PDL off, similarity plan knobs off, similarity epilogue 1 (chain-split), rollout version 2, class maps 1
 static int g_opt[kOptCount] = {0, 0, 0, 1, 2, 1, 0};
-static const char* const g_opt_name[kOptCount] = {"pdl", "sim_lanes", "sim_shared", "sim_epi", "rollout", "classmap", "debug", "logits_bwd"};
+static const char* const g_opt_name[kOptCount] = {"pdl", "sim_lanes", "sim_shared", "sim_epi", "rollout", "classmap", "debug", "logits_bwd", "gather"};
 
 int option(Option o) { return g_opt[o]; }
 bool pdl_enabled() { return g_opt[kOptPdl] != 0; }

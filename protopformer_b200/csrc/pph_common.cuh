@@ -47,7 +47,7 @@ bool pdl_enabled();
 
 // Measurement / variant switches, set once by the host binding through pph_set_option() (protopformer_b200/_lib.py reads
 // the PPH_* environment variables at load time); the launchers never read the environment.
-enum Option { kOptPdl = 0, kOptSimLanes, kOptSimShared, kOptSimEpi, kOptRollout, kOptClassmap, kOptDebug, kOptLogitsBwd, kOptCount };
+enum Option { kOptPdl = 0, kOptSimLanes, kOptSimShared, kOptSimEpi, kOptRollout, kOptClassmap, kOptDebug, kOptLogitsBwd, kOptGather, kOptCount };
 int option(Option o);
 
 template <typename... KArgs, typename... Args>

@@ -76,7 +76,11 @@ case $stage in
     timeout 300 python -m pytest tests/test_rollout_gpu.py -q -m gpu --tb=short 2>&1 | tail -2
     timeout 200 python scripts/rollout_bench.py 2>&1 | cut -c1-150 | tail -4 ;;
   gatherparts)
-    timeout 200 python scripts/gather_parts.py 2>&1 | tail -4 ;;
+    for v in 0 1; do echo "PPH_GATHER=$v"; PPH_GATHER=$v timeout 200 python scripts/gather_parts.py 2>&1 | tail -5; done ;;
+  bulktests)  # the sparse-backward tests with the bulk-copy gather selected
+    PPH_GATHER=1 timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_step2_gpu.py tests/test_fused_step_gpu.py -q -m gpu --tb=short \
+        -k "bwd or backward or train_step or benchmarked or variants or fixture or reproducible" > gpurun_out/t_bulk.log 2>&1
+    echo "== bulktests rc=$? $(tail -1 gpurun_out/t_bulk.log)" ;;
   hostgather)
     timeout 200 python scripts/host_gather_times.py 2>&1 | tail -12 ;;
   mgtest)     # multi-GPU pytest group (gpurun --gpus 2)
