@@ -75,6 +75,8 @@ case $stage in
   rollout)
     timeout 300 python -m pytest tests/test_rollout_gpu.py -q -m gpu --tb=short 2>&1 | tail -2
     timeout 200 python scripts/rollout_bench.py 2>&1 | cut -c1-150 | tail -4 ;;
+  execswitch)
+    timeout 300 python scripts/exec_switch.py 2>&1 | tail -4 ;;
   gatherparts)
     for v in 0 1; do echo "PPH_GATHER=$v"; PPH_GATHER=$v timeout 200 python scripts/gather_parts.py 2>&1 | tail -5; done ;;
   bulktests)  # the sparse-backward tests with the bulk-copy gather selected
