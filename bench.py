@@ -405,6 +405,8 @@ def main():
     ap.add_argument("--nbuf", type=int, default=16, help="distinct input batches the step rotates over")
     ap.add_argument("--e2e-load", default="selected", choices=["selected", "full"],
                     help="end-to-end leg: transfer only the token rows the head consumes (default) or the whole batch")
+    ap.add_argument("--no-overlap-graph", action="store_true",
+                    help="end-to-end leg: separate transfer / step graphs tied by events instead of one graph per iteration")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="headline numbers only (no roofline / next rows / drop-in legs)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "peer_nomc", "nccl"],
@@ -547,7 +549,24 @@ def main():
         step.run(last_slot)           # slots 0 / 1 were overwritten by the captures' warm-up transfers: harmless
         torch.cuda.synchronize()
 
+    # host pipeline with two slots: one graph per iteration = the step of this slot || the transfer of the next batch into the
+    # other slot (one host call per step, no cross-stream events)
+    overlapped = host_pipe and not args.no_overlap_graph
+    if overlapped:
+        pair_graphs = {(s, j): step.capture_host_overlapped(s, host[j]["tokens"], host[j]["scores"], host[j]["labels"])
+                       for s in range(2) for j in range(nbuf) if (j % 2 != s or nbuf % 2)}
+
+    def e2e_loop_overlapped(n):
+        b0 = host[0]
+        step.load_host(0, b0["tokens"], b0["scores"], b0["labels"])          # the first batch; every later one rides in a graph
+        for i in range(n):
+            pair_graphs[(i % 2, (i + 1) % nbuf)].replay()
+        torch.cuda.synchronize()
+        return float(step.loss_host[(n - 1) % 2][0].item())
+
     def e2e_loop(n):
+        if overlapped:
+            return e2e_loop_overlapped(n)
         cur = torch.cuda.current_stream()
         for i in range(n):
             s = i % 2

@@ -202,6 +202,32 @@ class GraphedHeadStep:
                 self.graphs_host.append(g)
         return self
 
+    def capture_host_overlapped(self, slot: int, next_tokens, next_scores, next_labels, n_ctas: int = 48):
+        """ONE graph for a whole end-to-end iteration: the step of `slot` (as run_host) on the capture's main branch and, on a
+        forked branch, the selection-first transfer of the NEXT batch (pinned host tensors) into the other slot.  A caller that
+        cycles through a ring of pinned staging buffers replays one of these per step -- one host call, no cross-stream
+        events -- and alternates slots 0 and 1.  Needs capture_host_pipeline()."""
+        assert len(self.tokens) >= 2 and slot in (0, 1) and hasattr(self, "graphs_host"), "slots 0 / 1, capture_host_pipeline() first"
+        other = 1 - slot
+        if not hasattr(self, "_xfer_stream"):
+            self._xfer_stream = torch.cuda.Stream()
+            self._xfer_ev = [torch.cuda.Event(), torch.cuda.Event()]
+        self.load_host(other, next_tokens, next_scores, next_labels, n_ctas)      # warm-up outside the capture
+        torch.cuda.synchronize()
+        extra = dict(idx32=self._load_idx[slot], loss_mirror=self.loss_host[slot].data_ptr())
+        g = torch.cuda.CUDAGraph()
+        ctx = torch.enable_grad() if self.train else torch.no_grad()
+        with ctx, torch.cuda.graph(g, capture_error_mode="thread_local"):
+            main = torch.cuda.current_stream()
+            self._xfer_ev[0].record(main)
+            self._xfer_stream.wait_event(self._xfer_ev[0])
+            with torch.cuda.stream(self._xfer_stream):
+                self.load_host(other, next_tokens, next_scores, next_labels, n_ctas)
+                self._xfer_ev[1].record(self._xfer_stream)
+            self._step_fused(slot, **extra)
+            main.wait_event(self._xfer_ev[1])
+        return g
+
     def run_host(self, slot: int = 0):
         self.graphs_host[slot].replay()
         return self.loss_host[slot]

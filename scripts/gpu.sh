@@ -91,6 +91,10 @@ case $stage in
   probe2)
     timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29514 \
         scripts/peer_probe.py > gpurun_out/probe2.log 2>&1; echo "== probe2 rc=$?"; grep -v "^W\|^\*\|OMP" gpurun_out/probe2.log | tail -30 ;;
+  peer8)      # N = 8, peer exchange only (gpurun --gpus 8)
+    timeout 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29551 \
+        bench.py --gpus 8 --steps 1000 --warmup 50 --no-extras > gpurun_out/bench_n8.json 2> gpurun_out/bench_n8.err
+    echo "== peer8 rc=$?"; tail -c 1500 gpurun_out/bench_n8.json; tail -3 gpurun_out/bench_n8.err ;;
   driver2)    # exactly what the driver runs at N = 2: both arms, default extras, its launch line
     t0=$(date +%s)
     timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 \
