@@ -239,3 +239,42 @@ def test_bench_arms_build_identical_config_objects():
     assert not train and shape.D == 384 and mode == "fp32"
     assert bench.parse_workload("cars_b64_bf16", None)[2] == "bf16"
     assert bench.step_flops(shape, False) < bench.step_flops(shape, True)
+
+
+def test_round2_entry_points_validate_arguments_before_touching_the_device():
+    """Every entry point added in round 2 checks its arguments first (negative PPH_E* codes), so the error behaviour of the
+    boundary can be held without a GPU; support queries and workspace sizes are pure host functions."""
+    import ctypes
+    from protopformer_b200 import _lib
+    lib = _lib.load()
+    n = ctypes.c_longlong(0)
+    # support queries / sizes (CUB shape and shapes outside the kernels' range)
+    assert lib.pph_addon_tc2_supported(64, 196, 192, 192, 81) == 15            # fwd | dgrad | wgrad | fused selection
+    assert lib.pph_addon_tc2_supported(256, 196, 384, 384, 81) & 1 == 0        # Din = 384: k range not resident
+    assert lib.pph_addon_tc2_supported(64, 400, 192, 192, 81) & 8 == 0         # N > 256: selection stays a separate launch
+    assert lib.pph_addon_tc2_supported(0, 196, 192, 192, 81) == 0
+    assert lib.pph_head_prep_supported(64, 196, 192, 192, 81) == 1
+    assert lib.pph_similarity_bwd2_supported(64, 81, 192, 2000, 2000) == 1 and lib.pph_similarity_bwd2_supported(64, 196, 192, 1000, 1000) == 1
+    for fn, dims in (("pph_head_mid_ws_bytes", (64, 81, 192, 2000, 2000, 200, 10)), ("pph_addon_tc2_ws_bytes", (64, 196, 192, 192, 81)),
+                     ("pph_similarity_bwd2_ws_bytes", (64, 81, 192, 2000)), ("pph_addon_bwd2_ws_bytes", (64, 196, 192, 192, 81))):
+        assert getattr(lib, fn)(*dims, ctypes.byref(n)) == 0 and n.value > 0, fn
+        assert getattr(lib, fn)(*dims, None) == -1, fn
+    assert lib.pph_peer_flag_bytes(ctypes.byref(n)) == 0 and n.value % 16 == 0 and n.value > 0
+    assert lib.pph_peer_flag_bytes(None) == -1
+    # argument errors
+    tbl = (ctypes.c_ulonglong * 2)(0x1000, 0x2000)
+    assert lib.pph_peer_allreduce(None, 0, 1024, 0, 2, 0, 64, 8, 0, None) == -1                 # no buffer table
+    assert lib.pph_peer_allreduce(ctypes.cast(tbl, ctypes.c_void_p), 0, 1024, 2, 2, 0, 64, 8, 0, None) == -1    # rank out of range
+    assert lib.pph_peer_allreduce(ctypes.cast(tbl, ctypes.c_void_p), 0, 1024, 0, 2, 2, 64, 8, 0, None) == -1    # lo not a multiple of 4
+    assert lib.pph_peer_allreduce(ctypes.cast(tbl, ctypes.c_void_p), 0, 100, 0, 2, 0, 64, 8, 0, None) == -1     # flag block inside the data
+    assert lib.pph_peer_allreduce(ctypes.cast(tbl, ctypes.c_void_p), 0, 1024, 0, 2, 0, 64, 65, 0, None) == -1   # too many CTAs
+    assert lib.pph_peer_allreduce(ctypes.cast(tbl, ctypes.c_void_p), 0, 1024, 0, 1, 0, 64, 8, 0, None) == 0     # world 1: nothing to do
+    assert lib.pph_gather_rows_host(None, None, 1, 196, 192, 81, None, 8, None) == -1
+    assert lib.pph_ppc_dense_fwd(None, None, None, 1, 20, 9, 5, 16, 1.0, 2.0, None, None, None, None, None) == -1
+    assert lib.pph_ppc_dense_bwd(None, None, None, None, None, None, 1, 20, 9, 5, 16, 2.0, None, None) == -1
+    assert lib.pph_select_addon_fwd(None, 1, None, None, None, 1, 196, 192, 192, 81, None, None, None, None, None, 0.5,
+                                    None, None, None, None, None, None, None, None, None, None) == -1
+    assert lib.pph_head_mid(*([None] * 8), 1, 81, 192, 2000, 2000, 200, 10, 196, 0.5, 0, 1e-4, 1.0, 1, 1, *([None] * 5),
+                            1.0, 2.0, 0.1, 0.5, *([None] * 14)) == -1
+    assert lib.pph_set_option(b"no_such_option", 1) == -1 and lib.pph_set_option(b"pdl", 0) == 0
+    assert b"pph_" in lib.pph_last_error_string() or len(lib.pph_last_error_string()) > 0
