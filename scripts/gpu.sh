@@ -75,6 +75,9 @@ case $stage in
   rollout)
     timeout 300 python -m pytest tests/test_rollout_gpu.py -q -m gpu --tb=short 2>&1 | tail -2
     timeout 200 python scripts/rollout_bench.py 2>&1 | cut -c1-150 | tail -4 ;;
+  pdlbench)
+    for v in 0 1; do echo "PPH_PDL=$v"; PPH_PDL=$v timeout 200 python bench.py --no-extras --no-cpu --steps 2000 --warmup 100 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('value %.0f (%.1f us) e2e %.0f'%(d['value'],1e3*d['ms_per_step'],d['e2e']['value']))"; done
+    echo "bf16"; timeout 200 python bench.py --mode bf16 --no-extras --no-cpu 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('value %.0f (%.1f us) e2e %.0f'%(d['value'],1e3*d['ms_per_step'],d['e2e']['value']))" ;;
   execswitch)
     timeout 300 python scripts/exec_switch.py 2>&1 | tail -4 ;;
   gatherparts)
