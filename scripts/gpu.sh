@@ -78,6 +78,8 @@ case $stage in
   pdlbench)
     for v in 0 1; do echo "PPH_PDL=$v"; PPH_PDL=$v timeout 200 python bench.py --no-extras --no-cpu --steps 2000 --warmup 100 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('value %.0f (%.1f us) e2e %.0f'%(d['value'],1e3*d['ms_per_step'],d['e2e']['value']))"; done
     echo "bf16"; timeout 200 python bench.py --mode bf16 --no-extras --no-cpu 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('value %.0f (%.1f us) e2e %.0f'%(d['value'],1e3*d['ms_per_step'],d['e2e']['value']))" ;;
+  dogscheck)
+    timeout 300 python bench.py --workload dogs_b256_eval --steps 200 --warmup 10 --no-extras 2> gpurun_out/dogs.err | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('value %.0f (%.1f us) e2e %.0f'%(d['value'],1e3*d['ms_per_step'],d['e2e']['value']), d['oracle_check'], d['cpu_baseline'] and d['cpu_baseline']['value'])"; tail -2 gpurun_out/dogs.err ;;
   execswitch)
     timeout 300 python scripts/exec_switch.py 2>&1 | tail -4 ;;
   gatherparts)
