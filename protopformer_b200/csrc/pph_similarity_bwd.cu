@@ -207,6 +207,10 @@ constexpr int kClsTB = 8, kClsThreads = 256, kClsSlices = 16;
 // Tried, measured, reverted: 32 slices of 64 rows with the final sum dealt to all threads (66 us), the dealt final sum alone
 // (44.5 us), 2 images x 64 rows x 32 slices (38.9 us, more re-read rows) -- every restructuring of this body so far made the
 // launch slower; a separate tensor-core product for dZc (a dense B x Pg x D GEMM) is the open item.
+// Also tried: every slice CTA of an image group waits for the others and sums its share of the outputs (32 slices) -- the pair
+// token + CLS drops to 23.1 us, but the waiting CTAs hold SM slots and the whole launch goes 32.1 -> 34.3 us; and the launch split
+// into a high-priority token + CLS branch and a low-priority prototype branch under the add-on backward: the step's span moves by
+// 136-139 vs 140 us, within run-to-run noise, because the add-on backward slows down by what the gather gains.
 
 __device__ __forceinline__ void
 cls_grad_body(int slice, int bgroup, int nslices, const float* __restrict__ g_g, const float* __restrict__ Zc,
