@@ -12,8 +12,12 @@ parameters (protopformer_b200/synth.py).  Prints ONE JSON line (rank 0).
 
   value        device-resident throughput: inputs already in HBM, CUDA-graph replays, CUDA events, max over ranks.
                The step rotates over NBUF distinct input batches whose total size exceeds L2 (config.l2).
-  e2e          same metric through the public API with HOST (pinned) inputs: H2D copy of every step's batch and a
-               D2H read of the loss inside the timed region, double-buffered on a copy stream.
+  e2e          same metric through the public API with HOST (pinned) inputs, every step inside the timed region: the
+               selection-first transfer of the step's batch (scores + labels by copy, then exactly the token rows the head
+               consumes read from the mapped host batch by pph_gather_rows_host -- e2e.h2d_bytes_per_step) into the other
+               of two slots while the current step runs (one CUDA graph per iteration), and the result (total, ce, ppc_cov,
+               ppc_mean) stored to pinned host memory by the kernel that completes the loss (e2e.d2h_bytes_per_step = 16).
+               Asserted bit-identical to the device-resident result of the same batch.  --e2e-load full copies whole batches.
   roofline     the kernel with the largest share of the step, timed alone with CUDA events on its launch stream,
                plus roofline.step = the whole step's algorithmic flops against the sustained bf16 peak.
   forward_only the eval path (no PPC / CE / backward) on the same inputs; dropin_module_path = PPNet.forward +
