@@ -141,8 +141,22 @@ def _gloo_worker(rank, world, port, q):
     loss = (P.sum() * x.sum()) + (W * (rank + 1)).sum()
     loss.backward()
     assert P.grad.data_ptr() == red.views[0].data_ptr()       # autograd accumulated in place into the flat buffer
-    red.allreduce()
-    q.put((rank, lo, hi, P.grad.tolist(), W.grad.tolist()))     # plain lists: no fd passing that can outlive the worker
+    # segment-wise exchange (what the in-graph hooks issue: prototypes first, add-on parameters later)
+    seg_ok = red.segment(("P",)) == (0, 24) and red.segment(("W",)) == (24, 27) and red.segment(("P", "W")) == (0, 27)
+    before = red.flat.clone()
+    red.allreduce(lo=0, hi=24)
+    seg_ok = seg_ok and torch.equal(red.flat[24:], before[24:])     # the other segment is untouched until its own call
+    red.allreduce(lo=24, hi=27)
+    gP, gW = P.grad.tolist(), W.grad.tolist()
+    P.grad = None                                                   # a detached gradient is reported, not averaged silently
+    try:
+        red.allreduce()
+        detached_reported = False
+    except RuntimeError:
+        detached_reported = True
+    red.zero()                                                      # re-attaches the views
+    red.check_attached()
+    q.put((rank, lo, hi, gP, gW, seg_ok and detached_reported))     # plain lists: no fd passing that can outlive the worker
     dist.destroy_process_group()
 
 
@@ -161,7 +175,8 @@ def test_flat_gradient_allreduce_gloo_world2():
     for p in procs:
         p.join(timeout=120)
         assert p.exitcode == 0
-    (_, lo0, hi0, gP0, gW0), (_, lo1, hi1, gP1, gW1) = res
+    (_, lo0, hi0, gP0, gW0, ok0), (_, lo1, hi1, gP1, gW1, ok1) = res
+    assert ok0 and ok1
     gP0, gW0, gP1, gW1 = (torch.tensor(t) for t in (gP0, gW0, gP1, gW1))
     assert (lo0, hi0, lo1, hi1) == (0, 5, 5, 10)
     assert torch.allclose(gP0, gP1) and torch.allclose(gW0, gW1)
