@@ -80,6 +80,10 @@ case $stage in
     echo "bf16"; timeout 200 python bench.py --mode bf16 --no-extras --no-cpu 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('value %.0f (%.1f us) e2e %.0f'%(d['value'],1e3*d['ms_per_step'],d['e2e']['value']))" ;;
   dogscheck)
     timeout 300 python bench.py --workload dogs_b256_eval --steps 200 --warmup 10 --no-extras 2> gpurun_out/dogs.err | python -c "import sys,json; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('value %.0f (%.1f us) e2e %.0f'%(d['value'],1e3*d['ms_per_step'],d['e2e']['value']), d['oracle_check'], d['cpu_baseline'] and d['cpu_baseline']['value'])"; tail -2 gpurun_out/dogs.err ;;
+  racecheck)  # shared-memory hazard check of the fused selection + add-on forward kernel and the dense PPC kernels (small shapes)
+    timeout 170 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_step2_gpu.py tests/test_module_gpu.py -q --tb=line -m gpu \
+        -k "(fused_selection and cub_b8-1-0) or (dense and small)" > gpurun_out/racecheck.log 2>&1
+    echo "== racecheck rc=$?"; grep -E "RACECHECK SUMMARY|hazard|passed|failed|Error" gpurun_out/racecheck.log | head -8 ;;
   execswitch)
     timeout 300 python scripts/exec_switch.py 2>&1 | tail -4 ;;
   gatherparts)
