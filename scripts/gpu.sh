@@ -84,6 +84,10 @@ case $stage in
     timeout 170 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_step2_gpu.py tests/test_module_gpu.py -q --tb=line -m gpu \
         -k "(fused_selection and cub_b8-1-0) or (dense and small)" > gpurun_out/racecheck.log 2>&1
     echo "== racecheck rc=$?"; grep -E "RACECHECK SUMMARY|hazard|passed|failed|Error" gpurun_out/racecheck.log | head -8 ;;
+  racecheck2) # the whole default step (cub_b8 fixture) under racecheck: grid-barrier kernels, tcshot epilogues, sparse backward
+    timeout 150 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_step2_gpu.py -q --tb=line -m gpu \
+        -k "step_variants and variants1" > gpurun_out/racecheck2.log 2>&1
+    echo "== racecheck2 rc=$?"; grep -E "RACECHECK SUMMARY|hazard|passed|failed|Error" gpurun_out/racecheck2.log | head -8 ;;
   execswitch)
     timeout 300 python scripts/exec_switch.py 2>&1 | tail -4 ;;
   gatherparts)
